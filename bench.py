@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the geometric guidance path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--dist room|rand]
+  python bench.py --impl reference ...     # the reference path on the host CPU cores
+
+A "step" is one pass of the fused path over one batch of synthetic RGB-D panoramas
+(config c2 = 512x1024, batch 8, one source frame, one target pose -- BASELINE.json configs[1]).
+Weak scaling: every rank (one process per GPU) runs the full config on its own batch; no
+data-path collective.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    'c1': dict(n=1, s=1, p=1, h=256, sweep=False),   # lowres, batch 1 (the reference's CPU-runnable case)
+    'c2': dict(n=8, s=1, p=1, h=512, sweep=False),   # highres, batch 8  <- the metric's config
+    'c3': dict(n=32, s=4, p=1, h=512, sweep=False),  # trajectory accumulation
+    'c4': dict(n=1, s=1, p=64, h=512, sweep=True),   # VLN perturbation sweep
+    'c5': dict(n=64, s=8, p=1, h=2048, sweep=False), # stress
+}
+L2_BYTES = 126 << 20
+
+
+def alg_bytes(c):
+  """7 B per unique source point + 20 B per target pixel."""
+  hw = c['h'] * 2 * c['h']
+  return c['n'] * c['s'] * hw * 7, c['n'] * c['p'] * hw * 20
+
+
+def measured_peak_gbs():
+  try:
+    with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+      return float(json.load(f)['hbm_gbs']), 'measured'
+  except Exception:  # pylint: disable=broad-except
+    return 6650.0, 'fallback'
+
+
+def committed_traffic():
+  """Per-launch DRAM bytes of the dominant kernel from the committed ncu summary, if any."""
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+      return json.load(f)
+  except Exception:  # pylint: disable=broad-except
+    return None
+
+
+class ClockSampler(threading.Thread):
+  """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+    self._stop_evt = threading.Event()
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception:  # pylint: disable=broad-except
+      self.nv = None
+
+  def run(self):
+    if self.nv is None:
+      return
+    nv = self.nv
+    names = {
+        'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8)),
+        'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40)),
+        'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20)),
+        'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)),
+    }
+    get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+    while not self._stop_evt.is_set():
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = get_reasons(self.h)
+        for k, bit in names.items():
+          if r & bit:
+            self.reasons.add(k)
+      except Exception:  # pylint: disable=broad-except
+        pass
+      time.sleep(0.002)
+
+  def stop(self):
+    self._stop_evt.set()
+    self.join(timeout=2)
+    return {'sm_mhz': statistics.median(self.samples) if self.samples else None, 'sm_max_mhz': self.max_mhz,
+            'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/): the restated reference path on host cores
+# ------------------------------------------------------------------------------------------
+def _cpu_one_batch(args):
+  """One reference-style call on `n` panoramas: literal numpy restatement (TF absent)."""
+  from oracle import ref_numpy as R
+  inp, which = args
+  t0 = time.perf_counter()
+  if which == 'numpy':
+    R.reproject_trajectory(inp['rgb'], inp['depth'], inp['src_pos'], inp['tgt_pos'][:, 0], mask_first_frame=True)
+  else:
+    from oracle import ref_exact as X
+    X.reproject(inp['rgb'], inp['depth'], inp['src_pos'], inp['tgt_pos'], mask_first_frame=True)
+  return time.perf_counter() - t0
+
+
+def cpu_baseline_single(cfg, dist, budget_s=12.0):
+  """cpu_baseline of our arm: 1 host core, a bounded sample of the same workload."""
+  from se3ds_b200 import synth
+  c = dict(cfg)
+  inp = synth.make_inputs(1, c['s'], c['p'], c['h'], seed=100, dist=dist, sweep=c['sweep'])
+  times = {}
+  for which in ('numpy', 'c'):
+    _cpu_one_batch((inp, which))  # warm-up (also builds / loads the C oracle)
+    ts, t_start = [], time.perf_counter()
+    while len(ts) < 3 or (time.perf_counter() - t_start < budget_s / 2 and len(ts) < 40):
+      ts.append(_cpu_one_batch((inp, which)))
+    times[which] = statistics.median(ts)
+  best = min(times, key=times.get)
+  panos = c['p']  # one item, P target panoramas
+  return {'value': panos / times[best], 'unit': 'panos/s', 'cores': 1, 'kind': 'port',
+          'sample': (f"1 item of the workload ({c['s']} frame(s), {c['p']} pose(s), {c['h']}x{2 * c['h']}) per call, "
+                     f"median of repeated calls; numpy restatement {times['numpy'] * 1e3:.1f} ms, "
+                     f"scalar C restatement {times['c'] * 1e3:.1f} ms per call; fastest ({best}) reported; "
+                     'TensorFlow is not installed, so this is the restated reference path'),
+          'mpoints_per_s': c['s'] * c['p'] * c['h'] * 2 * c['h'] / times[best] / 1e6}
+
+
+def run_reference_arm(args, cfg):
+  """--impl reference: the restated reference path on all host cores (process pool, one item per task)."""
+  import multiprocessing as mp
+  from se3ds_b200 import synth
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
+  workers = max(1, min(cores, 64))
+  c = dict(cfg)
+  inp = synth.make_inputs(1, c['s'], c['p'], c['h'], seed=100, dist=args.dist, sweep=c['sweep'])
+  # one step = `workers` items (a bounded sample of the config's batch), one per worker
+  steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+  which = 'c'
+  with mp.get_context('fork').Pool(workers) as pool:
+    for _ in range(warmup):
+      pool.map(_cpu_one_batch, [(inp, which)] * workers)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+      pool.map(_cpu_one_batch, [(inp, which)] * workers)
+    dt = time.perf_counter() - t0
+  panos = workers * c['p'] * steps
+  value = panos / dt
+  line = {
+      'impl': 'reference', 'metric': 'reprojected panoramas/s', 'value': value, 'unit': 'panos/s', 'n_gpus': args.gpus,
+      'steps': steps, 'warmup': warmup, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': workload_name(args.config, c, args.dist), 'sample_items_per_step': workers},
+      'cpu_baseline': {'value': value, 'unit': 'panos/s', 'cores': workers, 'kind': 'port',
+                       'sample': f'{workers} items per step (one per worker process), scalar C restatement of the '
+                                 'reference path (TensorFlow not installed)'},
+      'e2e': {'value': value, 'unit': 'panos/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'mpoints_per_s': value * c['s'] * c['h'] * 2 * c['h'] / 1e6,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def workload_name(name, c, dist):
+  return (f"{name}: N{c['n']} S{c['s']} P{c['p']} {c['h']}x{2 * c['h']} equirect RGB-D (u8 RGB + f32 depth), "
+          f"depth={dist}, mask frame 0, void -1/-1")
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=1000)
+  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+  ap.add_argument('--dist', default='room', choices=['room', 'rand'])
+  ap.add_argument('--no-graph', action='store_true', help='plain stream launches instead of CUDA-graph replay')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--e2e-steps', type=int, default=20)
+  args = ap.parse_args()
+  cfg = CONFIGS[args.config]
+  if args.impl == 'reference':
+    run_reference_arm(args, cfg)
+    return
+  args.warmup = max(args.warmup, 3)
+
+  import torch
+  import torch.distributed as dist
+  from se3ds_b200 import _lib, guidance, synth
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+
+  n, s, p, h = cfg['n'], cfg['s'], cfg['p'], cfg['h']
+  w = 2 * h
+  src_bytes, out_bytes = alg_bytes(cfg)
+  # ring of distinct input/output sets larger than 2x L2, so every step starts cold in L2
+  set_bytes = src_bytes + out_bytes
+  ring = max(2, min(16, -(-2 * L2_BYTES // set_bytes) + 1))
+  ws = _lib.Workspace(local_rank)
+  plans = []
+  for r in range(ring):
+    # every set differs only in its seed; large configs reuse one generated item per set
+    gen_n = min(n, 8)
+    inp = synth.make_inputs(gen_n, s, p, h, seed=1000 * rank + r, dist=args.dist, sweep=cfg['sweep'])
+    if gen_n < n:
+      inp = {k: np.concatenate([v] * (n // gen_n), axis=0) for k, v in inp.items()}
+    t = {k: torch.as_tensor(v).to(dev) for k, v in inp.items()}
+    plans.append(guidance.prepare(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, workspace=ws))
+  host_inp = {k: torch.as_tensor(v).pin_memory() for k, v in inp.items()}
+
+  stream = torch.cuda.Stream(dev)
+  with torch.cuda.stream(stream):
+    for pl in plans:  # grows the workspace, uploads tables
+      pl.run()
+    stream.synchronize()
+    graphs = None
+    if not args.no_graph:
+      graphs = []
+      for pl in plans:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+          pl.run()
+        graphs.append(g)
+    launches0 = ws.profile_read()[1]
+
+    def step(i):
+      if graphs is not None:
+        graphs[i % ring].replay()
+      else:
+        plans[i % ring].run()
+
+    def barrier():
+      stream.synchronize()
+      if world > 1:
+        dist.barrier()
+      torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+      step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+      step(i)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches_timed = ws.profile_read()[1] - launches0 if graphs is None else None
+
+    # per-kernel durations (cudaEvents between the launches, plain stream launches)
+    ws.profile(True)
+    prof_steps = min(args.steps, 200)
+    for i in range(prof_steps):
+      plans[i % ring].run()
+    kms, _ = ws.profile_read()
+    ws.profile(False)
+    kms = [x / prof_steps for x in kms]
+
+  t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_total = float(t.item())
+  ms_step = ms_total / args.steps
+  panos_per_s = world * n * p / (ms_step * 1e-3)
+  mpoints = world * n * s * p * h * w / (ms_step * 1e-3) / 1e6
+
+  # e2e: host buffers, H2D + kernels + D2H inside the C-ABI call (se3ds_reproject_host)
+  e2e_out = {}
+  for _ in range(3):
+    guidance.reproject_host(host_inp['rgb'], host_inp['depth'], host_inp['src_pos'], host_inp['tgt_pos'],
+                            mask_frames=1, out=e2e_out, device=local_rank, workspace=ws)
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  for _ in range(args.e2e_steps):
+    guidance.reproject_host(host_inp['rgb'], host_inp['depth'], host_inp['src_pos'], host_inp['tgt_pos'],
+                            mask_frames=1, out=e2e_out, device=local_rank, workspace=ws)
+  torch.cuda.synchronize()
+  e2e_ms = (time.perf_counter() - t0) / args.e2e_steps * 1e3
+  t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_ms = float(t.item())
+  h2d = sum(host_inp[k].numel() * host_inp[k].element_size() for k in host_inp)
+  d2h = sum(v.numel() * v.element_size() for v in e2e_out.values())
+
+  if rank == 0:
+    peak, peak_kind = measured_peak_gbs()
+    names = ['splat_depth_kernel', 'splat_feat_kernel', 'resolve_kernel']
+    kalg = [src_bytes, 0, out_bytes]
+    dom = max(range(3), key=lambda i: kms[i])
+    traffic = committed_traffic()
+    step_gbs = (src_bytes + out_bytes) / (sum(kms) * 1e-3) / 1e9
+    line = {
+        'metric': 'reprojected panoramas/s', 'value': panos_per_s, 'unit': 'panos/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.config, cfg, args.dist), 'per_gpu_batch': n,
+                   'cache': f'inputs+outputs rotate over a ring of {ring} sets ({ring * set_bytes >> 20} MiB > 2x L2)',
+                   'launch': 'cuda_graph_replay' if graphs is not None else 'stream', 'parallelism': f'dp{world}'},
+        'mpoints_per_s': mpoints,
+        'e2e': {'value': world * n * p / (e2e_ms * 1e-3), 'unit': 'panos/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms},
+        'gpu_launches': (3 * args.steps if launches_timed is None else launches_timed),
+        'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'kernel': names[dom], 'achieved': kalg[dom] / (kms[dom] * 1e-3) / 1e9, 'peak': peak,
+                     'unit': 'GB/s', 'frac': kalg[dom] / (kms[dom] * 1e-3) / 1e9 / peak, 'peak_kind': peak_kind,
+                     'traffic': (traffic or {}).get(names[dom]), 'ms': kms[dom]},
+        'roofline_step': {'bound': 'hbm', 'achieved': step_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': step_gbs / peak,
+                          'alg_bytes': src_bytes + out_bytes, 'ms_kernels': sum(kms),
+                          'frac_of_timed_step': (src_bytes + out_bytes) / (ms_step * 1e-3) / 1e9 / peak},
+        'kernels': [{'name': names[i], 'ms': kms[i], 'alg_bytes': kalg[i]} for i in range(3)],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+      line['cpu_baseline'] = cpu_baseline_single(cfg, args.dist)
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

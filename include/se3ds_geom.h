@@ -1,0 +1,143 @@
+/* se3ds_geom.h -- C ABI of the B200-native geometric guidance path of SE3DS.
+ *
+ * The reference (google-research/se3ds) has no FFI: the path sits behind plain
+ * Python functions.  Each entry point below names the reference function(s) it
+ * replaces (file:line relative to the reference checkout).  The Python shims in
+ * se3ds_b200/utils/*.py keep the reference signatures and call these through
+ * ctypes with raw device pointers; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns an se3ds_status (0 = ok); no C++ exceptions cross
+ *     the boundary; se3ds_last_error() gives a thread-local message.
+ *   - all tensor pointers are DEVICE pointers unless the name ends in _host;
+ *     tensors are dense, row-major, in the layouts of the reference.
+ *   - the caller owns every input and output buffer; the library owns only the
+ *     opaque workspace (z-buffer, feature buffer, per-point scratch, bins,
+ *     angle tables).  A workspace is bound to one device and may be used by one
+ *     stream at a time; distinct workspaces are independent (re-entrant).
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued
+ *     asynchronously on it unless stated otherwise.
+ *   - inputs must be finite; NaN/Inf depth or coordinates are rejected points.
+ */
+#ifndef SE3DS_GEOM_H_
+#define SE3DS_GEOM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE3DS_GEOM_VERSION 100 /* major*100 + minor */
+
+typedef struct se3ds_ws se3ds_ws;
+
+typedef enum {
+  SE3DS_OK = 0,
+  SE3DS_ERR_BAD_SHAPE = 1, /* reference raises ValueError / AssertionError on these */
+  SE3DS_ERR_BAD_DTYPE = 2, /* e.g. unsigned features with a negative void class   */
+  SE3DS_ERR_BAD_ARG = 3,
+  SE3DS_ERR_CUDA = 4,
+  SE3DS_ERR_NOMEM = 5
+} se3ds_status;
+
+typedef enum { SE3DS_U8 = 0, SE3DS_I32 = 1, SE3DS_F32 = 2 } se3ds_dtype;
+
+/* se3ds_reproject flags */
+#define SE3DS_FLAG_FILTER_VOID 1u /* drop points whose channels all equal unproject_void:
+                                     the compaction of models/models.py:229-237 (batch 1) */
+#define SE3DS_FLAG_BIN_PER_JOB 2u /* every (item, pose) job behaves like its own reference call
+                                     (batch 1): rejected points land on ITS pixel (0,0).  Default:
+                                     the whole call is one reference call; the global reject bin
+                                     (utils/point_cloud_utils.py:150-153) is job 0's pixel (0,0). */
+
+int se3ds_version(void);
+const char* se3ds_status_string(int status);
+const char* se3ds_last_error(void);
+
+/* Workspace.  max_bytes bounds the device memory the workspace may hold (0 = default 2 GiB);
+ * larger calls are processed in job chunks.  l2_chunk_bytes is the preferred size of one chunk's
+ * working set (0 = default, tuned for the 126 MB L2). */
+int se3ds_ws_create(int device, size_t max_bytes, size_t l2_chunk_bytes, se3ds_ws** out);
+int se3ds_ws_destroy(se3ds_ws* ws);
+int se3ds_ws_bytes(const se3ds_ws* ws, size_t* bytes);
+
+/* Measurement hooks (bench.py): with profiling enabled se3ds_reproject brackets its three kernel
+ * classes with cudaEvents on the caller's stream.  se3ds_ws_profile_read synchronises, returns the
+ * accumulated device milliseconds of {splat_depth, splat_feat, resolve} since the last read and the
+ * number of kernels this workspace has launched so far (counted always, profiling or not). */
+int se3ds_ws_profile(se3ds_ws* ws, int enable);
+int se3ds_ws_profile_read(se3ds_ws* ws, float ms[3], unsigned long long* launches);
+
+/* utils/pano_utils.py:245-265  mask_pano(pano, proportion, masked_region_value).
+ * pano/out (N,H,W,C) of `dtype`; rows r < int(H*p) or r > H - int(H*p) become the value. */
+int se3ds_mask_pano(const void* pano, int dtype, int n, int h, int w, int c, double proportion,
+                    double masked_region_value, void* out, void* stream);
+
+/* utils/pano_utils.py:164-242  equirectangular_to_pointcloud (size_mult == 1).
+ * feats (N,H,W,C) in_dtype, depth (N,H,W) f32 -> xyz1 (N,4,H*W) f32 planar, feats_out (N,H*W,C)
+ * out_dtype ('nearest' keeps the dtype, 'bilinear' -> f32).  Requires w == 2*h. */
+int se3ds_unproject_equirect(se3ds_ws* ws, const void* feats, int in_dtype, const float* depth, int n,
+                             int h, int w, int c, double void_class, float depth_scale,
+                             float* xyz1_out, void* feats_out, int out_dtype, void* stream);
+
+/* utils/pano_utils.py:117-161 project_feats_to_equirectangular (mode 0: coords are cartesian) and
+ * utils/point_cloud_utils.py:90-183 project_to_feat (mode 1: coords are "transformed_coords").
+ * coords (N,4,M) f32, feats (N,M,C) feat_dtype (cast to f32 like the reference) ->
+ * depth_out (N,H,W) f32 in [0,1], feats_out (N,H,W,C) f32, winner_out (N,H,W) int32 or NULL
+ * (index m of the nearest point, lowest index on ties, -1 = none).  M may be 0. */
+int se3ds_project_cloud(se3ds_ws* ws, const float* coords, const void* feats, int feat_dtype, int n,
+                        long long m, int c, int h, int w, int mode, float input_void_class,
+                        float output_void_class, float depth_scale, float* depth_out,
+                        float* feats_out, int32_t* winner_out, void* stream);
+
+/* The fused path: replaces, for S source frames and P target poses per batch item,
+ *   mask_pano (pano_utils.py:245-265, first `mask_frames` frames) ->
+ *   equirectangular_to_pointcloud (pano_utils.py:164-242) -> xyz1 += src_pos ->
+ *   [compaction, models.py:229-237] -> concat over frames -> coords - tgt_pos
+ *   (models.py:225-226,273-275; gan_manager.py:474-475,549) ->
+ *   project_feats_to_equirectangular (pano_utils.py:117-161 + point_cloud_utils.py:90-183) ->
+ *   guidance assembly (models.py:282-293; gan_manager.py:484-494)
+ * without materialising the cloud.
+ *   rgb (N,S,H,W,3) rgb_dtype (U8, or I32 with values in [-1,255]); depth (N,S,H,W) f32;
+ *   src_pos (N,S,3) f32; tgt_pos (N,P,3) f32 (device).  Jobs are (n,p) row-major, J = N*P.
+ *   proj_image (J,H,W,3) f32 = clip(rgb/255,0,1); proj_depth (J,H,W,1) f32; proj_mask (J,H,W,1)
+ *   f32 in {0,1}; winner_out (J,H,W) int32 or NULL: index s*H*W + r*W + c of the nearest valid
+ *   point of that pixel (lowest index on ties), -1 = none.
+ *   unproject_void: feature given to depth-invalid pixels; project_void: feature value that
+ *   makes a point invalid (any channel).  SE3DSModel: -1/-1 + FILTER_VOID; gan_manager: 0/-1;
+ *   eval_metric: -1/-1. */
+int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
+                    const float* src_pos, const float* tgt_pos, int n, int s, int p, int h, int w,
+                    float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
+                    int project_void, unsigned flags, float* proj_image, float* proj_depth,
+                    float* proj_mask, int32_t* winner_out, float* bin_out, void* stream);
+
+/* Multi-GPU support for the global reject bin.  When se3ds_reproject is given bin_out (device,
+ * 4 floats) the call's reject bin is NOT applied to job 0's pixel (0,0) but exported as
+ * (min depth or +inf, max R, max G, max B); ranks reduce their bins (min / max) and the owner of
+ * global job 0 applies the result with se3ds_apply_bin.  clip() and the divisions are monotone,
+ * so patching the finished outputs is bit-identical to the single-call result. */
+int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, float* proj_depth,
+                    float* proj_mask, void* stream);
+
+/* Same as se3ds_reproject with HOST buffers (pinned memory recommended): copies the inputs to the
+ * device, runs the fused path and copies the guidance tensors back, pipelined over batch items on
+ * the workspace's own streams.  Blocks until the outputs are complete. */
+int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, const float* depth_host,
+                         const float* src_pos_host, const float* tgt_pos_host, int n, int s, int p,
+                         int h, int w, float depth_scale, double mask_proportion, int mask_frames,
+                         int unproject_void, int project_void, unsigned flags,
+                         float* proj_image_host, float* proj_depth_host, float* proj_mask_host,
+                         int32_t* winner_out_host);
+
+/* inference/perturbation_utils.py:23-71 get_proportion_invalid_for_depth, batched over P offsets.
+ * offsets (P,3) f32 device, depth (H,W) f32 device -> out (P,) f32 device. */
+int se3ds_proportion_invalid(const float* offsets, int p, const float* depth, int h, int w,
+                             float distance_padding, float depth_scale, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE3DS_GEOM_H_ */

@@ -160,12 +160,13 @@ static int32_t pixel_of(float px, float py, float pz, int H, int W, int feat_val
  *   zbuf_out  (N,H,W)  raw scatter-min result             winner_out (N,H,W) int32
  *   flat_out  (N,M)    global flat index before tolerance (0 = rejected, as the reference)
  *   kept_out  (N,M)    global flat index after tolerance  rad_out (N,M) per point depth
+ *   valid_out (N,M)    1 if the point passed the validity tests of :137-149
  * winner = lowest point index m among the valid points of the pixel whose depth equals
  * the pixel minimum and is <= depth_scale; -1 if none. */
 void se3ds_oracle_splat(const float* coords, const float* feats, int N, long long M, int C, int H,
                         int W, int mode, float void_in, float void_out, float depth_scale,
                         float* depth_out, float* feat_out, float* zbuf_out, int32_t* winner_out,
-                        int32_t* flat_out, int32_t* kept_out, float* rad_out) {
+                        int32_t* flat_out, int32_t* kept_out, float* rad_out, uint8_t* valid_out) {
   size_t HW = (size_t)H * W, P = (size_t)N * HW, K = (size_t)N * (size_t)M;
   float* zbuf = (float*)malloc(sizeof(float) * P);
   float* fbuf = (float*)malloc(sizeof(float) * P * (size_t)C);
@@ -216,6 +217,7 @@ void se3ds_oracle_splat(const float* coords, const float* feats, int N, long lon
   if (zbuf_out) memcpy(zbuf_out, zbuf, sizeof(float) * P);
   if (flat_out) memcpy(flat_out, flat, sizeof(int32_t) * K);
   if (rad_out) memcpy(rad_out, rad, sizeof(float) * K);
+  if (valid_out) memcpy(valid_out, isvalid, K);
   free(zbuf); free(fbuf); free(flat); free(rad); free(isvalid);
 }
 

@@ -93,12 +93,13 @@ def splat(coords, feats, height, width, depth_scale, void_in, void_out=0.0, mode
   c = feats.shape[-1]
   out = dict(depth=np.empty((n, height, width), F32), feat=np.empty((n, height, width, c), F32),
              zbuf=np.empty((n, height, width), F32), winner=np.empty((n, height, width), np.int32),
-             flat=np.empty((n, m), np.int32), kept=np.empty((n, m), np.int32), rad=np.empty((n, m), F32))
+             flat=np.empty((n, m), np.int32), kept=np.empty((n, m), np.int32), rad=np.empty((n, m), F32),
+             valid=np.empty((n, m), np.uint8))
   lib().se3ds_oracle_splat(_p(coords), _p(feats), ctypes.c_int(n), ctypes.c_longlong(m), ctypes.c_int(c),
                            ctypes.c_int(height), ctypes.c_int(width), ctypes.c_int(mode),
                            ctypes.c_float(void_in), ctypes.c_float(void_out), ctypes.c_float(depth_scale),
                            _p(out['depth']), _p(out['feat']), _p(out['zbuf']), _p(out['winner']),
-                           _p(out['flat']), _p(out['kept']), _p(out['rad']))
+                           _p(out['flat']), _p(out['kept']), _p(out['rad']), _p(out['valid']))
   if scalar:
     out['feat'] = out['feat'][..., 0]
   return out
@@ -154,4 +155,29 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale=ref_numpy.DEPTH_SCALE,
     o = splat(rel, featj, h, w, depth_scale, project_void)
   image, d, mask = ref_numpy.guidance_from_projection(o['depth'], o['feat'])
   return dict(image=image, depth=d, mask=mask, winner=o['winner'], raw_rgb=o['feat'], zbuf=o['zbuf'],
-              flat=o['flat'], kept=o['kept'], rad=o['rad'])
+              flat=o['flat'], kept=o['kept'], rad=o['rad'], valid=o['valid'], feats_in=featj)
+
+
+def get_proportion_invalid_for_depth(position_offset, depth_image, distance_padding: float = 0.10):
+  """Canonical twin of ref_numpy.get_proportion_invalid_for_depth (canonical atan2, IEEE sqrt)."""
+  import math
+  po = np.asarray(position_offset, F32)
+  depth_image = np.asarray(depth_image, F32)
+  distance = np.sqrt(F32(F32(po[0] * po[0]) + F32(po[1] * po[1])) + F32(po[2] * po[2]))
+  height, width = depth_image.shape
+  heading = atan2f(np.array([-po[0]], F32), np.array([-po[1]], F32))[0]
+  if heading < 0:
+    heading = F32(heading + F32(2 * math.pi))
+  heading_proportion = F32(heading / F32(2 * math.pi))
+  delta_xy = F32(math.sqrt(float(F32(po[1] * po[1]) + F32(po[0] * po[0]))))
+  elevation = atan2f(np.array([delta_xy], F32), np.array([-po[2]], F32))[0]
+  if elevation < 0:
+    elevation = F32(elevation + F32(math.pi))
+  elevation_proportion = F32(elevation / F32(math.pi))
+  heading_start = int(F32(heading_proportion * F32(width)))
+  elevation_start = int(F32(elevation_proportion * F32(height)))
+  tw = int(30 / 360 * width)
+  th = int(60 / 180 * height)
+  region = depth_image[max(0, elevation_start - th):min(height, elevation_start + th),
+                       max(0, heading_start - tw):min(width, heading_start + tw)]
+  return float(F32(np.mean(region * F32(ref_numpy.DEPTH_SCALE) < F32(distance + F32(distance_padding)))))

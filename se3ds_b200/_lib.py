@@ -1,0 +1,174 @@
+"""ctypes binding of libse3ds_geom.so (include/se3ds_geom.h).
+
+torch is used only for device memory and streams: every call below passes raw
+device pointers (`tensor.data_ptr()`) and the current CUDA stream handle to the
+C ABI.  There is no CPU fallback: if the library cannot be loaded or no CUDA
+device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Dict, Optional
+
+import torch
+
+from . import build as _build
+
+OK, ERR_BAD_SHAPE, ERR_BAD_DTYPE, ERR_BAD_ARG, ERR_CUDA, ERR_NOMEM = range(6)
+U8, I32, F32 = 0, 1, 2
+FLAG_FILTER_VOID = 1
+FLAG_BIN_PER_JOB = 2
+
+_DTYPES = {torch.uint8: U8, torch.int32: I32, torch.float32: F32}
+
+_lib = None
+_lock = threading.Lock()
+
+_c = ctypes
+_vp, _i, _ll, _f, _d, _u, _sz = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float, _c.c_double, _c.c_uint, _c.c_size_t
+
+# name -> argtypes; must list every symbol include/se3ds_geom.h declares
+SIGNATURES = {
+    'se3ds_version': [],
+    'se3ds_status_string': [_i],
+    'se3ds_last_error': [],
+    'se3ds_ws_create': [_i, _sz, _sz, _c.POINTER(_vp)],
+    'se3ds_ws_destroy': [_vp],
+    'se3ds_ws_bytes': [_vp, _c.POINTER(_sz)],
+    'se3ds_ws_profile': [_vp, _i],
+    'se3ds_ws_profile_read': [_vp, _c.POINTER(_f * 3), _c.POINTER(_c.c_ulonglong)],
+    'se3ds_mask_pano': [_vp, _i, _i, _i, _i, _i, _d, _d, _vp, _vp],
+    'se3ds_unproject_equirect': [_vp, _vp, _i, _vp, _i, _i, _i, _i, _d, _f, _vp, _vp, _i, _vp],
+    'se3ds_project_cloud': [_vp, _vp, _vp, _i, _i, _ll, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp],
+    'se3ds_reproject': [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp, _vp,
+                        _vp, _vp, _vp],
+    'se3ds_apply_bin': [_vp, _f, _vp, _vp, _vp, _vp],
+    'se3ds_reproject_host': [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp,
+                             _vp, _vp],
+    'se3ds_proportion_invalid': [_vp, _i, _vp, _i, _i, _f, _f, _vp, _vp],
+}
+
+
+def library_path() -> str:
+  return _build.OUT
+
+
+def load():
+  """Loads (building first if the .so is missing and nvcc is available) the C-ABI library."""
+  global _lib
+  with _lock:
+    if _lib is not None:
+      return _lib
+    path = library_path()
+    if not os.path.exists(path):
+      try:
+        _build.build()
+      except Exception as e:  # pylint: disable=broad-except
+        raise RuntimeError(
+            f'{path} is missing and could not be built ({e}); run `python -m se3ds_b200.build`. '
+            'There is no CPU fallback for the geometric guidance path.') from e
+    lib = ctypes.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+      fn = getattr(lib, name)
+      fn.argtypes = argtypes
+      fn.restype = ctypes.c_char_p if name in ('se3ds_status_string', 'se3ds_last_error') else ctypes.c_int
+    _lib = lib
+    return lib
+
+
+class Se3dsError(RuntimeError):
+  pass
+
+
+def check(status: int):
+  if status == OK:
+    return
+  lib = load()
+  msg = (lib.se3ds_last_error() or b'').decode() or lib.se3ds_status_string(status).decode()
+  if status in (ERR_BAD_SHAPE, ERR_BAD_DTYPE, ERR_BAD_ARG):
+    raise ValueError(msg)
+  if status == ERR_NOMEM:
+    raise torch.cuda.OutOfMemoryError(msg)
+  raise Se3dsError(msg)
+
+
+def dtype_code(t: torch.Tensor) -> int:
+  try:
+    return _DTYPES[t.dtype]
+  except KeyError as e:
+    raise ValueError(f'unsupported tensor dtype {t.dtype}') from e
+
+
+def require_cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+  if not isinstance(t, torch.Tensor):
+    raise TypeError(f'{name} must be a torch.Tensor, got {type(t)}')
+  if not t.is_cuda:
+    if not torch.cuda.is_available():
+      raise Se3dsError('no CUDA device: the geometric guidance path has no CPU fallback')
+    t = t.cuda()
+  return t.contiguous()
+
+
+def ptr(t: Optional[torch.Tensor]):
+  return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_handle(device) -> ctypes.c_void_p:
+  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Workspace:
+  """Opaque se3ds_ws handle: z-buffer, feature buffer, scratch, bins, angle tables."""
+
+  def __init__(self, device: int = 0, max_bytes: int = 0, l2_chunk_bytes: int = 0):
+    self._h = ctypes.c_void_p()
+    self.device = device
+    check(load().se3ds_ws_create(device, max_bytes, l2_chunk_bytes, ctypes.byref(self._h)))
+
+  @property
+  def handle(self):
+    if not self._h:
+      raise Se3dsError('workspace was destroyed')
+    return self._h
+
+  def nbytes(self) -> int:
+    out = ctypes.c_size_t()
+    check(load().se3ds_ws_bytes(self.handle, ctypes.byref(out)))
+    return out.value
+
+  def profile(self, enable: bool):
+    check(load().se3ds_ws_profile(self.handle, int(enable)))
+
+  def profile_read(self):
+    """-> ((ms_splat_depth, ms_splat_feat, ms_resolve) since the last read, kernels launched so far)."""
+    ms = (ctypes.c_float * 3)()
+    n = ctypes.c_ulonglong()
+    check(load().se3ds_ws_profile_read(self.handle, ctypes.byref(ms), ctypes.byref(n)))
+    return tuple(ms), n.value
+
+  def close(self):
+    if self._h:
+      load().se3ds_ws_destroy(self._h)
+      self._h = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+
+_default_ws: Dict[int, Workspace] = {}
+
+
+def default_workspace(device) -> Workspace:
+  idx = torch.device(device).index
+  if idx is None:
+    idx = torch.cuda.current_device()
+  ws = _default_ws.get(idx)
+  if ws is None:
+    chunk = int(os.environ.get('SE3DS_L2_CHUNK_MB', '0')) << 20
+    ws = _default_ws[idx] = Workspace(idx, 0, chunk)
+  return ws

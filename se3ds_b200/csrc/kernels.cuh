@@ -1,0 +1,616 @@
+// kernels.cuh -- sm_100a kernels of the geometric guidance path.
+//
+// Fused path (se3ds_reproject), three launches per job chunk, no point cloud in memory:
+//   K2 splat_depth_kernel : RGB-D planes -> unproject -> +src -tgt -> project -> 64-bit
+//                           (depth bits | point index) REDG.MIN into the z-buffer; the per point
+//                           (pixel, depth) goes to an L2-resident scratch for K3.
+//   K3 splat_feat_kernel  : tolerance test d < dmin + 0.1 against the final z-buffer; surviving
+//                           non-winner points REDG.MAX.F16x4 their RGB into the feature buffer
+//                           (one 8-byte vector reduction = the reference's per-channel scatter-max);
+//                           rejected points are warp-reduced into the reject bin.
+//   K4 resolve_kernel     : per target pixel: gather the winner's RGB, merge with the feature
+//                           buffer and the bin, write proj_image / proj_depth / proj_mask / winner
+//                           once, re-arm z-buffer and feature buffer for the next chunk.
+// Compat path (se3ds_unproject_equirect / se3ds_project_cloud) works on materialised clouds with
+// float32 features of any channel count.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "canon_math.cuh"
+
+namespace se3ds {
+
+constexpr int kThreads = 256;
+constexpr unsigned long long kZArmed = 0xFFFFFFFFFFFFFFFFull;
+
+// scratch word: pixel index in bits 0..27, flags above
+constexpr uint32_t kScPixMask = 0x0FFFFFFFu;
+constexpr uint32_t kScInvalid = 1u << 28;   // rejected before the tolerance test (no pixel)
+constexpr uint32_t kScDepthInv = 1u << 29;  // depth-invalid source pixel: feature = unproject_void
+constexpr uint32_t kScDropped = 1u << 30;   // removed by the compaction (FILTER_VOID)
+
+// Reject bin of one reference call (all-zero = armed): zneg = ~ordered(min depth), f = max feature.
+struct Bin {
+  uint32_t zneg;
+  int f[3];
+};
+
+struct FusedParams {
+  const void* rgb;
+  const float* depth;
+  const float* src_pos;
+  const float* tgt_pos;
+  const float* tab;  // sin_e[H], cos_e[H], sin_h[W], cos_h[W]
+  unsigned long long* zbuf;
+  uint2* fbuf;
+  uint32_t* sc_flat;
+  float* sc_rad;
+  Bin* bins;  // J bins (per call: only bins[0] is used)
+  float* out_image;
+  float* out_depth;
+  float* out_mask;
+  int* out_winner;
+  int N, S, P, H, W, HW;
+  int n0, p0, PC;  // chunk: items n0.., poses p0..p0+PC-1; blockIdx.z = (n-n0)*PC + (p-p0)
+  int mh;          // int(H * mask_proportion)
+  int mask_frames;
+  int uv, pv;
+  unsigned flags;
+  float depth_scale;
+  int finalize_bins;  // 1: the bin of an owner pixel is complete when K4 runs
+  float* bin_out;     // export mode: no owner pixel, the bin is handed to the caller
+};
+
+__device__ __forceinline__ bool row_masked(const FusedParams& q, int s, int row) {
+  return s < q.mask_frames && (row < q.mh || row > q.H - q.mh);
+}
+
+__device__ __forceinline__ int3 load_rgb1(const uint8_t* rgb, size_t pix) {
+  const uint8_t* p = rgb + pix * 3;
+  return make_int3(p[0], p[1], p[2]);
+}
+__device__ __forceinline__ int3 load_rgb1(const int* rgb, size_t pix) {
+  const int* p = rgb + pix * 3;
+  return make_int3(p[0], p[1], p[2]);
+}
+
+// 4 consecutive pixels, 16-byte aligned vector loads.
+__device__ __forceinline__ void load_rgb4(const uint8_t* rgb, size_t pix0, int3 (&o)[4]) {
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(rgb + pix0 * 3);
+  const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  o[0] = make_int3(a & 255, (a >> 8) & 255, (a >> 16) & 255);
+  o[1] = make_int3(a >> 24, b & 255, (b >> 8) & 255);
+  o[2] = make_int3((b >> 16) & 255, b >> 24, c & 255);
+  o[3] = make_int3((c >> 8) & 255, (c >> 16) & 255, c >> 24);
+}
+__device__ __forceinline__ void load_rgb4(const int* rgb, size_t pix0, int3 (&o)[4]) {
+  const int4* p = reinterpret_cast<const int4*>(rgb + pix0 * 3);
+  const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  o[0] = make_int3(a.x, a.y, a.z);
+  o[1] = make_int3(a.w, b.x, b.y);
+  o[2] = make_int3(b.z, b.w, c.x);
+  o[3] = make_int3(c.y, c.z, c.w);
+}
+
+// Feature of a source pixel as the reference sees it after mask_pano + unprojection
+// (pano_utils.py:225,262-265): depth-invalid -> unproject_void, masked row -> -1, else RGB.
+__device__ __forceinline__ int3 point_feat(const FusedParams& q, bool dinv, bool masked, int3 raw) {
+  if (dinv) return make_int3(q.uv, q.uv, q.uv);
+  if (masked) return make_int3(-1, -1, -1);
+  return raw;
+}
+
+__device__ __forceinline__ uint2 pack_f16x4(int3 f) {
+  const uint32_t r = __half_as_ushort(__int2half_rn(f.x));
+  const uint32_t g = __half_as_ushort(__int2half_rn(f.y));
+  const uint32_t b = __half_as_ushort(__int2half_rn(f.z));
+  return make_uint2(r | (g << 16), b);
+}
+__device__ __forceinline__ float3 unpack_f16x4(uint2 v) {
+  return make_float3(__half2float(__ushort_as_half((unsigned short)(v.x & 0xffff))),
+                     __half2float(__ushort_as_half((unsigned short)(v.x >> 16))),
+                     __half2float(__ushort_as_half((unsigned short)(v.y & 0xffff))));
+}
+__device__ __forceinline__ void red_max_f16x4(uint2* addr, uint2 v) {
+  asm volatile("red.global.max.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// Warp-aggregated update of the reject bin: one REDG per warp and only if it can change the bin
+// (bins only grow, so a stale read is a safe filter).
+__device__ __forceinline__ void bin_min_depth(Bin* bin, bool has, float rad) {
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  if (m == 0) return;
+  const uint32_t v = __reduce_max_sync(0xffffffffu, has ? ~f32_ordered(rad) : 0u);
+  if ((threadIdx.x & 31) == 0 && v > *reinterpret_cast<volatile uint32_t*>(&bin->zneg)) atomicMax(&bin->zneg, v);
+}
+__device__ __forceinline__ void bin_max_feat(Bin* bin, bool has, int3 f) {
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  if (m == 0) return;
+  const int r = __reduce_max_sync(0xffffffffu, has ? f.x : 0);
+  const int g = __reduce_max_sync(0xffffffffu, has ? f.y : 0);
+  const int b = __reduce_max_sync(0xffffffffu, has ? f.z : 0);
+  if ((threadIdx.x & 31) == 0) {
+    volatile int* cur = bin->f;
+    if (r > cur[0]) atomicMax(&bin->f[0], r);
+    if (g > cur[1]) atomicMax(&bin->f[1], g);
+    if (b > cur[2]) atomicMax(&bin->f[2], b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: fused unproject + translate + project + depth splat
+// ------------------------------------------------------------------------------------------
+template <typename RGB_T, bool VEC>
+__global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
+  const int lj = blockIdx.z;
+  const int n = q.n0 + lj / q.PC, p = q.p0 + lj % q.PC;
+  const int s = blockIdx.y;
+  const int job = n * q.P + p;
+  const int pix0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
+  const bool active = pix0 < q.HW;
+  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? job : 0);
+
+  const size_t frame = (size_t)(n * q.S + s) * q.HW;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  int3 raw[4] = {};
+  int cnt = 0;
+  if (active) {
+    cnt = min(4, q.HW - pix0);
+    if (VEC) {
+      const float4 dv = __ldg(reinterpret_cast<const float4*>(q.depth + frame + pix0));
+      d[0] = dv.x; d[1] = dv.y; d[2] = dv.z; d[3] = dv.w;
+      load_rgb4(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
+    } else {
+      for (int k = 0; k < 4; ++k)
+        if (k < cnt) {
+          d[k] = q.depth[frame + pix0 + k];
+          raw[k] = load_rgb1(static_cast<const RGB_T*>(q.rgb), frame + pix0 + k);
+        }
+    }
+  }
+  const float* sp = q.src_pos + (size_t)(n * q.S + s) * 3;
+  const float* tp = q.tgt_pos + (size_t)job * 3;
+  const float sx = sp[0], sy = sp[1], sz = sp[2];
+  const float tx = tp[0], ty = tp[1], tz = tp[2];
+  const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
+  unsigned long long* zb = q.zbuf + (size_t)lj * q.HW;
+  const size_t sc0 = ((size_t)lj * q.S + s) * q.HW + pix0;
+
+  uint32_t scf[4];
+  float scr[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool on = k < cnt;
+    const int pix = pix0 + k;
+    const int row = on ? pix / q.W : 0, col = on ? pix - row * q.W : 0;
+    // pano_utils.py:220-236
+    const bool dvalid = d[k] > 0.0f && d[k] < 1.0f;
+    const float rad0 = __fmul_rn(__fmul_rn(d[k], q.depth_scale), dvalid ? 1.0f : 0.0f);
+    const float t = __fmul_rn(rad0, sin_e[row]);
+    const float x = __fmul_rn(t, cos_h[col]);
+    const float y = __fmul_rn(t, sin_h[col]);
+    const float z = __fmul_rn(rad0, cos_e[row]);
+    // models.py:225-226 then :273-275 -- two roundings
+    const float X = __fsub_rn(__fadd_rn(x, sx), tx);
+    const float Y = __fsub_rn(__fadd_rn(y, sy), ty);
+    const float Z = __fsub_rn(__fadd_rn(z, sz), tz);
+    const int3 f = point_feat(q, !dvalid, row_masked(q, s, row), raw[k]);
+    const bool dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
+    const bool fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
+    float px, py, rad;
+    pseudo_perspective(X, Y, Z, px, py, rad);
+    const int tpix = pixel_of(px, py, rad, q.H, q.W);
+    const bool live = on && !dropped;
+    const bool valid = live && fvalid && tpix >= 0;
+    const uint32_t dflag = dvalid ? 0u : kScDepthInv;
+    if (valid) {
+      const uint32_t idx = (uint32_t)(s * q.HW + pix);
+      const unsigned long long key =
+          ((unsigned long long)__float_as_uint(rad) << 32) | (idx << 1) | (dvalid ? 0u : 1u);
+      atomicMin(zb + tpix, key);
+    }
+    bin_min_depth(bin, live && !valid, rad);
+    scf[k] = !live ? kScDropped : (valid ? (uint32_t)tpix | dflag : kScInvalid | dflag);
+    scr[k] = rad;
+  }
+  if (active) {
+    if (VEC) {
+      *reinterpret_cast<uint4*>(q.sc_flat + sc0) = make_uint4(scf[0], scf[1], scf[2], scf[3]);
+      *reinterpret_cast<float4*>(q.sc_rad + sc0) = make_float4(scr[0], scr[1], scr[2], scr[3]);
+    } else {
+      for (int k = 0; k < cnt; ++k) { q.sc_flat[sc0 + k] = scf[k]; q.sc_rad[sc0 + k] = scr[k]; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: tolerance test + per-channel max of the surviving features
+// ------------------------------------------------------------------------------------------
+template <typename RGB_T, bool VEC>
+__global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams q) {
+  const int lj = blockIdx.z;
+  const int n = q.n0 + lj / q.PC, p = q.p0 + lj % q.PC;
+  const int s = blockIdx.y;
+  const int job = n * q.P + p;
+  const int pix0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
+  const bool active = pix0 < q.HW;
+  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? job : 0);
+  const size_t frame = (size_t)(n * q.S + s) * q.HW;
+  const size_t sc0 = ((size_t)lj * q.S + s) * q.HW + pix0;
+  uint32_t scf[4] = {kScDropped, kScDropped, kScDropped, kScDropped};
+  float scr[4] = {0.f, 0.f, 0.f, 0.f};
+  int3 raw[4] = {};
+  if (active) {
+    const int cnt = min(4, q.HW - pix0);
+    if (VEC) {
+      const uint4 a = *reinterpret_cast<const uint4*>(q.sc_flat + sc0);
+      const float4 b = *reinterpret_cast<const float4*>(q.sc_rad + sc0);
+      scf[0] = a.x; scf[1] = a.y; scf[2] = a.z; scf[3] = a.w;
+      scr[0] = b.x; scr[1] = b.y; scr[2] = b.z; scr[3] = b.w;
+      load_rgb4(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
+    } else {
+      for (int k = 0; k < cnt; ++k) {
+        scf[k] = q.sc_flat[sc0 + k];
+        scr[k] = q.sc_rad[sc0 + k];
+        raw[k] = load_rgb1(static_cast<const RGB_T*>(q.rgb), frame + pix0 + k);
+      }
+    }
+  }
+  const unsigned long long* zb = q.zbuf + (size_t)lj * q.HW;
+  uint2* fb = q.fbuf + (size_t)lj * q.HW;
+  // issue the four z-buffer gathers first, then consume
+  unsigned long long key[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool haspix = !(scf[k] & (kScDropped | kScInvalid));
+    key[k] = haspix ? zb[scf[k] & kScPixMask] : kZArmed;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool live = !(scf[k] & kScDropped);
+    const bool haspix = live && !(scf[k] & kScInvalid);
+    const int pix = pix0 + k;
+    const int row = pix / q.W;
+    const int3 f = point_feat(q, scf[k] & kScDepthInv, row_masked(q, s, row), raw[k]);
+    bool rejected = live && !haspix;
+    if (haspix) {
+      // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
+      const float zmin = fminf(__uint_as_float((uint32_t)(key[k] >> 32)), q.depth_scale);
+      const bool keep = scr[k] < __fadd_rn(zmin, 0.1f);
+      const bool winner = ((uint32_t)key[k] >> 1) == (uint32_t)(s * q.HW + pix);
+      if (keep && !winner) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
+      rejected = !keep;
+    }
+    bin_max_feat(bin, rejected, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: gather-resolve -> guidance tensors
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clip01_div255(float v) {
+  // models.py:290-291: clip_by_value(rgb / 255, 0, 1)
+  return fminf(fmaxf(__fdiv_rn(v, 255.0f), 0.0f), 1.0f);
+}
+
+template <typename RGB_T>
+__global__ void __launch_bounds__(kThreads) resolve_kernel(const FusedParams q) {
+  const int lj = blockIdx.y;
+  const int n = q.n0 + lj / q.PC, p = q.p0 + lj % q.PC;
+  const int job = n * q.P + p;
+  const int pix0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
+  if (pix0 >= q.HW) return;
+  const bool vec = (q.HW & 3) == 0;
+  const int cnt = min(4, q.HW - pix0);
+  unsigned long long* zb = q.zbuf + (size_t)lj * q.HW + pix0;
+  uint2* fb = q.fbuf + (size_t)lj * q.HW + pix0;
+  unsigned long long key[4];
+  uint2 fv[4];
+  if (vec) {
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(zb), b = *reinterpret_cast<const ulonglong2*>(zb + 2);
+    key[0] = a.x; key[1] = a.y; key[2] = b.x; key[3] = b.y;
+    const uint4 c = *reinterpret_cast<const uint4*>(fb), e = *reinterpret_cast<const uint4*>(fb + 2);
+    fv[0] = make_uint2(c.x, c.y); fv[1] = make_uint2(c.z, c.w);
+    fv[2] = make_uint2(e.x, e.y); fv[3] = make_uint2(e.z, e.w);
+  } else {
+    for (int k = 0; k < 4; ++k) {
+      key[k] = k < cnt ? zb[k] : kZArmed;
+      fv[k] = k < cnt ? fb[k] : make_uint2(0, 0);
+    }
+  }
+  // winner gathers (independent loads, issued together)
+  int3 wraw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    wraw[k] = make_int3(0, 0, 0);
+    if (key[k] != kZArmed && !((uint32_t)key[k] & 1u)) {
+      const uint32_t widx = (uint32_t)key[k] >> 1;
+      wraw[k] = load_rgb1(static_cast<const RGB_T*>(q.rgb), (size_t)n * q.S * q.HW + widx);
+    }
+  }
+  const bool per_job = q.flags & SE3DS_FLAG_BIN_PER_JOB;
+  float od[4], om[4], oi[12];
+  int ow[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool has = key[k] != kZArmed;
+    const float radw = __uint_as_float((uint32_t)(key[k] >> 32));
+    float zmin = has ? fminf(radw, q.depth_scale) : q.depth_scale;
+    float3 f = unpack_f16x4(fv[k]);
+    const bool owner = (pix0 + k == 0) && (per_job || job == 0) && q.bin_out == nullptr;
+    if (has) {
+      const uint32_t widx = (uint32_t)key[k] >> 1;
+      const int ws = widx / q.HW, wrow = (widx - ws * q.HW) / q.W;
+      const int3 wf = point_feat(q, (uint32_t)key[k] & 1u, row_masked(q, ws, wrow), wraw[k]);
+      // the winner survives the tolerance test unless min+0.1 rounds back to min; on the owner
+      // pixel a rejected winner lands on the same pixel through the bin anyway.
+      if (radw < __fadd_rn(zmin, 0.1f) || owner) {
+        f.x = fmaxf(f.x, (float)wf.x); f.y = fmaxf(f.y, (float)wf.y); f.z = fmaxf(f.z, (float)wf.z);
+      }
+    }
+    ow[k] = (has && radw <= q.depth_scale) ? (int)((uint32_t)key[k] >> 1) : -1;
+    if (owner) {
+      Bin* bin = q.bins + (per_job ? job : 0);
+      if (q.finalize_bins) {
+        if (bin->zneg) zmin = fminf(zmin, f32_unordered(~bin->zneg));
+        f.x = fmaxf(f.x, (float)bin->f[0]); f.y = fmaxf(f.y, (float)bin->f[1]); f.z = fmaxf(f.z, (float)bin->f[2]);
+        *bin = Bin{0u, {0, 0, 0}};  // re-arm
+      } else {
+        // more chunks will still add to the global bin: park this pixel's own values in it,
+        // patch_owner_kernel finishes the pixel after the last chunk.
+        atomicMax(&bin->zneg, ~f32_ordered(zmin));
+        atomicMax(&bin->f[0], (int)f.x); atomicMax(&bin->f[1], (int)f.y); atomicMax(&bin->f[2], (int)f.z);
+      }
+    }
+    // point_cloud_utils.py:160-162, models.py:282-293
+    const float depth = __fdiv_rn(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale);
+    od[k] = depth;
+    oi[3 * k + 0] = clip01_div255(f.x); oi[3 * k + 1] = clip01_div255(f.y); oi[3 * k + 2] = clip01_div255(f.z);
+    om[k] = (depth > 0.0f && depth < 1.0f && f.x != -1.0f && f.y != -1.0f && f.z != -1.0f) ? 1.0f : 0.0f;
+  }
+  const size_t o = (size_t)job * q.HW + pix0;
+  if (vec) {
+    *reinterpret_cast<float4*>(q.out_depth + o) = make_float4(od[0], od[1], od[2], od[3]);
+    *reinterpret_cast<float4*>(q.out_mask + o) = make_float4(om[0], om[1], om[2], om[3]);
+    float4* im = reinterpret_cast<float4*>(q.out_image + o * 3);
+    im[0] = make_float4(oi[0], oi[1], oi[2], oi[3]);
+    im[1] = make_float4(oi[4], oi[5], oi[6], oi[7]);
+    im[2] = make_float4(oi[8], oi[9], oi[10], oi[11]);
+    if (q.out_winner) *reinterpret_cast<int4*>(q.out_winner + o) = make_int4(ow[0], ow[1], ow[2], ow[3]);
+    const ulonglong2 arm = make_ulonglong2(kZArmed, kZArmed);
+    *reinterpret_cast<ulonglong2*>(zb) = arm; *reinterpret_cast<ulonglong2*>(zb + 2) = arm;
+    *reinterpret_cast<uint4*>(fb) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(fb + 2) = make_uint4(0, 0, 0, 0);
+  } else {
+    for (int k = 0; k < cnt; ++k) {
+      q.out_depth[o + k] = od[k]; q.out_mask[o + k] = om[k];
+      for (int c = 0; c < 3; ++c) q.out_image[(o + k) * 3 + c] = oi[3 * k + c];
+      if (q.out_winner) q.out_winner[o + k] = ow[k];
+      zb[k] = kZArmed; fb[k] = make_uint2(0, 0);
+    }
+  }
+}
+
+// After the last chunk of a multi-chunk call with the global bin: finish job 0's pixel (0,0).
+__global__ void patch_owner_kernel(const FusedParams q) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Bin* bin = q.bins;
+  const float zmin = bin->zneg ? f32_unordered(~bin->zneg) : q.depth_scale;
+  const float3 f = make_float3((float)bin->f[0], (float)bin->f[1], (float)bin->f[2]);
+  *bin = Bin{0u, {0, 0, 0}};
+  const float depth = __fdiv_rn(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale);
+  q.out_depth[0] = depth;
+  q.out_image[0] = clip01_div255(f.x); q.out_image[1] = clip01_div255(f.y); q.out_image[2] = clip01_div255(f.z);
+  q.out_mask[0] = (depth > 0.0f && depth < 1.0f && f.x != -1.0f && f.y != -1.0f && f.z != -1.0f) ? 1.0f : 0.0f;
+}
+
+// Export mode (multi-GPU): hand the call's bin to the caller as (min depth | +inf, max R, G, B).
+__global__ void export_bin_kernel(const FusedParams q) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Bin* bin = q.bins;
+  q.bin_out[0] = bin->zneg ? f32_unordered(~bin->zneg) : __int_as_float(0x7f800000);
+  q.bin_out[1] = (float)bin->f[0]; q.bin_out[2] = (float)bin->f[1]; q.bin_out[3] = (float)bin->f[2];
+  *bin = Bin{0u, {0, 0, 0}};
+}
+
+// Applies a (reduced) bin to pixel (0,0) of the first job of finished guidance tensors.
+__global__ void apply_bin_kernel(const float* bin, float depth_scale, float* image, float* depth, float* mask) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float d = fminf(depth[0], __fdiv_rn(fminf(fmaxf(bin[0], 0.0f), depth_scale), depth_scale));
+  depth[0] = d;
+  float f[3];
+  for (int c = 0; c < 3; ++c) { f[c] = fmaxf(image[c], clip01_div255(bin[1 + c])); image[c] = f[c]; }
+  mask[0] = (d > 0.0f && d < 1.0f) ? 1.0f : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// Compat path kernels (materialised clouds, float32 features, any channel count)
+// ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T cast_void(double v) { return (T)v; }
+
+// utils/pano_utils.py:245-265
+template <typename T>
+__global__ void mask_pano_kernel(const T* __restrict__ in, T* __restrict__ out, long long total, int H,
+                                 long long row_elems, int mh, T value) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)((i / row_elems) % H);
+    out[i] = (row >= mh && row <= H - mh) ? in[i] : value;
+  }
+}
+
+// utils/pano_utils.py:164-242: xyz1 (N,4,HW) planar + filtered features
+template <typename TI, typename TO>
+__global__ void unproject_kernel(const TI* __restrict__ feats, const float* __restrict__ depth,
+                                 const float* __restrict__ tab, int N, int H, int W, int C,
+                                 float depth_scale, TO void_value, float* __restrict__ xyz1,
+                                 TO* __restrict__ feats_out) {
+  const int HW = H * W;
+  const long long total = (long long)N * HW;
+  const float *sin_e = tab, *cos_e = tab + H, *sin_h = tab + 2 * H, *cos_h = sin_h + W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW), pix = (int)(i - (long long)b * HW);
+    const int row = pix / W, col = pix - row * W;
+    const float d = depth[i];
+    const bool dvalid = d > 0.0f && d < 1.0f;
+    const float rad0 = __fmul_rn(__fmul_rn(d, depth_scale), dvalid ? 1.0f : 0.0f);
+    const float t = __fmul_rn(rad0, sin_e[row]);
+    float* o = xyz1 + (size_t)b * 4 * HW + pix;
+    o[0] = __fmul_rn(t, cos_h[col]);
+    o[HW] = __fmul_rn(t, sin_h[col]);
+    o[2 * (size_t)HW] = __fmul_rn(rad0, cos_e[row]);
+    o[3 * (size_t)HW] = 1.0f;
+    for (int c = 0; c < C; ++c) feats_out[i * C + c] = dvalid ? (TO)feats[i * C + c] : void_value;
+  }
+}
+
+struct CloudParams {
+  const float* coords;  // (N,4,M)
+  const void* feats;    // (N,M,C)
+  unsigned long long* zbuf;
+  uint32_t* sc_flat;
+  float* sc_rad;
+  uint32_t* bin;  // [0] = ~ordered(min depth), [1+c] = ordered(max feature c); all-zero = armed
+  float* depth_out;
+  float* feats_out;  // (N,H,W,C), pre-filled with output_void_class; accumulated in place
+  int* winner_out;
+  long long M;
+  int N, C, H, W, HW, mode;
+  float void_in, void_out, depth_scale;
+};
+
+__device__ __forceinline__ float load_feat(const uint8_t* f, size_t i) { return (float)f[i]; }
+__device__ __forceinline__ float load_feat(const int* f, size_t i) { return (float)f[i]; }
+__device__ __forceinline__ float load_feat(const float* f, size_t i) { return f[i]; }
+
+// float max through integer atomics (works for mixed signs; -0.0 never replaces +0.0)
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) cloud_depth_kernel(const CloudParams q) {
+  const int b = blockIdx.y;
+  const long long m = blockIdx.x * (long long)kThreads + threadIdx.x;
+  const bool on = m < q.M;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  bool fvalid = true;
+  if (on) {
+    const float* cb = q.coords + (size_t)b * 4 * q.M;
+    const float x = cb[m], y = cb[q.M + m], z = cb[2 * q.M + m];
+    if (q.mode == 0) pseudo_perspective(x, y, z, px, py, pz);
+    else { px = x; py = y; pz = z; }
+    const size_t f0 = ((size_t)b * q.M + m) * q.C;
+    for (int c = 0; c < q.C; ++c) fvalid &= load_feat(static_cast<const T*>(q.feats), f0 + c) != q.void_in;
+  }
+  const int tpix = on ? pixel_of(px, py, pz, q.H, q.W) : -1;
+  const bool valid = on && fvalid && tpix >= 0;
+  if (valid) {
+    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | ((uint32_t)m << 1);
+    atomicMin(q.zbuf + (size_t)b * q.HW + tpix, key);
+  }
+  // reject bin: min depth of every rejected point (utils/point_cloud_utils.py:150-159)
+  const bool rej = on && !valid;
+  if (__ballot_sync(0xffffffffu, rej)) {
+    const uint32_t v = __reduce_max_sync(0xffffffffu, rej ? ~f32_ordered(pz) : 0u);
+    if ((threadIdx.x & 31) == 0 && v > *reinterpret_cast<volatile uint32_t*>(q.bin)) atomicMax(q.bin, v);
+  }
+  if (on) {
+    q.sc_flat[(size_t)b * q.M + m] = valid ? (uint32_t)tpix : kScInvalid;
+    q.sc_rad[(size_t)b * q.M + m] = pz;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) cloud_feat_kernel(const CloudParams q) {
+  const int b = blockIdx.y;
+  const long long m = blockIdx.x * (long long)kThreads + threadIdx.x;
+  if (m >= q.M) return;
+  const uint32_t fl = q.sc_flat[(size_t)b * q.M + m];
+  const float rad = q.sc_rad[(size_t)b * q.M + m];
+  bool keep = false;
+  if (!(fl & kScInvalid)) {
+    const unsigned long long key = q.zbuf[(size_t)b * q.HW + fl];
+    const float zmin = key == kZArmed ? q.depth_scale : fminf(__uint_as_float((uint32_t)(key >> 32)), q.depth_scale);
+    keep = rad < __fadd_rn(zmin, 0.1f);
+  }
+  const size_t f0 = ((size_t)b * q.M + m) * q.C;
+  if (keep) {
+    float* dst = q.feats_out + ((size_t)b * q.HW + fl) * q.C;
+    for (int c = 0; c < q.C; ++c) atomic_max_f32(dst + c, load_feat(static_cast<const T*>(q.feats), f0 + c));
+  } else {
+    for (int c = 0; c < q.C; ++c) {
+      const uint32_t v = f32_ordered(load_feat(static_cast<const T*>(q.feats), f0 + c));
+      if (v > *reinterpret_cast<volatile uint32_t*>(q.bin + 1 + c)) atomicMax(q.bin + 1 + c, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) cloud_resolve_kernel(const CloudParams q) {
+  const long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
+  const long long total = (long long)q.N * q.HW;
+  if (i >= total) return;
+  const unsigned long long key = q.zbuf[i];
+  const bool has = key != kZArmed;
+  const float radw = __uint_as_float((uint32_t)(key >> 32));
+  float zmin = has ? fminf(radw, q.depth_scale) : q.depth_scale;
+  if (i == 0) {
+    if (q.bin[0]) zmin = fminf(zmin, f32_unordered(~q.bin[0]));
+    for (int c = 0; c < q.C; ++c) {
+      if (q.bin[1 + c]) q.feats_out[c] = fmaxf(q.feats_out[c], f32_unordered(q.bin[1 + c]));
+      q.bin[1 + c] = 0u;
+    }
+    q.bin[0] = 0u;
+  }
+  q.depth_out[i] = __fdiv_rn(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale);
+  if (q.winner_out) q.winner_out[i] = (has && radw <= q.depth_scale) ? (int)((uint32_t)key >> 1) : -1;
+  q.zbuf[i] = kZArmed;
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// inference/perturbation_utils.py:23-71, one block per candidate offset
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) proportion_invalid_kernel(const float* __restrict__ offsets,
+                                                                     const float* __restrict__ depth, int H, int W,
+                                                                     float pad, float depth_scale,
+                                                                     float* __restrict__ out) {
+  const float ox = offsets[blockIdx.x * 3], oy = offsets[blockIdx.x * 3 + 1], oz = offsets[blockIdx.x * 3 + 2];
+  const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy)), __fmul_rn(oz, oz)));
+  float heading = canon_atan2f(-ox, -oy);
+  if (heading < 0.0f) heading = __fadd_rn(heading, CANON_TWO_PI);
+  const float hprop = __fdiv_rn(heading, CANON_TWO_PI);
+  // delta_xy: float32 squares and sum, float64 sqrt, back to float32 (perturbation_utils.py:46-47)
+  const float dxy = (float)sqrt((double)__fadd_rn(__fmul_rn(oy, oy), __fmul_rn(ox, ox)));
+  float elev = canon_atan2f(dxy, -oz);
+  if (elev < 0.0f) elev = __fadd_rn(elev, CANON_PI_HI);
+  const float eprop = __fdiv_rn(elev, CANON_PI_HI);
+  const int hs = (int)__fmul_rn(hprop, (float)W), es = (int)__fmul_rn(eprop, (float)H);
+  const int tw = (int)(30.0 / 360.0 * W), th = (int)(60.0 / 180.0 * H);
+  const int r0 = max(0, es - th), r1 = min(H, es + th), c0 = max(0, hs - tw), c1 = min(W, hs + tw);
+  const int rw = max(0, c1 - c0), rh = max(0, r1 - r0);
+  const float thr = __fadd_rn(dist, pad);
+  int cnt = 0;
+  for (int i = threadIdx.x; i < rw * rh; i += kThreads) {
+    const int r = r0 + i / rw, c = c0 + i % rw;
+    cnt += __fmul_rn(depth[(size_t)r * W + c], depth_scale) < thr;
+  }
+  __shared__ int sm[kThreads / 32];
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int i = 0; i < kThreads / 32; ++i) tot += sm[i];
+    // np.mean of a bool array: float64 count / size (nan for an empty window, like numpy)
+    out[blockIdx.x] = (float)((double)tot / (double)(rw * rh));
+  }
+}
+
+}  // namespace se3ds

@@ -1,0 +1,514 @@
+// se3ds_geom.cu -- C ABI (include/se3ds_geom.h) over the sm_100a kernels in kernels.cuh.
+// Host-side duties only: argument validation with the reference's error conditions, workspace
+// (z-buffer / feature buffer / scratch / bins / angle tables), job chunking, kernel launches.
+// There is no CPU fallback: without a CUDA device every entry point fails with SE3DS_ERR_CUDA.
+#include "se3ds_geom.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace se3ds;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(SE3DS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct TableEntry {
+  int h, w;
+  float* dev;
+};
+
+constexpr size_t kDefaultMaxBytes = (size_t)2 << 30;
+constexpr size_t kDefaultChunkBytes = (size_t)112 << 20;
+
+}  // namespace
+
+struct se3ds_ws {
+  int device = 0;
+  size_t max_bytes = kDefaultMaxBytes, chunk_bytes = kDefaultChunkBytes;
+  DevBuf zbuf, fbuf, scf, scr, bins, cbin;
+  std::vector<TableEntry> tables;
+  bool dirty = false;  // a pass was enqueued but its resolve (which re-arms) was not
+  // staging of the host-buffer entry point
+  DevBuf s_rgb, s_depth, s_src, s_tgt, s_img, s_dep, s_msk, s_win;
+  cudaStream_t hstream = nullptr;
+  // measurement hooks
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;  // groups of 4 events per profiled chunk
+  size_t ev_used = 0;
+  unsigned long long launches = 0;
+};
+
+namespace {
+
+size_t ws_total(const se3ds_ws* ws) {
+  size_t t = ws->zbuf.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->bins.cap + ws->cbin.cap +
+             ws->s_rgb.cap + ws->s_depth.cap + ws->s_src.cap + ws->s_tgt.cap + ws->s_img.cap +
+             ws->s_dep.cap + ws->s_msk.cap + ws->s_win.cap;
+  for (const auto& e : ws->tables) t += (size_t)(2 * e.h + 2 * e.w) * sizeof(float);
+  return t;
+}
+
+// Grow-only device buffer; armed buffers are (re)initialised with `pattern` on `stream`.
+int grow(DevBuf& b, size_t bytes, int pattern, cudaStream_t stream) {
+  if (bytes <= b.cap) return SE3DS_OK;
+  if (b.p) CU(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = (bytes + 255) & ~(size_t)255;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return fail(SE3DS_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  }
+  b.cap = want;
+  if (pattern >= 0) CU(cudaMemsetAsync(b.p, pattern, want, stream));
+  return SE3DS_OK;
+}
+
+int rearm(se3ds_ws* ws, cudaStream_t stream) {
+  if (ws->zbuf.p) CU(cudaMemsetAsync(ws->zbuf.p, 0xFF, ws->zbuf.cap, stream));
+  if (ws->fbuf.p) CU(cudaMemsetAsync(ws->fbuf.p, 0, ws->fbuf.cap, stream));
+  if (ws->bins.p) CU(cudaMemsetAsync(ws->bins.p, 0, ws->bins.cap, stream));
+  if (ws->cbin.p) CU(cudaMemsetAsync(ws->cbin.p, 0, ws->cbin.cap, stream));
+  ws->dirty = false;
+  return SE3DS_OK;
+}
+
+// tf.linspace in float32 (utils/pano_utils.py:211-219): exact end points, start + delta*i inside.
+void linspace_f32(float start, float stop, int n, float* out) {
+  if (n == 1) { out[0] = start; return; }
+  const float delta = (stop - start) / (float)(n - 1);
+  out[0] = start;
+  for (int i = 1; i < n - 1; ++i) {
+    volatile float step = delta * (float)i;  // two roundings, never an fma
+    out[i] = start + step;
+  }
+  out[n - 1] = stop;
+}
+
+// Angle tables of equirectangular_to_pointcloud, canonical sin/cos = float32(double libm).
+// Layout: sin_e[H], cos_e[H], sin_h[W], cos_h[W].  H + W values, computed once per shape.
+int get_tables(se3ds_ws* ws, int h, int w, cudaStream_t stream, const float** out) {
+  for (const auto& e : ws->tables)
+    if (e.h == h && e.w == w) { *out = e.dev; return SE3DS_OK; }
+  const double pi = 3.141592653589793;
+  const double hp = 0.5 * pi / (double)h;
+  std::vector<float> elev(h), head(w), host((size_t)2 * h + 2 * w);
+  linspace_f32((float)hp, (float)(pi - hp), h, elev.data());
+  linspace_f32((float)(1.5 * pi - hp), (float)(-0.5 * pi + hp), w, head.data());
+  for (int r = 0; r < h; ++r) {
+    host[r] = (float)std::sin((double)elev[r]);
+    host[h + r] = (float)std::cos((double)elev[r]);
+  }
+  for (int c = 0; c < w; ++c) {
+    host[2 * h + c] = (float)std::sin((double)head[c]);
+    host[2 * h + w + c] = (float)std::cos((double)head[c]);
+  }
+  float* dev = nullptr;
+  CU(cudaMalloc(&dev, host.size() * sizeof(float)));
+  CU(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+  CU(cudaStreamSynchronize(stream));  // host vector goes out of scope
+  if (ws->tables.size() >= 16) {
+    cudaFree(ws->tables.front().dev);
+    ws->tables.erase(ws->tables.begin());
+  }
+  ws->tables.push_back({h, w, dev});
+  *out = dev;
+  return SE3DS_OK;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+int launch_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SE3DS_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return SE3DS_OK;
+}
+
+template <typename RGB_T>
+int run_chunk(se3ds_ws* ws, const FusedParams& q, int nitems, bool vec, cudaStream_t st) {
+  const int gx = (q.HW + kThreads * 4 - 1) / (kThreads * 4);
+  const dim3 grid(gx, q.S, nitems * q.PC), block(kThreads);
+  cudaEvent_t* ev = nullptr;
+  if (ws->profile) {
+    if (ws->ev_used + 4 > ws->ev_pool.size())
+      for (int i = 0; i < 4; ++i) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ws->ev_pool.push_back(e);
+      }
+    ev = &ws->ev_pool[ws->ev_used];
+    ws->ev_used += 4;
+    CU(cudaEventRecord(ev[0], st));
+  }
+  if (vec) splat_depth_kernel<RGB_T, true><<<grid, block, 0, st>>>(q);
+  else splat_depth_kernel<RGB_T, false><<<grid, block, 0, st>>>(q);
+  if (ev) CU(cudaEventRecord(ev[1], st));
+  if (vec) splat_feat_kernel<RGB_T, true><<<grid, block, 0, st>>>(q);
+  else splat_feat_kernel<RGB_T, false><<<grid, block, 0, st>>>(q);
+  if (ev) CU(cudaEventRecord(ev[2], st));
+  resolve_kernel<RGB_T><<<dim3(gx, nitems * q.PC), block, 0, st>>>(q);
+  if (ev) CU(cudaEventRecord(ev[3], st));
+  ws->launches += 3;
+  return launch_check("fused reprojection kernels");
+}
+
+}  // namespace
+
+extern "C" {
+
+int se3ds_version(void) { return SE3DS_GEOM_VERSION; }
+
+const char* se3ds_status_string(int status) {
+  switch (status) {
+    case SE3DS_OK: return "ok";
+    case SE3DS_ERR_BAD_SHAPE: return "bad shape";
+    case SE3DS_ERR_BAD_DTYPE: return "bad dtype";
+    case SE3DS_ERR_BAD_ARG: return "bad argument";
+    case SE3DS_ERR_CUDA: return "CUDA error";
+    case SE3DS_ERR_NOMEM: return "out of device memory";
+    default: return "unknown status";
+  }
+}
+
+const char* se3ds_last_error(void) { return g_err; }
+
+int se3ds_ws_create(int device, size_t max_bytes, size_t l2_chunk_bytes, se3ds_ws** out) {
+  if (!out) return fail(SE3DS_ERR_BAD_ARG, "out is NULL");
+  int count = 0;
+  CU(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(SE3DS_ERR_BAD_ARG, "device %d of %d", device, count);
+  CU(cudaSetDevice(device));
+  se3ds_ws* ws = new se3ds_ws();
+  ws->device = device;
+  if (max_bytes) ws->max_bytes = max_bytes;
+  if (l2_chunk_bytes) ws->chunk_bytes = l2_chunk_bytes;
+  *out = ws;
+  return SE3DS_OK;
+}
+
+int se3ds_ws_destroy(se3ds_ws* ws) {
+  if (!ws) return SE3DS_OK;
+  cudaSetDevice(ws->device);
+  cudaDeviceSynchronize();
+  for (DevBuf* b : {&ws->zbuf, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->s_rgb, &ws->s_depth,
+                    &ws->s_src, &ws->s_tgt, &ws->s_img, &ws->s_dep, &ws->s_msk, &ws->s_win})
+    if (b->p) cudaFree(b->p);
+  for (auto& e : ws->tables) cudaFree(e.dev);
+  for (auto& e : ws->ev_pool) cudaEventDestroy(e);
+  if (ws->hstream) cudaStreamDestroy(ws->hstream);
+  delete ws;
+  return SE3DS_OK;
+}
+
+int se3ds_ws_bytes(const se3ds_ws* ws, size_t* bytes) {
+  if (!ws || !bytes) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  *bytes = ws_total(ws);
+  return SE3DS_OK;
+}
+
+int se3ds_ws_profile(se3ds_ws* ws, int enable) {
+  if (!ws) return fail(SE3DS_ERR_BAD_ARG, "NULL workspace");
+  ws->profile = enable != 0;
+  ws->ev_used = 0;
+  return SE3DS_OK;
+}
+
+int se3ds_ws_profile_read(se3ds_ws* ws, float ms[3], unsigned long long* launches) {
+  if (!ws || !ms) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(ws->device));
+  ms[0] = ms[1] = ms[2] = 0.f;
+  for (size_t i = 0; i + 4 <= ws->ev_used; i += 4) {
+    CU(cudaEventSynchronize(ws->ev_pool[i + 3]));
+    for (int k = 0; k < 3; ++k) {
+      float t = 0.f;
+      CU(cudaEventElapsedTime(&t, ws->ev_pool[i + k], ws->ev_pool[i + k + 1]));
+      ms[k] += t;
+    }
+  }
+  ws->ev_used = 0;
+  if (launches) *launches = ws->launches;
+  return SE3DS_OK;
+}
+
+int se3ds_mask_pano(const void* pano, int dtype, int n, int h, int w, int c, double proportion,
+                    double masked_region_value, void* out, void* stream) {
+  if (!pano || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL tensor");
+  if (n < 0 || h <= 0 || w <= 0 || c <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "pano must be (N,H,W,C)");
+  const long long total = (long long)n * h * w * c;
+  if (total == 0) return SE3DS_OK;
+  const int mh = (int)(h * proportion);
+  const long long row_elems = (long long)w * c;
+  const int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SE3DS_U8:
+      mask_pano_kernel<uint8_t><<<blocks, kThreads, 0, st>>>((const uint8_t*)pano, (uint8_t*)out, total, h, row_elems, mh, (uint8_t)masked_region_value);
+      break;
+    case SE3DS_I32:
+      mask_pano_kernel<int><<<blocks, kThreads, 0, st>>>((const int*)pano, (int*)out, total, h, row_elems, mh, (int)masked_region_value);
+      break;
+    case SE3DS_F32:
+      mask_pano_kernel<float><<<blocks, kThreads, 0, st>>>((const float*)pano, (float*)out, total, h, row_elems, mh, (float)masked_region_value);
+      break;
+    default: return fail(SE3DS_ERR_BAD_DTYPE, "dtype %d", dtype);
+  }
+  return launch_check("mask_pano_kernel");
+}
+
+int se3ds_unproject_equirect(se3ds_ws* ws, const void* feats, int in_dtype, const float* depth, int n,
+                             int h, int w, int c, double void_class, float depth_scale,
+                             float* xyz1_out, void* feats_out, int out_dtype, void* stream) {
+  if (!ws || !feats || !depth || !xyz1_out || !feats_out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (n < 0 || h <= 0 || c <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "feats should have shape (N, H, W) or (N, H, W, C)");
+  if (w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "Expected equirectangular input images");
+  if (void_class < 0.0 && in_dtype == SE3DS_U8)
+    return fail(SE3DS_ERR_BAD_DTYPE, "feats datatype must be signed if the void class is negative");
+  if (out_dtype != in_dtype && out_dtype != SE3DS_F32) return fail(SE3DS_ERR_BAD_DTYPE, "out dtype must be the input dtype or f32");
+  if (n == 0) return SE3DS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(ws->device));
+  const float* tab = nullptr;
+  if (int rc = get_tables(ws, h, w, st, &tab)) return rc;
+  const long long total = (long long)n * h * w;
+  const int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 16);
+#define UNPROJ(TI, TO)                                                                              \
+  unproject_kernel<TI, TO><<<blocks, kThreads, 0, st>>>((const TI*)feats, depth, tab, n, h, w, c, \
+                                                        depth_scale, (TO)void_class, xyz1_out, (TO*)feats_out)
+  if (in_dtype == SE3DS_U8 && out_dtype == SE3DS_U8) UNPROJ(uint8_t, uint8_t);
+  else if (in_dtype == SE3DS_U8 && out_dtype == SE3DS_F32) UNPROJ(uint8_t, float);
+  else if (in_dtype == SE3DS_I32 && out_dtype == SE3DS_I32) UNPROJ(int, int);
+  else if (in_dtype == SE3DS_I32 && out_dtype == SE3DS_F32) UNPROJ(int, float);
+  else if (in_dtype == SE3DS_F32 && out_dtype == SE3DS_F32) UNPROJ(float, float);
+  else return fail(SE3DS_ERR_BAD_DTYPE, "dtype combination %d -> %d", in_dtype, out_dtype);
+#undef UNPROJ
+  return launch_check("unproject_kernel");
+}
+
+int se3ds_project_cloud(se3ds_ws* ws, const float* coords, const void* feats, int feat_dtype, int n,
+                        long long m, int c, int h, int w, int mode, float input_void_class,
+                        float output_void_class, float depth_scale, float* depth_out,
+                        float* feats_out, int32_t* winner_out, void* stream) {
+  if (!ws || !depth_out || !feats_out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (n < 0 || m < 0 || c <= 0 || h <= 0 || w <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "feats should have shape (N, M) or (N, M, C)");
+  if (m > 0 && (!coords || !feats)) return fail(SE3DS_ERR_BAD_ARG, "NULL cloud");
+  if (m >= (1ll << 31) || (long long)h * w > (long long)kScPixMask) return fail(SE3DS_ERR_BAD_SHAPE, "cloud or image too large");
+  if (mode != 0 && mode != 1) return fail(SE3DS_ERR_BAD_ARG, "mode %d", mode);
+  if (feat_dtype < SE3DS_U8 || feat_dtype > SE3DS_F32) return fail(SE3DS_ERR_BAD_DTYPE, "dtype %d", feat_dtype);
+  if (n == 0) return SE3DS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(ws->device));
+  const long long npix = (long long)n * h * w;
+  if (ws->dirty)
+    if (int rc = rearm(ws, st)) return rc;
+  if (int rc = grow(ws->zbuf, (size_t)npix * 8, 0xFF, st)) return rc;
+  if (int rc = grow(ws->scf, (size_t)std::max<long long>(n * m, 1) * 4, -1, st)) return rc;
+  if (int rc = grow(ws->scr, (size_t)std::max<long long>(n * m, 1) * 4, -1, st)) return rc;
+  if (int rc = grow(ws->cbin, (size_t)(1 + c) * 4, 0, st)) return rc;
+  CloudParams q{};
+  q.coords = coords; q.feats = feats;
+  q.zbuf = (unsigned long long*)ws->zbuf.p; q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p;
+  q.bin = (uint32_t*)ws->cbin.p;
+  q.depth_out = depth_out; q.feats_out = feats_out; q.winner_out = winner_out;
+  q.M = m; q.N = n; q.C = c; q.H = h; q.W = w; q.HW = h * w; q.mode = mode;
+  q.void_in = input_void_class; q.void_out = output_void_class; q.depth_scale = depth_scale;
+  ws->dirty = true;
+  fill_f32_kernel<<<(int)std::min<long long>((npix * c + kThreads - 1) / kThreads, 148 * 16), kThreads, 0, st>>>(feats_out, npix * c, output_void_class);
+  if (m > 0) {
+    const dim3 grid((unsigned)((m + kThreads - 1) / kThreads), n);
+    switch (feat_dtype) {
+      case SE3DS_U8:
+        cloud_depth_kernel<uint8_t><<<grid, kThreads, 0, st>>>(q);
+        cloud_feat_kernel<uint8_t><<<grid, kThreads, 0, st>>>(q);
+        break;
+      case SE3DS_I32:
+        cloud_depth_kernel<int><<<grid, kThreads, 0, st>>>(q);
+        cloud_feat_kernel<int><<<grid, kThreads, 0, st>>>(q);
+        break;
+      default:
+        cloud_depth_kernel<float><<<grid, kThreads, 0, st>>>(q);
+        cloud_feat_kernel<float><<<grid, kThreads, 0, st>>>(q);
+        break;
+    }
+  }
+  cloud_resolve_kernel<<<(unsigned)((npix + kThreads - 1) / kThreads), kThreads, 0, st>>>(q);
+  ws->launches += m > 0 ? 4 : 2;
+  if (int rc = launch_check("cloud projection kernels")) return rc;
+  ws->dirty = false;
+  return SE3DS_OK;
+}
+
+int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
+                    const float* src_pos, const float* tgt_pos, int n, int s, int p, int h, int w,
+                    float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
+                    int project_void, unsigned flags, float* proj_image, float* proj_depth,
+                    float* proj_mask, int32_t* winner_out, float* bin_out, void* stream) {
+  if (!ws || !rgb || !depth || !src_pos || !tgt_pos || !proj_image || !proj_depth || !proj_mask)
+    return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (n < 0 || s <= 0 || p <= 0 || h <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "rgb must be (N,S,H,W,3), tgt_pos (N,P,3)");
+  if (w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "Expected equirectangular input images");
+  if (rgb_dtype != SE3DS_U8 && rgb_dtype != SE3DS_I32) return fail(SE3DS_ERR_BAD_DTYPE, "rgb must be uint8 or int32");
+  if (unproject_void < -1 || unproject_void > 255 || project_void < -1 || project_void > 255)
+    return fail(SE3DS_ERR_BAD_ARG, "void classes must be in [-1, 255]");
+  const long long hw = (long long)h * w;
+  if (hw > (long long)kScPixMask || (long long)s * hw >= (1ll << 31)) return fail(SE3DS_ERR_BAD_SHAPE, "S*H*W too large");
+  if (s > 65535) return fail(SE3DS_ERR_BAD_SHAPE, "S too large");
+  if (n == 0) return SE3DS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(ws->device));
+
+  // job chunking: a chunk's z-buffer + feature buffer + scratch should sit in L2
+  const long long J = (long long)n * p;
+  const size_t job_bytes = (size_t)hw * (16 + 8 * (size_t)s);
+  long long jpc = std::max<long long>(1, (long long)(std::min(ws->chunk_bytes, ws->max_bytes) / job_bytes));
+  jpc = std::min(jpc, J);
+  jpc = std::min<long long>(jpc, 65535);
+  int items_per_chunk, PC;
+  if (jpc >= p) {
+    const long long nchunks = (n + (jpc / p) - 1) / (jpc / p);
+    items_per_chunk = (int)((n + nchunks - 1) / nchunks);
+    PC = p;
+  } else {
+    const long long pchunks = (p + jpc - 1) / jpc;
+    items_per_chunk = 1;
+    PC = (int)((p + pchunks - 1) / pchunks);
+  }
+  const long long chunk_jobs = (long long)items_per_chunk * PC;
+  const long long nchunks_total = (long long)((n + items_per_chunk - 1) / items_per_chunk) * ((p + PC - 1) / PC);
+  const bool per_job = flags & SE3DS_FLAG_BIN_PER_JOB;
+  if (bin_out && per_job) return fail(SE3DS_ERR_BAD_ARG, "bin_out needs the per-call bin mode");
+
+  if (ws->dirty)
+    if (int rc = rearm(ws, st)) return rc;
+  if (int rc = grow(ws->zbuf, (size_t)chunk_jobs * hw * 8, 0xFF, st)) return rc;
+  if (int rc = grow(ws->fbuf, (size_t)chunk_jobs * hw * 8, 0, st)) return rc;
+  if (int rc = grow(ws->scf, (size_t)chunk_jobs * s * hw * 4, -1, st)) return rc;
+  if (int rc = grow(ws->scr, (size_t)chunk_jobs * s * hw * 4, -1, st)) return rc;
+  if (int rc = grow(ws->bins, (size_t)(per_job ? J : 1) * sizeof(Bin), 0, st)) return rc;
+  const float* tab = nullptr;
+  if (int rc = get_tables(ws, h, w, st, &tab)) return rc;
+
+  FusedParams q{};
+  q.rgb = rgb; q.depth = depth; q.src_pos = src_pos; q.tgt_pos = tgt_pos; q.tab = tab;
+  q.zbuf = (unsigned long long*)ws->zbuf.p; q.fbuf = (uint2*)ws->fbuf.p;
+  q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.bins = (Bin*)ws->bins.p;
+  q.out_image = proj_image; q.out_depth = proj_depth; q.out_mask = proj_mask; q.out_winner = winner_out;
+  q.N = n; q.S = s; q.P = p; q.H = h; q.W = w; q.HW = (int)hw;
+  q.mh = (int)(h * mask_proportion);
+  q.mask_frames = mask_frames;
+  q.uv = unproject_void; q.pv = project_void; q.flags = flags; q.depth_scale = depth_scale;
+  q.finalize_bins = (per_job || nchunks_total == 1) ? 1 : 0;
+  q.bin_out = bin_out;
+  const bool vec = (w % 4 == 0) && aligned(depth, 16) && aligned(rgb, rgb_dtype == SE3DS_U8 ? 4 : 16);
+
+  ws->dirty = true;
+  for (int n0 = 0; n0 < n; n0 += items_per_chunk) {
+    const int nitems = std::min(items_per_chunk, n - n0);
+    for (int p0 = 0; p0 < p; p0 += PC) {
+      q.n0 = n0; q.p0 = p0; q.PC = std::min(PC, p - p0);
+      const int rc = rgb_dtype == SE3DS_U8 ? run_chunk<uint8_t>(ws, q, nitems, vec, st) : run_chunk<int>(ws, q, nitems, vec, st);
+      if (rc) return rc;
+    }
+  }
+  if (bin_out) {
+    export_bin_kernel<<<1, 32, 0, st>>>(q);
+    ws->launches += 1;
+    if (int rc = launch_check("export_bin_kernel")) return rc;
+  } else if (!q.finalize_bins) {
+    patch_owner_kernel<<<1, 32, 0, st>>>(q);
+    ws->launches += 1;
+    if (int rc = launch_check("patch_owner_kernel")) return rc;
+  }
+  ws->dirty = false;
+  return SE3DS_OK;
+}
+
+int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, const float* depth_host,
+                         const float* src_pos_host, const float* tgt_pos_host, int n, int s, int p,
+                         int h, int w, float depth_scale, double mask_proportion, int mask_frames,
+                         int unproject_void, int project_void, unsigned flags,
+                         float* proj_image_host, float* proj_depth_host, float* proj_mask_host,
+                         int32_t* winner_out_host) {
+  if (!ws || !rgb_host || !depth_host || !src_pos_host || !tgt_pos_host || !proj_image_host ||
+      !proj_depth_host || !proj_mask_host)
+    return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (n <= 0 || s <= 0 || p <= 0 || h <= 0 || w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "bad shape");
+  if (rgb_dtype != SE3DS_U8 && rgb_dtype != SE3DS_I32) return fail(SE3DS_ERR_BAD_DTYPE, "rgb must be uint8 or int32");
+  CU(cudaSetDevice(ws->device));
+  if (!ws->hstream) CU(cudaStreamCreateWithFlags(&ws->hstream, cudaStreamNonBlocking));
+  cudaStream_t st = ws->hstream;
+  const size_t hw = (size_t)h * w, npts = (size_t)n * s * hw, npix = (size_t)n * p * hw;
+  const size_t rgb_bytes = npts * 3 * (rgb_dtype == SE3DS_U8 ? 1 : 4);
+  if (int rc = grow(ws->s_rgb, rgb_bytes, -1, st)) return rc;
+  if (int rc = grow(ws->s_depth, npts * 4, -1, st)) return rc;
+  if (int rc = grow(ws->s_src, (size_t)n * s * 12, -1, st)) return rc;
+  if (int rc = grow(ws->s_tgt, (size_t)n * p * 12, -1, st)) return rc;
+  if (int rc = grow(ws->s_img, npix * 12, -1, st)) return rc;
+  if (int rc = grow(ws->s_dep, npix * 4, -1, st)) return rc;
+  if (int rc = grow(ws->s_msk, npix * 4, -1, st)) return rc;
+  if (winner_out_host)
+    if (int rc = grow(ws->s_win, npix * 4, -1, st)) return rc;
+  CU(cudaMemcpyAsync(ws->s_rgb.p, rgb_host, rgb_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ws->s_depth.p, depth_host, npts * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ws->s_src.p, src_pos_host, (size_t)n * s * 12, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ws->s_tgt.p, tgt_pos_host, (size_t)n * p * 12, cudaMemcpyHostToDevice, st));
+  if (int rc = se3ds_reproject(ws, ws->s_rgb.p, rgb_dtype, (const float*)ws->s_depth.p, (const float*)ws->s_src.p,
+                               (const float*)ws->s_tgt.p, n, s, p, h, w, depth_scale, mask_proportion, mask_frames,
+                               unproject_void, project_void, flags, (float*)ws->s_img.p, (float*)ws->s_dep.p,
+                               (float*)ws->s_msk.p, winner_out_host ? (int32_t*)ws->s_win.p : nullptr, nullptr, st))
+    return rc;
+  CU(cudaMemcpyAsync(proj_image_host, ws->s_img.p, npix * 12, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(proj_depth_host, ws->s_dep.p, npix * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(proj_mask_host, ws->s_msk.p, npix * 4, cudaMemcpyDeviceToHost, st));
+  if (winner_out_host) CU(cudaMemcpyAsync(winner_out_host, ws->s_win.p, npix * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SE3DS_OK;
+}
+
+int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, float* proj_depth,
+                    float* proj_mask, void* stream) {
+  if (!bin || !proj_image || !proj_depth || !proj_mask) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  apply_bin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bin, depth_scale, proj_image, proj_depth, proj_mask);
+  return launch_check("apply_bin_kernel");
+}
+
+int se3ds_proportion_invalid(const float* offsets, int p, const float* depth, int h, int w,
+                             float distance_padding, float depth_scale, float* out, void* stream) {
+  if (!offsets || !depth || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (p < 0 || h <= 0 || w <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "depth_image must be (H, W)");
+  if (p == 0) return SE3DS_OK;
+  proportion_invalid_kernel<<<p, kThreads, 0, (cudaStream_t)stream>>>(offsets, depth, h, w, distance_padding, depth_scale, out);
+  return launch_check("proportion_invalid_kernel");
+}
+
+}  // extern "C"

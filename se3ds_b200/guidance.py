@@ -1,0 +1,286 @@
+"""Fused guidance path: RGB-D panoramas + poses -> (proj_image, proj_depth, proj_mask).
+
+`reproject` is the one-call form of what the reference spreads over
+  pano_utils.mask_pano -> pano_utils.equirectangular_to_pointcloud -> `xyz1 += position` ->
+  [compaction] -> tf.concat over frames -> `coords - position` ->
+  pano_utils.project_feats_to_equirectangular -> guidance dict
+(models/models.py:180-321, trainers/gan_manager.py:458-556, utils/eval_metric.py:144-240),
+without ever materialising the point cloud.  `GuidanceMemory` mirrors the memory interface of
+the reference's SE3DSModel (add_to_memory / __call__ / get, set, reset memory) on top of it,
+keeping the S source frames (7 B per point) instead of a concatenated cloud (28 B per point).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import constants
+from .utils import pano_utils
+
+
+class Conventions(NamedTuple):
+  """Void conventions of the three reference callers."""
+  unproject_void: int
+  project_void: int
+  filter_void: bool
+
+
+SE3DS_MODEL = Conventions(constants.INVALID_RGB_VALUE, constants.INVALID_RGB_VALUE, True)   # models/models.py
+GAN_MANAGER = Conventions(0, constants.INVALID_RGB_VALUE, False)                            # trainers/gan_manager.py:476-548
+EVAL_METRIC = Conventions(constants.INVALID_RGB_VALUE, constants.INVALID_RGB_VALUE, False)  # utils/eval_metric.py:163-236
+
+
+def _prep(rgb, depth, src_pos, tgt_pos, to_device: bool):
+  conv = (lambda t, n: _lib.require_cuda(torch.as_tensor(t), n)) if to_device else (lambda t, n: torch.as_tensor(t).contiguous())
+  rgb = conv(rgb, 'rgb')
+  if rgb.dim() == 4:
+    rgb = rgb[:, None]
+  if rgb.dim() != 5 or rgb.shape[-1] != 3:
+    raise ValueError(f'rgb should have shape (N, S, H, W, 3), got {tuple(rgb.shape)} instead.')
+  if rgb.dtype not in (torch.uint8, torch.int32):
+    if rgb.dtype in (torch.int64, torch.int16, torch.int8):
+      rgb = rgb.to(torch.int32)
+    else:
+      raise ValueError(f'rgb must be uint8 or int32 with values in [-1, 255], got {rgb.dtype}')
+  n, s, h, w, _ = rgb.shape
+  assert w == 2 * h, 'Expected equirectangular input images'
+  depth = conv(depth, 'depth').to(torch.float32).reshape(n, s, h, w).contiguous()
+  src_pos = conv(src_pos, 'src_pos').to(torch.float32).reshape(n, s, 3).contiguous()
+  tgt_pos = conv(tgt_pos, 'tgt_pos').to(torch.float32)
+  tgt_pos = tgt_pos.reshape(n, -1, 3).contiguous()
+  return rgb.contiguous(), depth, src_pos, tgt_pos
+
+
+def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_SCALE,
+              mask_proportion: float = 0.125, mask_frames: int = 0,
+              unproject_void: int = constants.INVALID_RGB_VALUE, project_void: int = constants.INVALID_RGB_VALUE,
+              filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
+              export_bin: bool = False, out: Optional[Dict[str, torch.Tensor]] = None,
+              workspace: Optional[_lib.Workspace] = None) -> Dict[str, torch.Tensor]:
+  """Re-projects S source RGB-D panos per item onto P target poses per item.
+
+  Args:
+    rgb: (N,S,H,W,3) uint8, or int32 in [-1,255] ((N,H,W,3) is taken as S=1).
+    depth: (N,S,H,W) float32 in [0,1].
+    src_pos: (N,S,3) source positions;  tgt_pos: (N,P,3) or (N,3) target positions.
+    mask_frames: the first `mask_frames` frames get mask_pano(., mask_proportion, -1).
+    unproject_void / project_void / filter_void: see `Conventions`.
+    per_job_bin: every (item,pose) job is its own reference call (batch 1).
+  Returns dict with proj_image (J,H,W,3), proj_depth (J,H,W,1), proj_mask (J,H,W,1),
+  blurred_mask (zeros, shares no memory), and optionally winner (J,H,W) int32, bin (4,).
+  """
+  rgb, depth, src_pos, tgt_pos = _prep(rgb, depth, src_pos, tgt_pos, True)
+  n, s, h, w, _ = rgb.shape
+  p = tgt_pos.shape[1]
+  j = n * p
+  dev = rgb.device
+  if out is None:
+    out = {}
+  def buf(name, shape, dtype=torch.float32):
+    t = out.get(name)
+    if t is None or tuple(t.shape) != shape or t.dtype != dtype or t.device != dev:
+      t = out[name] = torch.empty(shape, dtype=dtype, device=dev)
+    return t
+  image = buf('proj_image', (j, h, w, 3))
+  pdepth = buf('proj_depth', (j, h, w, 1))
+  mask = buf('proj_mask', (j, h, w, 1))
+  winner = buf('winner', (j, h, w), torch.int32) if return_winner else None
+  binb = buf('bin', (4,)) if export_bin else None
+  flags = (_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0)
+  ws = workspace or _lib.default_workspace(dev)
+  _lib.check(_lib.load().se3ds_reproject(
+      ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
+      n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),
+      int(project_void), flags, _lib.ptr(image), _lib.ptr(pdepth), _lib.ptr(mask), _lib.ptr(winner),
+      _lib.ptr(binb), _lib.stream_handle(dev)))
+  return out
+
+
+class PreparedReprojection:
+  """A reprojection call with every argument pre-bound: `run()` is one C-ABI call and nothing
+  else (no tensor bookkeeping on the host), suitable for CUDA-graph capture after one warm-up
+  run.  The tensors passed to `prepare` are kept alive and read / written in place."""
+
+  def __init__(self, tensors, out, args, ws):
+    self.tensors, self.out, self._args, self.workspace = tensors, out, args, ws
+    self._fn = _lib.load().se3ds_reproject
+    self.device = out['proj_image'].device
+
+  def run(self, stream=None):
+    st = _lib.stream_handle(self.device) if stream is None else ctypes.c_void_p(stream)
+    _lib.check(self._fn(*self._args, st))
+    return self.out
+
+
+def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_SCALE,
+            mask_proportion: float = 0.125, mask_frames: int = 0,
+            unproject_void: int = constants.INVALID_RGB_VALUE, project_void: int = constants.INVALID_RGB_VALUE,
+            filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
+            workspace: Optional[_lib.Workspace] = None) -> PreparedReprojection:
+  """Same arguments as `reproject`; allocates the outputs once and returns a PreparedReprojection."""
+  rgb, depth, src_pos, tgt_pos = _prep(rgb, depth, src_pos, tgt_pos, True)
+  n, s, h, w, _ = rgb.shape
+  p = tgt_pos.shape[1]
+  j = n * p
+  dev = rgb.device
+  out = dict(proj_image=torch.empty((j, h, w, 3), device=dev), proj_depth=torch.empty((j, h, w, 1), device=dev),
+             proj_mask=torch.empty((j, h, w, 1), device=dev))
+  if return_winner:
+    out['winner'] = torch.empty((j, h, w), dtype=torch.int32, device=dev)
+  flags = (_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0)
+  ws = workspace or _lib.default_workspace(dev)
+  args = (ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
+          n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),
+          int(project_void), flags, _lib.ptr(out['proj_image']), _lib.ptr(out['proj_depth']),
+          _lib.ptr(out['proj_mask']), _lib.ptr(out.get('winner')), None)
+  return PreparedReprojection((rgb, depth, src_pos, tgt_pos), out, args, ws)
+
+
+def apply_bin(bin_values: torch.Tensor, out: Dict[str, torch.Tensor], depth_scale: float = constants.DEPTH_SCALE):
+  """Applies a reduced reject bin to pixel (0,0) of job 0 of `out` (see se3ds_apply_bin)."""
+  dev = out['proj_image'].device
+  _lib.check(_lib.load().se3ds_apply_bin(_lib.ptr(bin_values.contiguous()), float(depth_scale),
+                                         _lib.ptr(out['proj_image']), _lib.ptr(out['proj_depth']),
+                                         _lib.ptr(out['proj_mask']), _lib.stream_handle(dev)))
+
+
+def reproject_host(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_SCALE,
+                   mask_proportion: float = 0.125, mask_frames: int = 0,
+                   unproject_void: int = constants.INVALID_RGB_VALUE,
+                   project_void: int = constants.INVALID_RGB_VALUE, filter_void: bool = False,
+                   per_job_bin: bool = False, return_winner: bool = False,
+                   out: Optional[Dict[str, torch.Tensor]] = None, device: int = 0,
+                   workspace: Optional[_lib.Workspace] = None) -> Dict[str, torch.Tensor]:
+  """`reproject` for HOST tensors (pinned memory recommended): host->device copies, the fused
+  kernels and the device->host copies of the guidance tensors all happen inside the C ABI call
+  (se3ds_reproject_host), which returns when the host outputs are complete."""
+  rgb, depth, src_pos, tgt_pos = _prep(rgb, depth, src_pos, tgt_pos, False)
+  for t in (rgb, depth, src_pos, tgt_pos):
+    if t.is_cuda:
+      raise ValueError('reproject_host takes host tensors; use reproject for device tensors')
+  n, s, h, w, _ = rgb.shape
+  p = tgt_pos.shape[1]
+  j = n * p
+  if out is None:
+    out = {}
+  pin = torch.cuda.is_available()
+  def buf(name, shape, dtype=torch.float32):
+    t = out.get(name)
+    if t is None or tuple(t.shape) != shape or t.dtype != dtype or t.is_cuda:
+      t = out[name] = torch.empty(shape, dtype=dtype, pin_memory=pin)
+    return t
+  image = buf('proj_image', (j, h, w, 3))
+  pdepth = buf('proj_depth', (j, h, w, 1))
+  mask = buf('proj_mask', (j, h, w, 1))
+  winner = buf('winner', (j, h, w), torch.int32) if return_winner else None
+  flags = (_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0)
+  ws = workspace or _lib.default_workspace(torch.device('cuda', device))
+  _lib.check(_lib.load().se3ds_reproject_host(
+      ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
+      n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),
+      int(project_void), flags, _lib.ptr(image), _lib.ptr(pdepth), _lib.ptr(mask), _lib.ptr(winner)))
+  return out
+
+
+class MemoryState(NamedTuple):
+  """Frame-ring memory: the S observations instead of the reference's concatenated cloud
+  (models/models.py:77-87 keeps coords (N,4,M) / feats / rgb_coords / rgb)."""
+  rgb: List[torch.Tensor]        # each (N,H,W,3) uint8 or int32
+  semantic: List[torch.Tensor]   # each (N,H,W,1) uint8
+  depth: List[torch.Tensor]      # each (N,H,W) float32
+  position: List[torch.Tensor]   # each (N,3) float32
+  masked: List[bool]
+
+
+class GuidanceMemory(object):
+  """The guidance half of the reference's SE3DSModel (models/models.py:90-321).
+
+  add_to_memory(...) stores an observation; __call__(position) returns the generator inputs
+  `proj_image`, `proj_depth`, `proj_mask`, `blurred_mask` (+ `proj_semantic`) for a target
+  position.  The generator itself (models/models.py:323-366) is out of scope.
+  """
+
+  def __init__(self, image_height: int, depth_scale: float = constants.DEPTH_SCALE, batch_size: int = 1,
+               project_semantic: bool = False):
+    if batch_size != 1:
+      raise ValueError('Several methods do not support batch_size > 1.')
+    self.batch_size = batch_size
+    self.height = image_height
+    self.width = image_height * 2
+    self.depth_scale = depth_scale
+    self.project_semantic = project_semantic
+    self.reset_memory()
+
+  def _check_batch_size(self, input_batch_size):
+    if input_batch_size != self.batch_size:
+      raise ValueError('Input batch size is not suitable. Expected '
+                       f'{self.batch_size}, got {input_batch_size} instead.')
+
+  def reset_memory(self):
+    self._memory = MemoryState([], [], [], [], [])
+
+  def get_memory_state(self) -> MemoryState:
+    m = self._memory
+    return MemoryState([t.clone() for t in m.rgb], [t.clone() for t in m.semantic],
+                       [t.clone() for t in m.depth], [t.clone() for t in m.position], list(m.masked))
+
+  def set_memory_state(self, state: MemoryState):
+    self._memory = MemoryState([t.clone() for t in state.rgb], [t.clone() for t in state.semantic],
+                               [t.clone() for t in state.depth], [t.clone() for t in state.position],
+                               list(state.masked))
+
+  def add_to_memory(self, pano_rgb, pano_semantic, pano_depth, position, mask_blurred=True):
+    """models/models.py:180-245 (the cloud is not built; the frame is kept)."""
+    pano_semantic = _lib.require_cuda(torch.as_tensor(pano_semantic), 'pano_semantic')
+    self._check_batch_size(pano_semantic.shape[0])
+    pano_rgb = _lib.require_cuda(torch.as_tensor(pano_rgb), 'pano_rgb')
+    assert pano_rgb.dtype in (torch.uint8, torch.int32)
+    assert pano_semantic.dtype in (torch.uint8, torch.int32)
+    m = self._memory
+    m.rgb.append(pano_rgb)
+    m.semantic.append(pano_semantic.to(torch.uint8))
+    m.depth.append(_lib.require_cuda(torch.as_tensor(pano_depth), 'pano_depth').to(torch.float32))
+    m.position.append(_lib.require_cuda(torch.as_tensor(position), 'position').to(torch.float32).reshape(-1, 3))
+    m.masked.append(bool(mask_blurred))
+
+  def __call__(self, position) -> Dict[str, torch.Tensor]:
+    """The guidance half of models/models.py:247-321 for one (N,3) target position."""
+    position = _lib.require_cuda(torch.as_tensor(position), 'position').to(torch.float32).reshape(-1, 3)
+    self._check_batch_size(position.shape[0])
+    m = self._memory
+    if not m.rgb:
+      raise ValueError('memory is empty: call add_to_memory first')
+    # frames that want the blurred rows masked go first (mask_frames is a prefix count)
+    order = sorted(range(len(m.rgb)), key=lambda i: not m.masked[i])
+    dt = torch.int32 if any(t.dtype == torch.int32 for t in m.rgb) else torch.uint8
+    rgb = torch.stack([m.rgb[i].to(dt) for i in order], dim=1)
+    depth = torch.stack([m.depth[i] for i in order], dim=1)
+    src = torch.stack([m.position[i] for i in order], dim=1)
+    out = reproject(rgb, depth, src, position, self.depth_scale, mask_frames=sum(m.masked),
+                    unproject_void=SE3DS_MODEL.unproject_void, project_void=SE3DS_MODEL.project_void,
+                    filter_void=True, per_job_bin=True)
+    out['blurred_mask'] = torch.zeros_like(out['proj_mask'])
+    if self.project_semantic:
+      out['proj_semantic'] = self._project_semantic(position)
+    return out
+
+  def _project_semantic(self, position):
+    """models/models.py:217-219,229-231,276-278 through the materialising compat path."""
+    m = self._memory
+    coords, feats = [], []
+    for sem, depth, pos in zip(m.semantic, m.depth, m.position):
+      xyz1, f = pano_utils.equirectangular_to_pointcloud(sem, depth, constants.INVALID_SEM_VALUE, self.depth_scale)
+      xyz1 = xyz1 + torch.cat([pos, torch.zeros_like(pos[:, :1])], dim=1)[:, :, None]
+      valid = (f != constants.INVALID_SEM_VALUE).any(dim=0).any(dim=-1)
+      coords.append(xyz1[:, :, valid])
+      feats.append(f[:, valid, 0])
+    coords = torch.cat(coords, dim=2)
+    feats = torch.cat(feats, dim=1)
+    rel = coords - torch.cat([position, torch.zeros_like(position[:, :1])], dim=1)[:, :, None]
+    _, sem = pano_utils.project_feats_to_equirectangular(feats, rel, self.height, self.width,
+                                                         constants.INVALID_SEM_VALUE, self.depth_scale)
+    return sem.to(torch.uint8)

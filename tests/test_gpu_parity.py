@@ -1,0 +1,400 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the canonical oracle.
+
+Bar (BASELINE.json north_star): bit-exact target-pixel indices / z-buffer winners / masks, and
+RGB / depth within 1e-5 relative.  The canonical arithmetic makes everything bit-exact, so the
+assertions below use exact equality; the 1e-5 tolerance is only needed against the libm
+restatement (tests/test_oracle_exact.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_exact as X
+from oracle import ref_numpy as R
+
+pytestmark = pytest.mark.gpu
+
+F32 = np.float32
+
+
+@pytest.fixture(scope='module')
+def mods():
+  from se3ds_b200 import _lib, guidance, synth
+  from se3ds_b200.inference import perturbation_utils
+  from se3ds_b200.utils import pano_utils, point_cloud_utils
+  assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+  _lib.load()
+  return dict(lib=_lib, g=guidance, synth=synth, pano=pano_utils, pc=point_cloud_utils, pert=perturbation_utils)
+
+
+def _cuda(d):
+  return {k: torch.as_tensor(v).cuda() for k, v in d.items()}
+
+
+def _check_fused(mods, inp, conv=None, mask_frames=0, per_job_bin=False, ws=None):
+  g = mods['g']
+  conv = conv or g.EVAL_METRIC
+  t = _cuda(inp)
+  out = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=mask_frames,
+                    unproject_void=conv.unproject_void, project_void=conv.project_void,
+                    filter_void=conv.filter_void, per_job_bin=per_job_bin, return_winner=True, workspace=ws)
+  torch.cuda.synchronize()
+  if conv.filter_void:
+    ref = _oracle_filtered(inp, mask_frames, per_job_bin)
+  else:
+    ref = _oracle_masked(inp, conv, mask_frames, per_job_bin)
+  np.testing.assert_array_equal(out['winner'].cpu().numpy(), ref['winner'])
+  np.testing.assert_array_equal(out['proj_depth'].cpu().numpy(), ref['depth'])
+  np.testing.assert_array_equal(out['proj_mask'].cpu().numpy(), ref['mask'])
+  np.testing.assert_array_equal(out['proj_image'].cpu().numpy(), ref['image'])
+  return out, ref
+
+
+def _oracle_masked(inp, conv, mask_frames, per_job_bin):
+  """X.reproject masks frame 0 only; emulate a prefix of masked frames by pre-masking."""
+  rgb = inp['rgb'].astype(np.int32).copy()
+  for k in range(mask_frames):
+    rgb[:, k] = R.mask_pano(rgb[:, k], masked_region_value=-1)
+  return X.reproject(rgb, inp['depth'], inp['src_pos'], inp['tgt_pos'], unproject_void=conv.unproject_void,
+                     project_void=conv.project_void, mask_first_frame=False, per_job_bin=per_job_bin)
+
+
+def _oracle_filtered(inp, mask_frames, per_job_bin):
+  """SE3DSModel convention: compaction (models/models.py:229-237) before projection.  Winner
+  indices are reported in the un-compacted numbering s*H*W + pixel, like the kernels do."""
+  rgb = inp['rgb'].astype(np.int32).copy()
+  n, s, h, w, _ = rgb.shape
+  assert n == 1, 'the compaction reduces over the batch axis; SE3DSModel is batch 1'
+  coords, feats, index = [], [], []
+  for k in range(s):
+    frame = rgb[:, k]
+    if k < mask_frames:
+      frame = R.mask_pano(frame, masked_region_value=-1)
+    xyz1, f = X.equirectangular_to_pointcloud(frame, inp['depth'][:, k], -1, 20.0, interpolation_method='bilinear')
+    xyz1 = xyz1 + np.concatenate([inp['src_pos'][:, k], np.zeros((n, 1), F32)], 1)[:, :, None]
+    valid = np.any(f != -1, axis=(0, 2))
+    coords.append(xyz1[:, :, valid]); feats.append(f[:, valid]); index.append(k * h * w + np.nonzero(valid)[0])
+  coords = np.concatenate(coords, 2); feats = np.concatenate(feats, 1); index = np.concatenate(index)
+  tgt = inp['tgt_pos'].reshape(n, -1, 3)
+  outs = []
+  for p in range(tgt.shape[1]):
+    rel = coords - np.concatenate([tgt[:, p], np.zeros((n, 1), F32)], 1)[:, :, None]
+    o = X.splat(rel, feats, h, w, 20.0, -1.0)
+    o['winner'] = np.where(o['winner'] >= 0, index[np.maximum(o['winner'], 0)], -1).astype(np.int32)
+    outs.append(o)
+  assert per_job_bin or len(outs) == 1
+  o = {k: np.concatenate([x[k] for x in outs], 0) for k in ('depth', 'feat', 'winner')}
+  image, d, mask = R.guidance_from_projection(o['depth'], o['feat'])
+  return dict(image=image, depth=d, mask=mask, winner=o['winner'])
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dist', ['room', 'rand'])
+@pytest.mark.parametrize('h', [64, 256])
+def test_fused_single_frame(mods, dist, h):
+  """Config c1 shape family: one pano, one pose (BASELINE.json configs[0])."""
+  inp = mods['synth'].make_inputs(1, 1, 1, h, seed=h, dist=dist)
+  out, ref = _check_fused(mods, inp)
+  assert (ref['winner'] >= 0).mean() > 0.2
+
+
+def test_fused_batch_global_bin(mods):
+  """Whole-call reject bin: rejected points of every job land on job 0's pixel (0,0)."""
+  inp = mods['synth'].make_inputs(3, 1, 1, 64, seed=1, dist='rand')
+  out, ref = _check_fused(mods, inp)
+  assert out['proj_image'][0, 0, 0].max().item() > 0.9
+
+
+def test_fused_per_job_bin(mods):
+  inp = mods['synth'].make_inputs(2, 1, 2, 64, seed=2, dist='rand')
+  _check_fused(mods, inp, per_job_bin=True)
+
+
+def test_fused_trajectory_and_mask(mods):
+  """Config c3 shape family: S prior frames fused into one target; frame 0 masked
+  (trainers/gan_manager.py:530-535)."""
+  inp = mods['synth'].make_inputs(2, 4, 1, 64, seed=3, dist='room')
+  for conv in (mods['g'].EVAL_METRIC, mods['g'].GAN_MANAGER):
+    _check_fused(mods, inp, conv=conv, mask_frames=1)
+
+
+def test_fused_pose_sweep(mods):
+  """Config c4 shape family: P perturbed poses of one pano."""
+  inp = mods['synth'].make_inputs(1, 1, 8, 64, seed=4, dist='room', sweep=True)
+  _check_fused(mods, inp, per_job_bin=True)
+  _check_fused(mods, inp, per_job_bin=False)
+
+
+def test_fused_se3ds_model_convention(mods):
+  """models/models.py flow: mask, compaction, void -1 on both sides, batch 1."""
+  inp = mods['synth'].make_inputs(1, 3, 1, 64, seed=5, dist='room')
+  _check_fused(mods, inp, conv=mods['g'].SE3DS_MODEL, mask_frames=3, per_job_bin=True)
+
+
+def test_fused_int32_rgb_with_void_values(mods):
+  """int32 RGB in [-1,255] as the rollout loops produce (gan_manager.py:541-543)."""
+  inp = mods['synth'].make_inputs(2, 2, 1, 32, seed=6, dist='rand', rgb_dtype=np.int32)
+  rng = np.random.default_rng(0)
+  inp['rgb'][rng.uniform(size=inp['rgb'].shape) < 0.05] = -1
+  for conv in (mods['g'].EVAL_METRIC, mods['g'].GAN_MANAGER):
+    _check_fused(mods, inp, conv=conv, mask_frames=1)
+
+
+@pytest.mark.parametrize('h', [3, 4, 5, 10])
+def test_fused_tiny_and_ragged_sizes(mods, h):
+  """W % 4 != 0 takes the scalar-load path; tiny panos exercise partially filled warps."""
+  inp = mods['synth'].make_inputs(2, 2, 3, h, seed=h, dist='rand')
+  _check_fused(mods, inp, mask_frames=1)
+
+
+def test_fused_chunked_equals_unchunked(mods):
+  """Job chunking (bounded workspace) must not change a bit, including the global bin."""
+  inp = mods['synth'].make_inputs(3, 2, 3, 32, seed=7, dist='rand')
+  ws = mods['lib'].Workspace(0, 0, 32 * 64 * (16 + 16) * 2)  # two jobs per chunk
+  _check_fused(mods, inp, ws=ws)
+  _check_fused(mods, inp, per_job_bin=True, ws=ws)
+  ws1 = mods['lib'].Workspace(0, 0, 1)  # one job per chunk
+  _check_fused(mods, inp, ws=ws1)
+  ws.close(); ws1.close()
+
+
+def test_fused_identity_reprojection(mods):
+  """models/models_test.py:64-68: project at the source position => >= 95 % RGB equal."""
+  inp = mods['synth'].make_inputs(1, 1, 1, 128, seed=8, dist='rand')
+  inp['tgt_pos'] = inp['src_pos'][:, 0].copy()
+  out, _ = _check_fused(mods, inp, conv=mods['g'].SE3DS_MODEL, per_job_bin=True)
+  proj_u8 = (out['proj_image'] * 255).to(torch.uint8).cpu().numpy()
+  assert np.all(proj_u8[0] == inp['rgb'][0, 0], axis=-1).mean() >= 0.95
+
+
+def test_fused_all_invalid_depth(mods):
+  """Nothing valid: every output pixel is void (depth 1, mask 0, black)."""
+  inp = mods['synth'].make_inputs(1, 1, 1, 16, seed=9)
+  inp['depth'][:] = 0
+  out, _ = _check_fused(mods, inp, conv=mods['g'].SE3DS_MODEL, per_job_bin=True)
+  assert out['proj_mask'].sum().item() == 0
+  assert (out['proj_depth'] == 1).all()
+
+
+def test_export_and_apply_bin(mods):
+  """Multi-GPU bin protocol on one GPU: export per shard, reduce, apply == whole-call result."""
+  g = mods['g']
+  inp = mods['synth'].make_inputs(4, 1, 1, 32, seed=10, dist='rand')
+  ref = X.reproject(inp['rgb'], inp['depth'], inp['src_pos'], inp['tgt_pos'], mask_first_frame=False)
+  t = _cuda(inp)
+  parts, bins = [], []
+  for lo, hi in ((0, 2), (2, 4)):
+    o = g.reproject(t['rgb'][lo:hi], t['depth'][lo:hi], t['src_pos'][lo:hi], t['tgt_pos'][lo:hi], export_bin=True)
+    bins.append(o['bin'].clone()); parts.append({k: v.clone() for k, v in o.items()})
+  b = torch.stack(bins)
+  red = torch.cat([b[:, :1].min(dim=0).values, b[:, 1:].max(dim=0).values])
+  g.apply_bin(red, parts[0])
+  for k, r in (('proj_image', 'image'), ('proj_depth', 'depth'), ('proj_mask', 'mask')):
+    got = torch.cat([parts[0][k], parts[1][k]]).cpu().numpy()
+    np.testing.assert_array_equal(got, ref[r])
+
+
+def test_determinism(mods):
+  """Atomic min / max are order independent: repeated runs are bit-stable."""
+  g = mods['g']
+  t = _cuda(mods['synth'].make_inputs(2, 2, 2, 128, seed=11, dist='rand'))
+  first = {k: v.clone() for k, v in g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], return_winner=True).items()}
+  for _ in range(3):
+    again = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], return_winner=True)
+    for k in first:
+      assert torch.equal(first[k], again[k]), k
+
+
+def test_reproject_host_equals_device(mods):
+  g = mods['g']
+  inp = mods['synth'].make_inputs(2, 2, 1, 64, seed=12)
+  t = _cuda(inp)
+  dev = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, return_winner=True)
+  host = g.reproject_host(*(torch.as_tensor(inp[k]) for k in ('rgb', 'depth', 'src_pos', 'tgt_pos')),
+                          mask_frames=1, return_winner=True)
+  for k in ('proj_image', 'proj_depth', 'proj_mask', 'winner'):
+    assert not host[k].is_cuda
+    assert torch.equal(host[k], dev[k].cpu()), k
+
+
+def test_full_size_c2_against_oracle(mods):
+  """BASELINE.json configs[1]: 512x1024, batch 8 -- full size, still bit-exact."""
+  inp = mods['synth'].make_inputs(8, 1, 1, 512, seed=13, dist='room')
+  out, ref = _check_fused(mods, inp, mask_frames=1)
+  hit = (ref['winner'] >= 0).mean()
+  assert 0.2 < hit < 1.0
+
+
+# ------------------------------------------------------------------------------------------
+# compat path: the reference's own function signatures
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('batch_size,image_size,multi', [(2, 64, False), (1, 128, False), (2, 64, True), (1, 128, True)])
+def test_equirectangular_to_pointcloud(mods, batch_size, image_size, multi):
+  """utils/pano_utils_test.py:89-111 + exact parity of xyz1."""
+  rng = np.random.default_rng(1)
+  shape = (batch_size, image_size, 2 * image_size) + ((3,) if multi else ())
+  feats = rng.integers(0, R.NUM_MP3D_CLASSES, shape).astype(np.int32)
+  depth = rng.uniform(0, R.DEPTH_SCALE, (batch_size, image_size, 2 * image_size)).astype(F32)
+  depth[0, :4] = rng.uniform(0, 1, depth[0, :4].shape)
+  xyz1, ff = mods['pano'].equirectangular_to_pointcloud(torch.as_tensor(feats), torch.as_tensor(depth), 0, 20.0)
+  ex, ef = X.equirectangular_to_pointcloud(feats, depth, 0, 20.0)
+  assert tuple(xyz1.shape) == (batch_size, 4, 2 * image_size**2)
+  assert ff.dtype == torch.int32
+  np.testing.assert_array_equal(xyz1.cpu().numpy(), ex)
+  np.testing.assert_array_equal(ff.cpu().numpy(), ef)
+  _, fb = mods['pano'].equirectangular_to_pointcloud(torch.as_tensor(feats), torch.as_tensor(depth), 0, 20.0,
+                                                     interpolation_method='bilinear')
+  assert fb.dtype == torch.float32
+
+
+@pytest.mark.parametrize('batch_size,image_size', [(2, 64), (1, 128)])
+def test_project_feats_to_equirectangular(mods, batch_size, image_size):
+  """utils/pano_utils_test.py:67-87 (random normal cloud, scalar semantic features)."""
+  rng = np.random.default_rng(2)
+  m = image_size**2
+  feats = rng.integers(0, R.NUM_MP3D_CLASSES, (batch_size, m)).astype(np.int32)
+  xyz = rng.standard_normal((batch_size, 3, m)).astype(F32)
+  xyz1 = np.concatenate([xyz, np.ones((batch_size, 1, m), F32)], axis=1)
+  d, f, win = mods['pano'].project_feats_to_equirectangular(torch.as_tensor(feats), torch.as_tensor(xyz1), image_size,
+                                                            image_size * 2, 0, 20.0, return_winner=True)
+  o = X.splat(xyz1, feats, image_size, image_size * 2, 20.0, 0.0)
+  assert tuple(d.shape) == (batch_size, image_size, image_size * 2) and tuple(f.shape) == tuple(d.shape)
+  np.testing.assert_array_equal(d.cpu().numpy(), o['depth'])
+  np.testing.assert_array_equal(f.cpu().numpy(), o['feat'])
+  np.testing.assert_array_equal(win.cpu().numpy(), o['winner'])
+  assert 0 <= d.min().item() and d.max().item() <= 1
+  assert 0 <= f.min().item() and f.max().item() <= R.NUM_MP3D_CLASSES
+
+
+@pytest.mark.parametrize('batch_size,image_size,multi', [(2, 64, False), (1, 128, True)])
+def test_project_to_feat_perspective(mods, batch_size, image_size, multi):
+  """utils/point_cloud_utils_test.py:42-64: square target through project_to_feat itself."""
+  rng = np.random.default_rng(3)
+  shape = (batch_size, image_size, image_size) + ((3,) if multi else ())
+  feats = rng.integers(0, R.NUM_MP3D_CLASSES, shape).astype(np.int32)
+  depth = rng.uniform(0, R.DEPTH_SCALE, (batch_size, image_size, image_size)).astype(F32)
+  xyz1, ff = R.get_filtered_coords_and_feats(feats, depth, 20.0)
+  g_xyz1, g_ff = mods['pc'].get_filtered_coords_and_feats(torch.as_tensor(feats), torch.as_tensor(depth), 20.0)
+  np.testing.assert_allclose(g_xyz1.cpu().numpy(), xyz1, rtol=1e-6, atol=1e-6)
+  np.testing.assert_array_equal(g_ff.cpu().numpy(), ff)
+  pd, pf = mods['pc'].project_to_feat(torch.as_tensor(xyz1), torch.as_tensor(ff), image_size, image_size, 20.0, 0)
+  ed, ef = X.project_to_feat(xyz1, ff, image_size, image_size, 20.0, 0)
+  np.testing.assert_array_equal(pd.cpu().numpy(), ed)
+  np.testing.assert_array_equal(pf.cpu().numpy(), ef)
+  assert tuple(pf.shape) == shape
+
+
+def test_project_cloud_float_feats_negative_and_void_out(mods):
+  """float32 features of mixed sign, non-zero output void class, C = 5."""
+  rng = np.random.default_rng(4)
+  n, m, c, h = 2, 5000, 5, 32
+  xyz1 = np.concatenate([rng.standard_normal((n, 3, m)).astype(F32) * 3, np.ones((n, 1, m), F32)], 1)
+  feats = rng.standard_normal((n, m, c)).astype(F32) * 10
+  feats[rng.uniform(size=(n, m)) < 0.1] = -7.0
+  coords = np.stack([xyz1[:, 0], xyz1[:, 1], np.abs(xyz1[:, 2]) + 0.1, xyz1[:, 3]], 1)
+  # transformed-coordinates mode with an explicit output void class
+  pd, pf = mods['pc'].project_to_feat(torch.as_tensor(coords), torch.as_tensor(feats), h, h, 20.0, -7.0, -3.0)
+  ed, ef = X.project_to_feat(coords, feats, h, h, 20.0, -7.0, -3.0)
+  np.testing.assert_array_equal(pd.cpu().numpy(), ed)
+  np.testing.assert_array_equal(pf.cpu().numpy(), ef)
+
+
+def test_project_empty_cloud(mods):
+  """M = 0: the first frame of a rollout projects an empty memory (gan_manager.py:462-483)."""
+  d, f = mods['pano'].project_feats_to_equirectangular(torch.zeros((2, 0, 3), dtype=torch.int32),
+                                                       torch.zeros((2, 4, 0)), 16, 32, -1, 20.0)
+  assert (d == 1).all() and (f == 0).all() and tuple(f.shape) == (2, 16, 32, 3)
+
+
+def test_compat_pipeline_matches_fused(mods):
+  """The op-by-op reference call sequence (materialised cloud) and the fused call agree."""
+  g, pano = mods['g'], mods['pano']
+  inp = mods['synth'].make_inputs(2, 2, 1, 64, seed=14, dist='room')
+  t = _cuda(inp)
+  coords, feats = [], []
+  for k in range(2):
+    frame = t['rgb'][:, k].to(torch.int32)
+    if k == 0:
+      frame = pano.mask_pano(frame, masked_region_value=-1)
+    xyz1, f = pano.equirectangular_to_pointcloud(frame, t['depth'][:, k], -1, 20.0)
+    pos = torch.cat([t['src_pos'][:, k], torch.zeros_like(t['src_pos'][:, k, :1])], 1)
+    coords.append(xyz1 + pos[:, :, None]); feats.append(f)
+  coords = torch.cat(coords, 2); feats = torch.cat(feats, 1)
+  tp = torch.cat([t['tgt_pos'][:, 0], torch.zeros_like(t['tgt_pos'][:, 0, :1])], 1)
+  d, f = pano.project_feats_to_equirectangular(feats, coords - tp[:, :, None], 64, 128, -1, 20.0)
+  out = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1)
+  assert torch.equal(out['proj_depth'][..., 0], d)
+  assert torch.equal(out['proj_image'], torch.clip(f / 255, 0, 1))
+
+
+@pytest.mark.parametrize('batch_size,h,dtype', [(2, 64, torch.float32), (2, 64, torch.int32), (1, 256, torch.int32), (1, 8, torch.uint8)])
+def test_mask_pano(mods, batch_size, h, dtype):
+  """utils/pano_utils_test.py:113-123 + exact parity."""
+  rng = np.random.default_rng(5)
+  pano = torch.as_tensor(rng.uniform(0, 255, (batch_size, h, 2 * h, 3))).to(dtype)
+  for value in (0, -1 if dtype != torch.uint8 else 7):
+    out = mods['pano'].mask_pano(pano, masked_region_value=value)
+    assert out.shape == pano.shape and out.dtype == pano.dtype
+    np.testing.assert_array_equal(out.cpu().numpy(), R.mask_pano(pano.numpy(), masked_region_value=value))
+
+
+@pytest.mark.parametrize('distance,depth_distance,expected', [(0.5, 0.5, 1.0), (0.3, 0.5, 0.0)])
+def test_proportion_invalid_kat(mods, distance, depth_distance, expected):
+  """inference/perturbation_utils_test.py:30-41."""
+  depth = torch.full((64, 128), depth_distance / 20.0)
+  got = mods['pert'].get_proportion_invalid_for_depth(torch.tensor([0.0, distance, 0.0]), depth)
+  assert got == expected
+
+
+def test_proportion_invalid_offsets_and_batch(mods):
+  """inference/perturbation_utils_test.py:43-94 + 64 random offsets against the oracle."""
+  pert = mods['pert']
+  for offset, centre in (([0.0, 0.5, 0.0], (0.5, 0.5)), ([0.5, 0.5, 0.0], (0.75, 0.75))):
+    img = np.full((64, 128), 1.0, F32)
+    hs, ws = int(64 * centre[0]), int(128 * centre[1])
+    img[hs - 10:hs + 10, ws - 10:ws + 10] = 0.0
+    assert pert.get_proportion_invalid_for_depth(torch.tensor(offset), torch.as_tensor(img)) > 0.0
+    img = np.full((64, 128), 1.0, F32)
+    img[:10, :10] = 0.0
+    assert pert.get_proportion_invalid_for_depth(torch.tensor(offset), torch.as_tensor(img)) == 0.0
+  rng = np.random.default_rng(6)
+  depth = rng.uniform(0, 0.2, (128, 256)).astype(F32)
+  offs = np.concatenate([rng.uniform(-1.5, 1.5, (64, 2)), rng.uniform(-0.1, 0.1, (64, 1))], 1).astype(F32)
+  got = pert.get_proportion_invalid_for_depth_batch(torch.as_tensor(offs), torch.as_tensor(depth)).cpu().numpy()
+  want = np.array([X.get_proportion_invalid_for_depth(o, depth) for o in offs], F32)
+  np.testing.assert_array_equal(got, want)
+
+
+def test_guidance_memory_matches_reference_flow(mods):
+  """GuidanceMemory (frame ring) against the oracle's SE3DSModel memory flow."""
+  g = mods['g']
+  inp = mods['synth'].make_inputs(1, 2, 1, 64, seed=15, dist='room')
+  rng = np.random.default_rng(7)
+  sem = rng.integers(1, R.NUM_MP3D_CLASSES, (1, 2, 64, 128, 1)).astype(np.uint8)
+  mem = g.GuidanceMemory(64, project_semantic=True)
+  ora = R.SE3DSMemoryOracle(64)
+  for k in range(2):
+    mem.add_to_memory(torch.as_tensor(inp['rgb'][:, k]), torch.as_tensor(sem[:, k]), torch.as_tensor(inp['depth'][:, k]),
+                      torch.as_tensor(inp['src_pos'][:, k]))
+    ora.add_to_memory(inp['rgb'][:, k], sem[:, k], inp['depth'][:, k], inp['src_pos'][:, k])
+  out = mem(torch.as_tensor(inp['tgt_pos'][:, 0]))
+  want = ora.project(inp['tgt_pos'][:, 0])  # libm arithmetic: boundary cases may differ
+  for k in ('proj_image', 'proj_depth', 'proj_mask'):
+    bad = np.mean(np.any(out[k].cpu().numpy() != want[k], axis=-1))
+    assert bad < 1e-3, (k, bad)
+  assert np.mean(out['proj_semantic'].cpu().numpy() != want['proj_semantic']) < 1e-3
+  with pytest.raises(ValueError):
+    g.GuidanceMemory(64, batch_size=2)
+
+
+def test_error_behaviour(mods):
+  """Same exception types as the reference (pano_utils.py:190-202, point_cloud_utils.py:120-122)."""
+  pano, pc = mods['pano'], mods['pc']
+  with pytest.raises(ValueError):
+    pano.equirectangular_to_pointcloud(torch.zeros((1, 4, 8, 3, 1), dtype=torch.int32), torch.zeros((1, 4, 8)), 0, 20.0)
+  with pytest.raises(ValueError):
+    pano.equirectangular_to_pointcloud(torch.zeros((1, 4, 8, 3), dtype=torch.uint8), torch.zeros((1, 4, 8)), -1, 20.0)
+  with pytest.raises(AssertionError):
+    pano.equirectangular_to_pointcloud(torch.zeros((1, 4, 9, 3), dtype=torch.int32), torch.zeros((1, 4, 9)), -1, 20.0)
+  with pytest.raises(ValueError):
+    pc.project_to_feat(torch.zeros((1, 4, 5)), torch.zeros((1, 5, 3, 1)), 8, 8, 20.0, 0)

@@ -22,7 +22,7 @@
 
 namespace se3ds {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr unsigned long long kZArmed = 0xFFFFFFFFFFFFFFFFull;
 
 // scratch word: pixel index in bits 0..27, flags above
@@ -61,6 +61,7 @@ struct FusedParams {
   float depth_scale;
   int finalize_bins;  // 1: the bin of an owner pixel is complete when K4 runs
   float* bin_out;     // export mode: no owner pixel, the bin is handed to the caller
+  float inv_depth_scale;  // RN(1 / depth_scale), computed on the host with an IEEE division
 };
 
 __device__ __forceinline__ bool row_masked(const FusedParams& q, int s, int row) {
@@ -117,224 +118,249 @@ __device__ __forceinline__ void red_max_f16x4(uint2* addr, uint2 v) {
   asm volatile("red.global.max.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
-// Warp-aggregated update of the reject bin: one REDG per warp and only if it can change the bin
-// (bins only grow, so a stale read is a safe filter).
-__device__ __forceinline__ void bin_min_depth(Bin* bin, bool has, float rad) {
-  const unsigned m = __ballot_sync(0xffffffffu, has);
-  if (m == 0) return;
-  const uint32_t v = __reduce_max_sync(0xffffffffu, has ? ~f32_ordered(rad) : 0u);
-  if ((threadIdx.x & 31) == 0 && v > *reinterpret_cast<volatile uint32_t*>(&bin->zneg)) atomicMax(&bin->zneg, v);
+// Block-aggregated update of the reject bin.  Every thread contributes the reduction of its own
+// points; one barrier decides whether the block has anything to add, then one thread compares with
+// the bin (an L2 read -- bins only grow, so a stale value is a safe filter) and issues the REDG.
+__device__ __forceinline__ void bin_min_depth_block(Bin* bin, bool has, uint32_t zneg) {
+  __shared__ uint32_t sm_z[kThreads / 32];
+  if (!__syncthreads_or(has)) return;
+  const uint32_t v = __reduce_max_sync(0xffffffffu, has ? zneg : 0u);
+  if ((threadIdx.x & 31) == 0) sm_z[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t m = sm_z[0];
+#pragma unroll
+    for (int i = 1; i < kThreads / 32; ++i) m = max(m, sm_z[i]);
+    if (m > __ldcg(&bin->zneg)) atomicMax(&bin->zneg, m);
+  }
 }
-__device__ __forceinline__ void bin_max_feat(Bin* bin, bool has, int3 f) {
-  const unsigned m = __ballot_sync(0xffffffffu, has);
-  if (m == 0) return;
+__device__ __forceinline__ void bin_max_feat_block(Bin* bin, bool has, int3 f) {
+  __shared__ int sm_f[kThreads / 32][3];
+  if (!__syncthreads_or(has)) return;
   const int r = __reduce_max_sync(0xffffffffu, has ? f.x : 0);
   const int g = __reduce_max_sync(0xffffffffu, has ? f.y : 0);
   const int b = __reduce_max_sync(0xffffffffu, has ? f.z : 0);
-  if ((threadIdx.x & 31) == 0) {
-    volatile int* cur = bin->f;
-    if (r > cur[0]) atomicMax(&bin->f[0], r);
-    if (g > cur[1]) atomicMax(&bin->f[1], g);
-    if (b > cur[2]) atomicMax(&bin->f[2], b);
+  if ((threadIdx.x & 31) == 0) { sm_f[threadIdx.x >> 5][0] = r; sm_f[threadIdx.x >> 5][1] = g; sm_f[threadIdx.x >> 5][2] = b; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int m = sm_f[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < kThreads / 32; ++i) m = max(m, sm_f[i][threadIdx.x]);
+    if (m > __ldcg(&bin->f[threadIdx.x])) atomicMax(&bin->f[threadIdx.x], m);
   }
+}
+
+// Launch geometry shared by K2 / K3: blockIdx.y = source row, blockIdx.x * kThreads + tid = group
+// of PPT consecutive columns, blockIdx.z = local job * S + frame.  PPT = 4 is the vector path
+// (W % 4 == 0, 16-byte aligned planes), PPT = 1 the generic one.
+struct SrcIdx {
+  int lj, s, n, p, job, row, col0;
+  bool active;
+};
+template <int PPT>
+__device__ __forceinline__ SrcIdx src_index(const FusedParams& q) {
+  SrcIdx i;
+  const int z = blockIdx.z;
+  if (q.S == 1) { i.lj = z; i.s = 0; } else { i.lj = z / q.S; i.s = z - i.lj * q.S; }
+  if (q.PC == 1) { i.n = q.n0 + i.lj; i.p = q.p0; } else { const int a = i.lj / q.PC; i.n = q.n0 + a; i.p = q.p0 + (i.lj - a * q.PC); }
+  i.job = i.n * q.P + i.p;
+  i.row = blockIdx.y;
+  i.col0 = (blockIdx.x * kThreads + threadIdx.x) * PPT;
+  i.active = i.col0 < q.W;
+  return i;
+}
+
+template <typename RGB_T, int PPT>
+__device__ __forceinline__ void load_rgbn(const RGB_T* rgb, size_t pix0, int3 (&o)[PPT]) {
+  if constexpr (PPT == 4) load_rgb4(rgb, pix0, o);
+  else o[0] = load_rgb1(rgb, pix0);
 }
 
 // ------------------------------------------------------------------------------------------
 // K2: fused unproject + translate + project + depth splat
 // ------------------------------------------------------------------------------------------
-template <typename RGB_T, bool VEC>
+template <typename RGB_T, int PPT>
 __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
-  const int lj = blockIdx.z;
-  const int n = q.n0 + lj / q.PC, p = q.p0 + lj % q.PC;
-  const int s = blockIdx.y;
-  const int job = n * q.P + p;
-  const int pix0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
-  const bool active = pix0 < q.HW;
-  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? job : 0);
-
-  const size_t frame = (size_t)(n * q.S + s) * q.HW;
-  float d[4] = {0.f, 0.f, 0.f, 0.f};
-  int3 raw[4] = {};
-  int cnt = 0;
-  if (active) {
-    cnt = min(4, q.HW - pix0);
-    if (VEC) {
+  const SrcIdx ix = src_index<PPT>(q);
+  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
+  bool bin_has = false;
+  uint32_t bin_z = 0u;
+  if (ix.active) {
+    const int pix0 = ix.row * q.W + ix.col0;
+    const size_t frame = (size_t)(ix.n * q.S + ix.s) * q.HW;
+    float d[PPT], sh[PPT], ch[PPT];
+    int3 raw[PPT];
+    const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
+    if constexpr (PPT == 4) {
       const float4 dv = __ldg(reinterpret_cast<const float4*>(q.depth + frame + pix0));
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sin_h + ix.col0));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cos_h + ix.col0));
       d[0] = dv.x; d[1] = dv.y; d[2] = dv.z; d[3] = dv.w;
-      load_rgb4(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
+      sh[0] = s4.x; sh[1] = s4.y; sh[2] = s4.z; sh[3] = s4.w;
+      ch[0] = c4.x; ch[1] = c4.y; ch[2] = c4.z; ch[3] = c4.w;
     } else {
-      for (int k = 0; k < 4; ++k)
-        if (k < cnt) {
-          d[k] = q.depth[frame + pix0 + k];
-          raw[k] = load_rgb1(static_cast<const RGB_T*>(q.rgb), frame + pix0 + k);
-        }
+      d[0] = __ldg(q.depth + frame + pix0); sh[0] = __ldg(sin_h + ix.col0); ch[0] = __ldg(cos_h + ix.col0);
     }
-  }
-  const float* sp = q.src_pos + (size_t)(n * q.S + s) * 3;
-  const float* tp = q.tgt_pos + (size_t)job * 3;
-  const float sx = sp[0], sy = sp[1], sz = sp[2];
-  const float tx = tp[0], ty = tp[1], tz = tp[2];
-  const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
-  unsigned long long* zb = q.zbuf + (size_t)lj * q.HW;
-  const size_t sc0 = ((size_t)lj * q.S + s) * q.HW + pix0;
-
-  uint32_t scf[4];
-  float scr[4];
+    load_rgbn<RGB_T, PPT>(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
+    const float se = __ldg(sin_e + ix.row), ce = __ldg(cos_e + ix.row);
+    const float* sp = q.src_pos + (size_t)(ix.n * q.S + ix.s) * 3;
+    const float* tp = q.tgt_pos + (size_t)ix.job * 3;
+    const float sx = __ldg(sp), sy = __ldg(sp + 1), sz = __ldg(sp + 2);
+    const float tx = __ldg(tp), ty = __ldg(tp + 1), tz = __ldg(tp + 2);
+    const bool masked = row_masked(q, ix.s, ix.row);
+    unsigned long long* zb = q.zbuf + (size_t)ix.lj * q.HW;
+    uint32_t scf[PPT];
+    float scr[PPT];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool on = k < cnt;
-    const int pix = pix0 + k;
-    const int row = on ? pix / q.W : 0, col = on ? pix - row * q.W : 0;
-    // pano_utils.py:220-236
-    const bool dvalid = d[k] > 0.0f && d[k] < 1.0f;
-    const float rad0 = __fmul_rn(__fmul_rn(d[k], q.depth_scale), dvalid ? 1.0f : 0.0f);
-    const float t = __fmul_rn(rad0, sin_e[row]);
-    const float x = __fmul_rn(t, cos_h[col]);
-    const float y = __fmul_rn(t, sin_h[col]);
-    const float z = __fmul_rn(rad0, cos_e[row]);
-    // models.py:225-226 then :273-275 -- two roundings
-    const float X = __fsub_rn(__fadd_rn(x, sx), tx);
-    const float Y = __fsub_rn(__fadd_rn(y, sy), ty);
-    const float Z = __fsub_rn(__fadd_rn(z, sz), tz);
-    const int3 f = point_feat(q, !dvalid, row_masked(q, s, row), raw[k]);
-    const bool dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
-    const bool fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
-    float px, py, rad;
-    pseudo_perspective(X, Y, Z, px, py, rad);
-    const int tpix = pixel_of(px, py, rad, q.H, q.W);
-    const bool live = on && !dropped;
-    const bool valid = live && fvalid && tpix >= 0;
-    const uint32_t dflag = dvalid ? 0u : kScDepthInv;
-    if (valid) {
-      const uint32_t idx = (uint32_t)(s * q.HW + pix);
-      const unsigned long long key =
-          ((unsigned long long)__float_as_uint(rad) << 32) | (idx << 1) | (dvalid ? 0u : 1u);
-      atomicMin(zb + tpix, key);
+    for (int k = 0; k < PPT; ++k) {
+      // pano_utils.py:220-236
+      const bool dvalid = d[k] > 0.0f && d[k] < 1.0f;
+      const float rad0 = __fmul_rn(__fmul_rn(d[k], q.depth_scale), dvalid ? 1.0f : 0.0f);
+      const float t = __fmul_rn(rad0, se);
+      const float x = __fmul_rn(t, ch[k]);
+      const float y = __fmul_rn(t, sh[k]);
+      const float z = __fmul_rn(rad0, ce);
+      // models.py:225-226 then :273-275 -- two roundings
+      const float X = __fsub_rn(__fadd_rn(x, sx), tx);
+      const float Y = __fsub_rn(__fadd_rn(y, sy), ty);
+      const float Z = __fsub_rn(__fadd_rn(z, sz), tz);
+      const int3 f = point_feat(q, !dvalid, masked, raw[k]);
+      const bool dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
+      const bool fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
+      float rad;
+      const int tpix = project_pixel(X, Y, Z, q.H, q.W, rad);
+      const bool valid = !dropped && fvalid && tpix >= 0;
+      const uint32_t dflag = dvalid ? 0u : kScDepthInv;
+      if (valid) {
+        const uint32_t idx = (uint32_t)(ix.s * q.HW + pix0 + k);
+        atomicMin(zb + tpix, ((unsigned long long)__float_as_uint(rad) << 32) | (idx << 1) | (dvalid ? 0u : 1u));
+      } else if (!dropped) {
+        bin_has = true;
+        bin_z = max(bin_z, ~f32_ordered(rad));
+      }
+      scf[k] = dropped ? kScDropped : (valid ? (uint32_t)tpix | dflag : kScInvalid | dflag);
+      scr[k] = rad;
     }
-    bin_min_depth(bin, live && !valid, rad);
-    scf[k] = !live ? kScDropped : (valid ? (uint32_t)tpix | dflag : kScInvalid | dflag);
-    scr[k] = rad;
-  }
-  if (active) {
-    if (VEC) {
-      *reinterpret_cast<uint4*>(q.sc_flat + sc0) = make_uint4(scf[0], scf[1], scf[2], scf[3]);
-      *reinterpret_cast<float4*>(q.sc_rad + sc0) = make_float4(scr[0], scr[1], scr[2], scr[3]);
+    const size_t sc0 = ((size_t)ix.lj * q.S + ix.s) * q.HW + pix0;
+    if constexpr (PPT == 4) {
+      __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc0), make_uint4(scf[0], scf[1], scf[2], scf[3]));
+      __stcg(reinterpret_cast<float4*>(q.sc_rad + sc0), make_float4(scr[0], scr[1], scr[2], scr[3]));
     } else {
-      for (int k = 0; k < cnt; ++k) { q.sc_flat[sc0 + k] = scf[k]; q.sc_rad[sc0 + k] = scr[k]; }
+      q.sc_flat[sc0] = scf[0]; q.sc_rad[sc0] = scr[0];
     }
   }
+  bin_min_depth_block(bin, bin_has, bin_z);
 }
 
 // ------------------------------------------------------------------------------------------
 // K3: tolerance test + per-channel max of the surviving features
 // ------------------------------------------------------------------------------------------
-template <typename RGB_T, bool VEC>
+template <typename RGB_T, int PPT>
 __global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams q) {
-  const int lj = blockIdx.z;
-  const int n = q.n0 + lj / q.PC, p = q.p0 + lj % q.PC;
-  const int s = blockIdx.y;
-  const int job = n * q.P + p;
-  const int pix0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
-  const bool active = pix0 < q.HW;
-  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? job : 0);
-  const size_t frame = (size_t)(n * q.S + s) * q.HW;
-  const size_t sc0 = ((size_t)lj * q.S + s) * q.HW + pix0;
-  uint32_t scf[4] = {kScDropped, kScDropped, kScDropped, kScDropped};
-  float scr[4] = {0.f, 0.f, 0.f, 0.f};
-  int3 raw[4] = {};
-  if (active) {
-    const int cnt = min(4, q.HW - pix0);
-    if (VEC) {
-      const uint4 a = *reinterpret_cast<const uint4*>(q.sc_flat + sc0);
-      const float4 b = *reinterpret_cast<const float4*>(q.sc_rad + sc0);
+  const SrcIdx ix = src_index<PPT>(q);
+  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
+  bool bin_has = false;
+  int3 bin_f = make_int3(0, 0, 0);
+  if (ix.active) {
+    const int pix0 = ix.row * q.W + ix.col0;
+    const size_t frame = (size_t)(ix.n * q.S + ix.s) * q.HW;
+    const size_t sc0 = ((size_t)ix.lj * q.S + ix.s) * q.HW + pix0;
+    uint32_t scf[PPT];
+    float scr[PPT];
+    int3 raw[PPT];
+    if constexpr (PPT == 4) {
+      const uint4 a = __ldcg(reinterpret_cast<const uint4*>(q.sc_flat + sc0));
+      const float4 b = __ldcg(reinterpret_cast<const float4*>(q.sc_rad + sc0));
       scf[0] = a.x; scf[1] = a.y; scf[2] = a.z; scf[3] = a.w;
       scr[0] = b.x; scr[1] = b.y; scr[2] = b.z; scr[3] = b.w;
-      load_rgb4(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
     } else {
-      for (int k = 0; k < cnt; ++k) {
-        scf[k] = q.sc_flat[sc0 + k];
-        scr[k] = q.sc_rad[sc0 + k];
-        raw[k] = load_rgb1(static_cast<const RGB_T*>(q.rgb), frame + pix0 + k);
+      scf[0] = q.sc_flat[sc0]; scr[0] = q.sc_rad[sc0];
+    }
+    load_rgbn<RGB_T, PPT>(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
+    const unsigned long long* zb = q.zbuf + (size_t)ix.lj * q.HW;
+    uint2* fb = q.fbuf + (size_t)ix.lj * q.HW;
+    // issue the z-buffer gathers first, then consume
+    unsigned long long key[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const bool haspix = !(scf[k] & (kScDropped | kScInvalid));
+      key[k] = haspix ? __ldcg(zb + (scf[k] & kScPixMask)) : kZArmed;
+    }
+    const bool masked = row_masked(q, ix.s, ix.row);
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const bool live = !(scf[k] & kScDropped);
+      const bool haspix = live && !(scf[k] & kScInvalid);
+      const int3 f = point_feat(q, scf[k] & kScDepthInv, masked, raw[k]);
+      bool rejected = live && !haspix;
+      if (haspix) {
+        // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
+        const float zmin = fminf(__uint_as_float((uint32_t)(key[k] >> 32)), q.depth_scale);
+        const bool keep = scr[k] < __fadd_rn(zmin, 0.1f);
+        const bool winner = ((uint32_t)key[k] >> 1) == (uint32_t)(ix.s * q.HW + pix0 + k);
+        if (keep && !winner) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
+        rejected = !keep;
+      }
+      if (rejected) {
+        bin_has = true;
+        bin_f.x = max(bin_f.x, f.x); bin_f.y = max(bin_f.y, f.y); bin_f.z = max(bin_f.z, f.z);
       }
     }
   }
-  const unsigned long long* zb = q.zbuf + (size_t)lj * q.HW;
-  uint2* fb = q.fbuf + (size_t)lj * q.HW;
-  // issue the four z-buffer gathers first, then consume
-  unsigned long long key[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool haspix = !(scf[k] & (kScDropped | kScInvalid));
-    key[k] = haspix ? zb[scf[k] & kScPixMask] : kZArmed;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool live = !(scf[k] & kScDropped);
-    const bool haspix = live && !(scf[k] & kScInvalid);
-    const int pix = pix0 + k;
-    const int row = pix / q.W;
-    const int3 f = point_feat(q, scf[k] & kScDepthInv, row_masked(q, s, row), raw[k]);
-    bool rejected = live && !haspix;
-    if (haspix) {
-      // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
-      const float zmin = fminf(__uint_as_float((uint32_t)(key[k] >> 32)), q.depth_scale);
-      const bool keep = scr[k] < __fadd_rn(zmin, 0.1f);
-      const bool winner = ((uint32_t)key[k] >> 1) == (uint32_t)(s * q.HW + pix);
-      if (keep && !winner) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
-      rejected = !keep;
-    }
-    bin_max_feat(bin, rejected, f);
-  }
+  bin_max_feat_block(bin, bin_has, bin_f);
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: gather-resolve -> guidance tensors
+// K4: gather-resolve -> guidance tensors.  blockIdx.y = target row, blockIdx.z = local job.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float clip01_div255(float v) {
-  // models.py:290-291: clip_by_value(rgb / 255, 0, 1)
-  return fminf(fmaxf(__fdiv_rn(v, 255.0f), 0.0f), 1.0f);
+  // models.py:290-291: clip_by_value(rgb / 255, 0, 1).  v / 255 as q0 = v*y, r = v - 255*q0 (exact,
+  // fma), q = q0 + r*y with y = RN(1/255): bit-identical to IEEE division for every float32
+  // (exhaustively verified over all mantissas, tests/test_canon_math.py).
+  const float y = 0x1.010102p-8f;
+  const float q0 = __fmul_rn(v, y);
+  const float q1 = __fmaf_rn(__fmaf_rn(-255.0f, q0, v), y, q0);
+  return fminf(fmaxf(q1, 0.0f), 1.0f);
 }
 
-template <typename RGB_T>
+template <typename RGB_T, int PPT>
 __global__ void __launch_bounds__(kThreads) resolve_kernel(const FusedParams q) {
-  const int lj = blockIdx.y;
-  const int n = q.n0 + lj / q.PC, p = q.p0 + lj % q.PC;
+  const int lj = blockIdx.z;
+  int n, p;
+  if (q.PC == 1) { n = q.n0 + lj; p = q.p0; } else { const int a = lj / q.PC; n = q.n0 + a; p = q.p0 + (lj - a * q.PC); }
   const int job = n * q.P + p;
-  const int pix0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
-  if (pix0 >= q.HW) return;
-  const bool vec = (q.HW & 3) == 0;
-  const int cnt = min(4, q.HW - pix0);
+  const int row = blockIdx.y;
+  const int col0 = (blockIdx.x * kThreads + threadIdx.x) * PPT;
+  if (col0 >= q.W) return;
+  const int pix0 = row * q.W + col0;
   unsigned long long* zb = q.zbuf + (size_t)lj * q.HW + pix0;
   uint2* fb = q.fbuf + (size_t)lj * q.HW + pix0;
-  unsigned long long key[4];
-  uint2 fv[4];
-  if (vec) {
-    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(zb), b = *reinterpret_cast<const ulonglong2*>(zb + 2);
+  unsigned long long key[PPT];
+  uint2 fv[PPT];
+  if constexpr (PPT == 4) {
+    const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(zb)), b = __ldcg(reinterpret_cast<const ulonglong2*>(zb + 2));
     key[0] = a.x; key[1] = a.y; key[2] = b.x; key[3] = b.y;
-    const uint4 c = *reinterpret_cast<const uint4*>(fb), e = *reinterpret_cast<const uint4*>(fb + 2);
+    const uint4 c = __ldcg(reinterpret_cast<const uint4*>(fb)), e = __ldcg(reinterpret_cast<const uint4*>(fb + 2));
     fv[0] = make_uint2(c.x, c.y); fv[1] = make_uint2(c.z, c.w);
     fv[2] = make_uint2(e.x, e.y); fv[3] = make_uint2(e.z, e.w);
   } else {
-    for (int k = 0; k < 4; ++k) {
-      key[k] = k < cnt ? zb[k] : kZArmed;
-      fv[k] = k < cnt ? fb[k] : make_uint2(0, 0);
-    }
+    key[0] = zb[0]; fv[0] = fb[0];
   }
   // winner gathers (independent loads, issued together)
-  int3 wraw[4];
+  int3 wraw[PPT];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < PPT; ++k) {
     wraw[k] = make_int3(0, 0, 0);
-    if (key[k] != kZArmed && !((uint32_t)key[k] & 1u)) {
-      const uint32_t widx = (uint32_t)key[k] >> 1;
-      wraw[k] = load_rgb1(static_cast<const RGB_T*>(q.rgb), (size_t)n * q.S * q.HW + widx);
-    }
+    if (key[k] != kZArmed && !((uint32_t)key[k] & 1u))
+      wraw[k] = load_rgb1(static_cast<const RGB_T*>(q.rgb), (size_t)n * q.S * q.HW + ((uint32_t)key[k] >> 1));
   }
   const bool per_job = q.flags & SE3DS_FLAG_BIN_PER_JOB;
-  float od[4], om[4], oi[12];
-  int ow[4];
+  // a masked source row can only win when -1 is not the projection void class
+  const bool mask_possible = q.mask_frames > 0 && q.pv != -1;
+  float od[PPT], om[PPT], oi[3 * PPT];
+  int ow[PPT];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < PPT; ++k) {
     const bool has = key[k] != kZArmed;
     const float radw = __uint_as_float((uint32_t)(key[k] >> 32));
     float zmin = has ? fminf(radw, q.depth_scale) : q.depth_scale;
@@ -342,8 +368,12 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const FusedParams q) 
     const bool owner = (pix0 + k == 0) && (per_job || job == 0) && q.bin_out == nullptr;
     if (has) {
       const uint32_t widx = (uint32_t)key[k] >> 1;
-      const int ws = widx / q.HW, wrow = (widx - ws * q.HW) / q.W;
-      const int3 wf = point_feat(q, (uint32_t)key[k] & 1u, row_masked(q, ws, wrow), wraw[k]);
+      bool wmasked = false;
+      if (mask_possible) {
+        const int ws = widx / q.HW, wrow = (widx - ws * q.HW) / q.W;
+        wmasked = row_masked(q, ws, wrow);
+      }
+      const int3 wf = point_feat(q, (uint32_t)key[k] & 1u, wmasked, wraw[k]);
       // the winner survives the tolerance test unless min+0.1 rounds back to min; on the owner
       // pixel a rejected winner lands on the same pixel through the bin anyway.
       if (radw < __fadd_rn(zmin, 0.1f) || owner) {
@@ -365,30 +395,28 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const FusedParams q) 
       }
     }
     // point_cloud_utils.py:160-162, models.py:282-293
-    const float depth = __fdiv_rn(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale);
+    const float depth = div_rcp(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale, q.inv_depth_scale);
     od[k] = depth;
     oi[3 * k + 0] = clip01_div255(f.x); oi[3 * k + 1] = clip01_div255(f.y); oi[3 * k + 2] = clip01_div255(f.z);
     om[k] = (depth > 0.0f && depth < 1.0f && f.x != -1.0f && f.y != -1.0f && f.z != -1.0f) ? 1.0f : 0.0f;
   }
   const size_t o = (size_t)job * q.HW + pix0;
-  if (vec) {
-    *reinterpret_cast<float4*>(q.out_depth + o) = make_float4(od[0], od[1], od[2], od[3]);
-    *reinterpret_cast<float4*>(q.out_mask + o) = make_float4(om[0], om[1], om[2], om[3]);
+  if constexpr (PPT == 4) {
+    __stcs(reinterpret_cast<float4*>(q.out_depth + o), make_float4(od[0], od[1], od[2], od[3]));
+    __stcs(reinterpret_cast<float4*>(q.out_mask + o), make_float4(om[0], om[1], om[2], om[3]));
     float4* im = reinterpret_cast<float4*>(q.out_image + o * 3);
-    im[0] = make_float4(oi[0], oi[1], oi[2], oi[3]);
-    im[1] = make_float4(oi[4], oi[5], oi[6], oi[7]);
-    im[2] = make_float4(oi[8], oi[9], oi[10], oi[11]);
-    if (q.out_winner) *reinterpret_cast<int4*>(q.out_winner + o) = make_int4(ow[0], ow[1], ow[2], ow[3]);
+    __stcs(im, make_float4(oi[0], oi[1], oi[2], oi[3]));
+    __stcs(im + 1, make_float4(oi[4], oi[5], oi[6], oi[7]));
+    __stcs(im + 2, make_float4(oi[8], oi[9], oi[10], oi[11]));
+    if (q.out_winner) __stcs(reinterpret_cast<int4*>(q.out_winner + o), make_int4(ow[0], ow[1], ow[2], ow[3]));
     const ulonglong2 arm = make_ulonglong2(kZArmed, kZArmed);
     *reinterpret_cast<ulonglong2*>(zb) = arm; *reinterpret_cast<ulonglong2*>(zb + 2) = arm;
     *reinterpret_cast<uint4*>(fb) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(fb + 2) = make_uint4(0, 0, 0, 0);
   } else {
-    for (int k = 0; k < cnt; ++k) {
-      q.out_depth[o + k] = od[k]; q.out_mask[o + k] = om[k];
-      for (int c = 0; c < 3; ++c) q.out_image[(o + k) * 3 + c] = oi[3 * k + c];
-      if (q.out_winner) q.out_winner[o + k] = ow[k];
-      zb[k] = kZArmed; fb[k] = make_uint2(0, 0);
-    }
+    q.out_depth[o] = od[0]; q.out_mask[o] = om[0];
+    for (int c = 0; c < 3; ++c) q.out_image[o * 3 + c] = oi[c];
+    if (q.out_winner) q.out_winner[o] = ow[0];
+    zb[0] = kZArmed; fb[0] = make_uint2(0, 0);
   }
 }
 
@@ -399,7 +427,7 @@ __global__ void patch_owner_kernel(const FusedParams q) {
   const float zmin = bin->zneg ? f32_unordered(~bin->zneg) : q.depth_scale;
   const float3 f = make_float3((float)bin->f[0], (float)bin->f[1], (float)bin->f[2]);
   *bin = Bin{0u, {0, 0, 0}};
-  const float depth = __fdiv_rn(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale);
+  const float depth = div_rcp(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale, q.inv_depth_scale);
   q.out_depth[0] = depth;
   q.out_image[0] = clip01_div255(f.x); q.out_image[1] = clip01_div255(f.y); q.out_image[2] = clip01_div255(f.z);
   q.out_mask[0] = (depth > 0.0f && depth < 1.0f && f.x != -1.0f && f.y != -1.0f && f.z != -1.0f) ? 1.0f : 0.0f;

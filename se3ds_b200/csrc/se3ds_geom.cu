@@ -155,10 +155,11 @@ int launch_check(const char* what) {
   return SE3DS_OK;
 }
 
-template <typename RGB_T>
-int run_chunk(se3ds_ws* ws, const FusedParams& q, int nitems, bool vec, cudaStream_t st) {
-  const int gx = (q.HW + kThreads * 4 - 1) / (kThreads * 4);
-  const dim3 grid(gx, q.S, nitems * q.PC), block(kThreads);
+template <typename RGB_T, int PPT>
+int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st) {
+  const int gx = (q.W + kThreads * PPT - 1) / (kThreads * PPT);
+  const int jobs = nitems * q.PC;
+  const dim3 grid(gx, q.H, jobs * q.S), block(kThreads);
   cudaEvent_t* ev = nullptr;
   if (ws->profile) {
     if (ws->ev_used + 4 > ws->ev_pool.size())
@@ -171,16 +172,19 @@ int run_chunk(se3ds_ws* ws, const FusedParams& q, int nitems, bool vec, cudaStre
     ws->ev_used += 4;
     CU(cudaEventRecord(ev[0], st));
   }
-  if (vec) splat_depth_kernel<RGB_T, true><<<grid, block, 0, st>>>(q);
-  else splat_depth_kernel<RGB_T, false><<<grid, block, 0, st>>>(q);
+  splat_depth_kernel<RGB_T, PPT><<<grid, block, 0, st>>>(q);
   if (ev) CU(cudaEventRecord(ev[1], st));
-  if (vec) splat_feat_kernel<RGB_T, true><<<grid, block, 0, st>>>(q);
-  else splat_feat_kernel<RGB_T, false><<<grid, block, 0, st>>>(q);
+  splat_feat_kernel<RGB_T, PPT><<<grid, block, 0, st>>>(q);
   if (ev) CU(cudaEventRecord(ev[2], st));
-  resolve_kernel<RGB_T><<<dim3(gx, nitems * q.PC), block, 0, st>>>(q);
+  resolve_kernel<RGB_T, PPT><<<dim3(gx, q.H, jobs), block, 0, st>>>(q);
   if (ev) CU(cudaEventRecord(ev[3], st));
   ws->launches += 3;
   return launch_check("fused reprojection kernels");
+}
+
+template <typename RGB_T>
+int run_chunk(se3ds_ws* ws, const FusedParams& q, int nitems, bool vec, cudaStream_t st) {
+  return vec ? run_chunk_t<RGB_T, 4>(ws, q, nitems, st) : run_chunk_t<RGB_T, 1>(ws, q, nitems, st);
 }
 
 }  // namespace
@@ -382,7 +386,7 @@ int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* d
     return fail(SE3DS_ERR_BAD_ARG, "void classes must be in [-1, 255]");
   const long long hw = (long long)h * w;
   if (hw > (long long)kScPixMask || (long long)s * hw >= (1ll << 31)) return fail(SE3DS_ERR_BAD_SHAPE, "S*H*W too large");
-  if (s > 65535) return fail(SE3DS_ERR_BAD_SHAPE, "S too large");
+  if (s > 65535 || h > 65535) return fail(SE3DS_ERR_BAD_SHAPE, "S or H too large");
   if (n == 0) return SE3DS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(ws->device));
@@ -392,7 +396,7 @@ int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* d
   const size_t job_bytes = (size_t)hw * (16 + 8 * (size_t)s);
   long long jpc = std::max<long long>(1, (long long)(std::min(ws->chunk_bytes, ws->max_bytes) / job_bytes));
   jpc = std::min(jpc, J);
-  jpc = std::min<long long>(jpc, 65535);
+  jpc = std::min<long long>(jpc, std::max(1, 65535 / s));
   int items_per_chunk, PC;
   if (jpc >= p) {
     const long long nchunks = (n + (jpc / p) - 1) / (jpc / p);
@@ -429,6 +433,10 @@ int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* d
   q.uv = unproject_void; q.pv = project_void; q.flags = flags; q.depth_scale = depth_scale;
   q.finalize_bins = (per_job || nchunks_total == 1) ? 1 : 0;
   q.bin_out = bin_out;
+  {
+    volatile float one = 1.0f, ds = depth_scale;
+    q.inv_depth_scale = one / ds;  // IEEE single division on the host: RN(1 / depth_scale)
+  }
   const bool vec = (w % 4 == 0) && aligned(depth, 16) && aligned(rgb, rgb_dtype == SE3DS_U8 ? 4 : 16);
 
   ws->dirty = true;

@@ -194,6 +194,7 @@ def main():
   ap.add_argument('--no-graph', action='store_true', help='plain stream launches instead of CUDA-graph replay')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--e2e-steps', type=int, default=20)
+  ap.add_argument('--chunk-mb', type=int, default=0, help='workspace L2 chunk size (0 = library default)')
   args = ap.parse_args()
   cfg = CONFIGS[args.config]
   if args.impl == 'reference':
@@ -219,7 +220,7 @@ def main():
   # ring of distinct input/output sets larger than 2x L2, so every step starts cold in L2
   set_bytes = src_bytes + out_bytes
   ring = max(2, min(16, -(-2 * L2_BYTES // set_bytes) + 1))
-  ws = _lib.Workspace(local_rank)
+  ws = _lib.Workspace(local_rank, 0, args.chunk_mb << 20)
   plans = []
   for r in range(ring):
     # every set differs only in its seed; large configs reuse one generated item per set
@@ -244,7 +245,11 @@ def main():
         with torch.cuda.graph(g, stream=stream):
           pl.run()
         graphs.append(g)
+    launches_a = ws.profile_read()[1]
+    plans[0].run()
+    stream.synchronize()
     launches0 = ws.profile_read()[1]
+    launches_per_step = launches0 - launches_a
 
     def step(i):
       if graphs is not None:
@@ -324,11 +329,12 @@ def main():
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(args.config, cfg, args.dist), 'per_gpu_batch': n,
                    'cache': f'inputs+outputs rotate over a ring of {ring} sets ({ring * set_bytes >> 20} MiB > 2x L2)',
-                   'launch': 'cuda_graph_replay' if graphs is not None else 'stream', 'parallelism': f'dp{world}'},
+                   'launch': 'cuda_graph_replay' if graphs is not None else 'stream', 'parallelism': f'dp{world}',
+                   'chunk_mb': args.chunk_mb or 'default'},
         'mpoints_per_s': mpoints,
         'e2e': {'value': world * n * p / (e2e_ms * 1e-3), 'unit': 'panos/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms},
-        'gpu_launches': (3 * args.steps if launches_timed is None else launches_timed),
+        'gpu_launches': (launches_per_step * args.steps if launches_timed is None else launches_timed),
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'kernel': names[dom], 'achieved': kalg[dom] / (kms[dom] * 1e-3) / 1e9, 'peak': peak,
                      'unit': 'GB/s', 'frac': kalg[dom] / (kms[dom] * 1e-3) / 1e9 / peak, 'peak_kind': peak_kind,

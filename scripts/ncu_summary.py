@@ -1,0 +1,31 @@
+"""Prints the headline metrics of every kernel in an .ncu-rep (run where ncu is installed)."""
+import csv
+import subprocess
+import sys
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'launch__registers_per_thread',
+        'launch__grid_size', 'launch__block_size', 'lts__t_sectors_op_red.sum', 'lts__t_sectors_op_atom.sum',
+        'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'sm__cycles_elapsed.max',
+        'smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct', 'smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct',
+        'smsp__warp_issue_stalled_barrier_per_warp_active.pct', 'smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct',
+        'smsp__warp_issue_stalled_not_selected_per_warp_active.pct', 'smsp__warp_issue_stalled_wait_per_warp_active.pct',
+        'smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct', 'smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct',
+        'smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct', 'smsp__warp_issue_stalled_no_instruction_per_warp_active.pct']
+
+
+def main(path):
+  out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+  rows = list(csv.reader(out.splitlines()))
+  hdr, units = rows[0], rows[1]
+  for r in rows[2:]:
+    print('==', r[hdr.index('Kernel Name')][:90])
+    for w in WANT:
+      if w in hdr:
+        print(f'   {w:75s} {r[hdr.index(w)]:>16s} {units[hdr.index(w)]}')
+
+
+if __name__ == '__main__':
+  main(sys.argv[1])

@@ -179,7 +179,10 @@ __device__ __forceinline__ void load_rgbn(const RGB_T* rgb, size_t pix0, int3 (&
 // ------------------------------------------------------------------------------------------
 // K2: fused unproject + translate + project + depth splat
 // ------------------------------------------------------------------------------------------
-template <typename RGB_T, int PPT>
+// FAST: uint8 RGB with project_void == -1 (every reference caller) and, if the compaction is on,
+// unproject_void == -1: a raw colour can then never equal a void class, so validity is decided by
+// the depth and the row mask alone and the per-channel compares disappear.
+template <typename RGB_T, int PPT, bool FAST>
 __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
   const SrcIdx ix = src_index<PPT>(q);
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     } else {
       d[0] = __ldg(q.depth + frame + pix0); sh[0] = __ldg(sin_h + ix.col0); ch[0] = __ldg(cos_h + ix.col0);
     }
-    load_rgbn<RGB_T, PPT>(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
+    if constexpr (!FAST) load_rgbn<RGB_T, PPT>(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
     const float se = __ldg(sin_e + ix.row), ce = __ldg(cos_e + ix.row);
     const float* sp = q.src_pos + (size_t)(ix.n * q.S + ix.s) * 3;
     const float* tp = q.tgt_pos + (size_t)ix.job * 3;
@@ -224,9 +227,16 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       const float X = __fsub_rn(__fadd_rn(x, sx), tx);
       const float Y = __fsub_rn(__fadd_rn(y, sy), ty);
       const float Z = __fsub_rn(__fadd_rn(z, sz), tz);
-      const int3 f = point_feat(q, !dvalid, masked, raw[k]);
-      const bool dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
-      const bool fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
+      bool dropped, fvalid;
+      if constexpr (FAST) {
+        const bool is_void = !dvalid || masked;  // feature is (uv,uv,uv) or (-1,-1,-1)
+        dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && is_void;
+        fvalid = dvalid ? !masked : (q.uv != -1);
+      } else {
+        const int3 f = point_feat(q, !dvalid, masked, raw[k]);
+        dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
+        fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
+      }
       float rad;
       const int tpix = project_pixel(X, Y, Z, q.H, q.W, rad);
       const bool valid = !dropped && fvalid && tpix >= 0;
@@ -297,8 +307,7 @@ __global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams 
         // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
         const float zmin = fminf(__uint_as_float((uint32_t)(key[k] >> 32)), q.depth_scale);
         const bool keep = scr[k] < __fadd_rn(zmin, 0.1f);
-        const bool winner = ((uint32_t)key[k] >> 1) == (uint32_t)(ix.s * q.HW + pix0 + k);
-        if (keep && !winner) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
+        if (keep) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
         rejected = !keep;
       }
       if (rejected) {
@@ -323,8 +332,8 @@ __device__ __forceinline__ float clip01_div255(float v) {
   return fminf(fmaxf(q1, 0.0f), 1.0f);
 }
 
-template <typename RGB_T, int PPT>
-__global__ void __launch_bounds__(kThreads) resolve_kernel(const FusedParams q) {
+template <int PPT>
+__global__ void __launch_bounds__(kThreads, 12) resolve_kernel(const FusedParams q) {
   const int lj = blockIdx.z;
   int n, p;
   if (q.PC == 1) { n = q.n0 + lj; p = q.p0; } else { const int a = lj / q.PC; n = q.n0 + a; p = q.p0 + (lj - a * q.PC); }
@@ -346,17 +355,7 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const FusedParams q) 
   } else {
     key[0] = zb[0]; fv[0] = fb[0];
   }
-  // winner gathers (independent loads, issued together)
-  int3 wraw[PPT];
-#pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    wraw[k] = make_int3(0, 0, 0);
-    if (key[k] != kZArmed && !((uint32_t)key[k] & 1u))
-      wraw[k] = load_rgb1(static_cast<const RGB_T*>(q.rgb), (size_t)n * q.S * q.HW + ((uint32_t)key[k] >> 1));
-  }
   const bool per_job = q.flags & SE3DS_FLAG_BIN_PER_JOB;
-  // a masked source row can only win when -1 is not the projection void class
-  const bool mask_possible = q.mask_frames > 0 && q.pv != -1;
   float od[PPT], om[PPT], oi[3 * PPT];
   int ow[PPT];
 #pragma unroll
@@ -364,24 +363,9 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const FusedParams q) 
     const bool has = key[k] != kZArmed;
     const float radw = __uint_as_float((uint32_t)(key[k] >> 32));
     float zmin = has ? fminf(radw, q.depth_scale) : q.depth_scale;
-    float3 f = unpack_f16x4(fv[k]);
-    const bool owner = (pix0 + k == 0) && (per_job || job == 0) && q.bin_out == nullptr;
-    if (has) {
-      const uint32_t widx = (uint32_t)key[k] >> 1;
-      bool wmasked = false;
-      if (mask_possible) {
-        const int ws = widx / q.HW, wrow = (widx - ws * q.HW) / q.W;
-        wmasked = row_masked(q, ws, wrow);
-      }
-      const int3 wf = point_feat(q, (uint32_t)key[k] & 1u, wmasked, wraw[k]);
-      // the winner survives the tolerance test unless min+0.1 rounds back to min; on the owner
-      // pixel a rejected winner lands on the same pixel through the bin anyway.
-      if (radw < __fadd_rn(zmin, 0.1f) || owner) {
-        f.x = fmaxf(f.x, (float)wf.x); f.y = fmaxf(f.y, (float)wf.y); f.z = fmaxf(f.z, (float)wf.z);
-      }
-    }
+    float3 f = unpack_f16x4(fv[k]);  // per-channel max of every point that passed the tolerance test
     ow[k] = (has && radw <= q.depth_scale) ? (int)((uint32_t)key[k] >> 1) : -1;
-    if (owner) {
+    if ((pix0 + k == 0) && (per_job || job == 0) && q.bin_out == nullptr) {  // owner pixel of a reject bin
       Bin* bin = q.bins + (per_job ? job : 0);
       if (q.finalize_bins) {
         if (bin->zneg) zmin = fminf(zmin, f32_unordered(~bin->zneg));
@@ -409,9 +393,16 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const FusedParams q) 
     __stcs(im + 1, make_float4(oi[4], oi[5], oi[6], oi[7]));
     __stcs(im + 2, make_float4(oi[8], oi[9], oi[10], oi[11]));
     if (q.out_winner) __stcs(reinterpret_cast<int4*>(q.out_winner + o), make_int4(ow[0], ow[1], ow[2], ow[3]));
+    // re-arm only what was touched (a touched feature buffer entry implies a touched z-buffer entry)
     const ulonglong2 arm = make_ulonglong2(kZArmed, kZArmed);
-    *reinterpret_cast<ulonglong2*>(zb) = arm; *reinterpret_cast<ulonglong2*>(zb + 2) = arm;
-    *reinterpret_cast<uint4*>(fb) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(fb + 2) = make_uint4(0, 0, 0, 0);
+    if (key[0] != kZArmed || key[1] != kZArmed) {
+      *reinterpret_cast<ulonglong2*>(zb) = arm;
+      *reinterpret_cast<uint4*>(fb) = make_uint4(0, 0, 0, 0);
+    }
+    if (key[2] != kZArmed || key[3] != kZArmed) {
+      *reinterpret_cast<ulonglong2*>(zb + 2) = arm;
+      *reinterpret_cast<uint4*>(fb + 2) = make_uint4(0, 0, 0, 0);
+    }
   } else {
     q.out_depth[o] = od[0]; q.out_mask[o] = om[0];
     for (int c = 0; c < 3; ++c) q.out_image[o * 3 + c] = oi[c];

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "kernels.cuh"
@@ -60,7 +61,8 @@ struct se3ds_ws {
   bool dirty = false;  // a pass was enqueued but its resolve (which re-arms) was not
   // staging of the host-buffer entry point
   DevBuf s_rgb, s_depth, s_src, s_tgt, s_img, s_dep, s_msk, s_win;
-  cudaStream_t hstream = nullptr;
+  cudaStream_t hstream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> pipe_ev;  // 2 per batch item: inputs on device, outputs computed
   // measurement hooks
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;  // groups of 4 events per profiled chunk
@@ -172,11 +174,15 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
     ws->ev_used += 4;
     CU(cudaEventRecord(ev[0], st));
   }
-  splat_depth_kernel<RGB_T, PPT><<<grid, block, 0, st>>>(q);
+  // FAST feature mode: see splat_depth_kernel
+  const bool fast = std::is_same<RGB_T, uint8_t>::value && q.pv == -1 &&
+                    (!(q.flags & SE3DS_FLAG_FILTER_VOID) || q.uv == -1);
+  if (fast) splat_depth_kernel<RGB_T, PPT, true><<<grid, block, 0, st>>>(q);
+  else splat_depth_kernel<RGB_T, PPT, false><<<grid, block, 0, st>>>(q);
   if (ev) CU(cudaEventRecord(ev[1], st));
   splat_feat_kernel<RGB_T, PPT><<<grid, block, 0, st>>>(q);
   if (ev) CU(cudaEventRecord(ev[2], st));
-  resolve_kernel<RGB_T, PPT><<<dim3(gx, q.H, jobs), block, 0, st>>>(q);
+  resolve_kernel<PPT><<<dim3(gx, q.H, jobs), block, 0, st>>>(q);
   if (ev) CU(cudaEventRecord(ev[3], st));
   ws->launches += 3;
   return launch_check("fused reprojection kernels");
@@ -230,7 +236,9 @@ int se3ds_ws_destroy(se3ds_ws* ws) {
     if (b->p) cudaFree(b->p);
   for (auto& e : ws->tables) cudaFree(e.dev);
   for (auto& e : ws->ev_pool) cudaEventDestroy(e);
-  if (ws->hstream) cudaStreamDestroy(ws->hstream);
+  for (auto& e : ws->pipe_ev) cudaEventDestroy(e);
+  for (cudaStream_t st : {ws->hstream, ws->h2d_stream, ws->d2h_stream})
+    if (st) cudaStreamDestroy(st);
   delete ws;
   return SE3DS_OK;
 }
@@ -372,11 +380,25 @@ int se3ds_project_cloud(se3ds_ws* ws, const float* coords, const void* feats, in
   return SE3DS_OK;
 }
 
-int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
-                    const float* src_pos, const float* tgt_pos, int n, int s, int p, int h, int w,
-                    float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
-                    int project_void, unsigned flags, float* proj_image, float* proj_depth,
-                    float* proj_mask, int32_t* winner_out, float* bin_out, void* stream) {
+}  // extern "C"
+
+namespace {
+
+// Host pipeline of se3ds_reproject_host: chunk c (one batch item) waits for its inputs on the
+// compute stream and hands its outputs to the device->host stream as soon as its resolve is done.
+struct HostPipe {
+  cudaStream_t d2h;
+  cudaEvent_t* in_ready;   // [n]
+  cudaEvent_t* out_ready;  // [n]
+  float *image_host, *depth_host, *mask_host;
+  int32_t* winner_host;
+};
+
+int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
+                   const float* src_pos, const float* tgt_pos, int n, int s, int p, int h, int w,
+                   float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
+                   int project_void, unsigned flags, float* proj_image, float* proj_depth,
+                   float* proj_mask, int32_t* winner_out, float* bin_out, void* stream, const HostPipe* pipe) {
   if (!ws || !rgb || !depth || !src_pos || !tgt_pos || !proj_image || !proj_depth || !proj_mask)
     return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
   if (n < 0 || s <= 0 || p <= 0 || h <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "rgb must be (N,S,H,W,3), tgt_pos (N,P,3)");
@@ -397,6 +419,7 @@ int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* d
   long long jpc = std::max<long long>(1, (long long)(std::min(ws->chunk_bytes, ws->max_bytes) / job_bytes));
   jpc = std::min(jpc, J);
   jpc = std::min<long long>(jpc, std::max(1, 65535 / s));
+  if (pipe) jpc = std::min<long long>(jpc, p);  // one batch item per chunk: finest copy/compute overlap
   int items_per_chunk, PC;
   if (jpc >= p) {
     const long long nchunks = (n + (jpc / p) - 1) / (jpc / p);
@@ -442,10 +465,21 @@ int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* d
   ws->dirty = true;
   for (int n0 = 0; n0 < n; n0 += items_per_chunk) {
     const int nitems = std::min(items_per_chunk, n - n0);
+    if (pipe) CU(cudaStreamWaitEvent(st, pipe->in_ready[n0], 0));
     for (int p0 = 0; p0 < p; p0 += PC) {
       q.n0 = n0; q.p0 = p0; q.PC = std::min(PC, p - p0);
       const int rc = rgb_dtype == SE3DS_U8 ? run_chunk<uint8_t>(ws, q, nitems, vec, st) : run_chunk<int>(ws, q, nitems, vec, st);
       if (rc) return rc;
+    }
+    if (pipe) {  // items_per_chunk == 1 here: ship item n0's guidance tensors
+      CU(cudaEventRecord(pipe->out_ready[n0], st));
+      CU(cudaStreamWaitEvent(pipe->d2h, pipe->out_ready[n0], 0));
+      const size_t o = (size_t)n0 * p * hw, cnt = (size_t)p * hw;
+      CU(cudaMemcpyAsync(pipe->image_host + o * 3, proj_image + o * 3, cnt * 12, cudaMemcpyDeviceToHost, pipe->d2h));
+      CU(cudaMemcpyAsync(pipe->depth_host + o, proj_depth + o, cnt * 4, cudaMemcpyDeviceToHost, pipe->d2h));
+      CU(cudaMemcpyAsync(pipe->mask_host + o, proj_mask + o, cnt * 4, cudaMemcpyDeviceToHost, pipe->d2h));
+      if (pipe->winner_host)
+        CU(cudaMemcpyAsync(pipe->winner_host + o, winner_out + o, cnt * 4, cudaMemcpyDeviceToHost, pipe->d2h));
     }
   }
   if (bin_out) {
@@ -456,9 +490,30 @@ int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* d
     patch_owner_kernel<<<1, 32, 0, st>>>(q);
     ws->launches += 1;
     if (int rc = launch_check("patch_owner_kernel")) return rc;
+    if (pipe) {  // job 0's pixel (0,0) changed after it was shipped: send its 20 bytes again
+      CU(cudaEventRecord(pipe->out_ready[0], st));
+      CU(cudaStreamWaitEvent(pipe->d2h, pipe->out_ready[0], 0));
+      CU(cudaMemcpyAsync(pipe->image_host, proj_image, 12, cudaMemcpyDeviceToHost, pipe->d2h));
+      CU(cudaMemcpyAsync(pipe->depth_host, proj_depth, 4, cudaMemcpyDeviceToHost, pipe->d2h));
+      CU(cudaMemcpyAsync(pipe->mask_host, proj_mask, 4, cudaMemcpyDeviceToHost, pipe->d2h));
+    }
   }
   ws->dirty = false;
   return SE3DS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
+                    const float* src_pos, const float* tgt_pos, int n, int s, int p, int h, int w,
+                    float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
+                    int project_void, unsigned flags, float* proj_image, float* proj_depth,
+                    float* proj_mask, int32_t* winner_out, float* bin_out, void* stream) {
+  return reproject_core(ws, rgb, rgb_dtype, depth, src_pos, tgt_pos, n, s, p, h, w, depth_scale, mask_proportion,
+                        mask_frames, unproject_void, project_void, flags, proj_image, proj_depth, proj_mask,
+                        winner_out, bin_out, stream, nullptr);
 }
 
 int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, const float* depth_host,
@@ -473,11 +528,17 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
   if (n <= 0 || s <= 0 || p <= 0 || h <= 0 || w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "bad shape");
   if (rgb_dtype != SE3DS_U8 && rgb_dtype != SE3DS_I32) return fail(SE3DS_ERR_BAD_DTYPE, "rgb must be uint8 or int32");
   CU(cudaSetDevice(ws->device));
-  if (!ws->hstream) CU(cudaStreamCreateWithFlags(&ws->hstream, cudaStreamNonBlocking));
-  cudaStream_t st = ws->hstream;
+  for (cudaStream_t* sp : {&ws->hstream, &ws->h2d_stream, &ws->d2h_stream})
+    if (!*sp) CU(cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking));
+  while (ws->pipe_ev.size() < (size_t)2 * n) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ws->pipe_ev.push_back(e);
+  }
+  cudaStream_t st = ws->hstream, up = ws->h2d_stream;
   const size_t hw = (size_t)h * w, npts = (size_t)n * s * hw, npix = (size_t)n * p * hw;
-  const size_t rgb_bytes = npts * 3 * (rgb_dtype == SE3DS_U8 ? 1 : 4);
-  if (int rc = grow(ws->s_rgb, rgb_bytes, -1, st)) return rc;
+  const size_t px = rgb_dtype == SE3DS_U8 ? 3 : 12;  // rgb bytes per point
+  if (int rc = grow(ws->s_rgb, npts * px, -1, st)) return rc;
   if (int rc = grow(ws->s_depth, npts * 4, -1, st)) return rc;
   if (int rc = grow(ws->s_src, (size_t)n * s * 12, -1, st)) return rc;
   if (int rc = grow(ws->s_tgt, (size_t)n * p * 12, -1, st)) return rc;
@@ -486,19 +547,26 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
   if (int rc = grow(ws->s_msk, npix * 4, -1, st)) return rc;
   if (winner_out_host)
     if (int rc = grow(ws->s_win, npix * 4, -1, st)) return rc;
-  CU(cudaMemcpyAsync(ws->s_rgb.p, rgb_host, rgb_bytes, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ws->s_depth.p, depth_host, npts * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ws->s_src.p, src_pos_host, (size_t)n * s * 12, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ws->s_tgt.p, tgt_pos_host, (size_t)n * p * 12, cudaMemcpyHostToDevice, st));
-  if (int rc = se3ds_reproject(ws, ws->s_rgb.p, rgb_dtype, (const float*)ws->s_depth.p, (const float*)ws->s_src.p,
-                               (const float*)ws->s_tgt.p, n, s, p, h, w, depth_scale, mask_proportion, mask_frames,
-                               unproject_void, project_void, flags, (float*)ws->s_img.p, (float*)ws->s_dep.p,
-                               (float*)ws->s_msk.p, winner_out_host ? (int32_t*)ws->s_win.p : nullptr, nullptr, st))
+  // upload stream: poses first, then item by item (an event per item lets item i compute while
+  // item i+1 is still on the wire and item i-1 is already travelling back)
+  CU(cudaMemcpyAsync(ws->s_src.p, src_pos_host, (size_t)n * s * 12, cudaMemcpyHostToDevice, up));
+  CU(cudaMemcpyAsync(ws->s_tgt.p, tgt_pos_host, (size_t)n * p * 12, cudaMemcpyHostToDevice, up));
+  const size_t item_pts = (size_t)s * hw;
+  for (int i = 0; i < n; ++i) {
+    CU(cudaMemcpyAsync((char*)ws->s_rgb.p + i * item_pts * px, (const char*)rgb_host + i * item_pts * px, item_pts * px,
+                       cudaMemcpyHostToDevice, up));
+    CU(cudaMemcpyAsync((float*)ws->s_depth.p + i * item_pts, depth_host + i * item_pts, item_pts * 4,
+                       cudaMemcpyHostToDevice, up));
+    CU(cudaEventRecord(ws->pipe_ev[i], up));
+  }
+  HostPipe pipe{ws->d2h_stream, ws->pipe_ev.data(), ws->pipe_ev.data() + n, proj_image_host, proj_depth_host,
+                proj_mask_host, winner_out_host};
+  if (int rc = reproject_core(ws, ws->s_rgb.p, rgb_dtype, (const float*)ws->s_depth.p, (const float*)ws->s_src.p,
+                              (const float*)ws->s_tgt.p, n, s, p, h, w, depth_scale, mask_proportion, mask_frames,
+                              unproject_void, project_void, flags, (float*)ws->s_img.p, (float*)ws->s_dep.p,
+                              (float*)ws->s_msk.p, winner_out_host ? (int32_t*)ws->s_win.p : nullptr, nullptr, st, &pipe))
     return rc;
-  CU(cudaMemcpyAsync(proj_image_host, ws->s_img.p, npix * 12, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(proj_depth_host, ws->s_dep.p, npix * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(proj_mask_host, ws->s_msk.p, npix * 4, cudaMemcpyDeviceToHost, st));
-  if (winner_out_host) CU(cudaMemcpyAsync(winner_out_host, ws->s_win.p, npix * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(ws->d2h_stream));
   CU(cudaStreamSynchronize(st));
   return SE3DS_OK;
 }

@@ -39,7 +39,8 @@ def test_no_torch_symbols_in_the_abi_library():
   """The boundary is plain C: the shared object must not link against libtorch / libc10."""
   import subprocess
   out = subprocess.run(['ldd', _lib.library_path()], capture_output=True, text=True).stdout
-  assert 'torch' not in out and 'c10' not in out
+  names = [line.split()[0] for line in out.splitlines() if line.strip()]
+  assert names and not any('torch' in n or 'c10' in n for n in names), names
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')

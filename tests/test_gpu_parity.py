@@ -382,7 +382,10 @@ def test_guidance_memory_matches_reference_flow(mods):
   out = mem(torch.as_tensor(inp['tgt_pos'][:, 0]))
   want = ora.project(inp['tgt_pos'][:, 0])  # libm arithmetic: boundary cases may differ
   for k in ('proj_image', 'proj_depth', 'proj_mask'):
-    bad = np.mean(np.any(out[k].cpu().numpy() != want[k], axis=-1))
+    got = out[k].cpu().numpy()
+    # libm sin/cos differ from the canonical tables by an ulp, so depth agrees to 1e-5 relative
+    # (north_star tolerance) rather than bit for bit; indices / colours flip only at pixel borders.
+    bad = np.mean(np.any(np.abs(got - want[k]) > 1e-5 * np.abs(want[k]), axis=-1))
     assert bad < 1e-3, (k, bad)
   assert np.mean(out['proj_semantic'].cpu().numpy() != want['proj_semantic']) < 1e-3
   with pytest.raises(ValueError):

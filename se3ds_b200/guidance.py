@@ -28,6 +28,10 @@ class Conventions(NamedTuple):
   project_void: int
   filter_void: bool
 
+  def kwargs(self):
+    """Keyword arguments for `reproject` / `prepare` / `reproject_host`."""
+    return dict(unproject_void=self.unproject_void, project_void=self.project_void, filter_void=self.filter_void)
+
 
 SE3DS_MODEL = Conventions(constants.INVALID_RGB_VALUE, constants.INVALID_RGB_VALUE, True)   # models/models.py
 GAN_MANAGER = Conventions(0, constants.INVALID_RGB_VALUE, False)                            # trainers/gan_manager.py:476-548

@@ -195,8 +195,12 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--e2e-steps', type=int, default=20)
   ap.add_argument('--chunk-mb', type=int, default=0, help='workspace L2 chunk size (0 = library default)')
+  ap.add_argument('--n-override', type=int, default=0, help='override the batch size of the config (memory-bounded runs)')
+  ap.add_argument('--proj-mode', type=int, default=1, help='0 canonical projection only, 1 certified fast path (default)')
   args = ap.parse_args()
-  cfg = CONFIGS[args.config]
+  cfg = dict(CONFIGS[args.config])
+  if args.n_override:
+    cfg['n'] = args.n_override
   if args.impl == 'reference':
     run_reference_arm(args, cfg)
     return
@@ -221,6 +225,7 @@ def main():
   set_bytes = src_bytes + out_bytes
   ring = max(2, min(16, -(-2 * L2_BYTES // set_bytes) + 1))
   ws = _lib.Workspace(local_rank, 0, args.chunk_mb << 20)
+  ws.projection_mode(args.proj_mode)
   plans = []
   for r in range(ring):
     # every set differs only in its seed; large configs reuse one generated item per set
@@ -330,7 +335,8 @@ def main():
         'config': {'workload': workload_name(args.config, cfg, args.dist), 'per_gpu_batch': n,
                    'cache': f'inputs+outputs rotate over a ring of {ring} sets ({ring * set_bytes >> 20} MiB > 2x L2)',
                    'launch': 'cuda_graph_replay' if graphs is not None else 'stream', 'parallelism': f'dp{world}',
-                   'chunk_mb': args.chunk_mb or 'default'},
+                   'chunk_mb': args.chunk_mb or 'default',
+                   'projection': 'certified_fast+canonical_fallback' if args.proj_mode == 1 else 'canonical'},
         'mpoints_per_s': mpoints,
         'e2e': {'value': world * n * p / (e2e_ms * 1e-3), 'unit': 'panos/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms},

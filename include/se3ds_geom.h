@@ -63,6 +63,17 @@ int se3ds_ws_create(int device, size_t max_bytes, size_t l2_chunk_bytes, se3ds_w
 int se3ds_ws_destroy(se3ds_ws* ws);
 int se3ds_ws_bytes(const se3ds_ws* ws, size_t* bytes);
 
+/* Projection mode of the fused path.  0: every point takes the canonical (IEEE-division)
+ * projection; 1 (default): certified fast path -- MUFU approximations, accepted only when both
+ * pixel coordinates are farther than the margin from an integer, canonical fallback otherwise, so
+ * the results are the canonical ones bit for bit; 2: verify -- both are evaluated and compared
+ * (slow; tests).  margin_scale > 0 overrides the margin (dx = W*scale, dy = 2*H*scale pixels).
+ * se3ds_ws_verify_read returns {points, certified, certified-but-different} and the largest
+ * distance by which a fast coordinate fell outside its canonical pixel (x, y; in pixels) since the
+ * last read. */
+int se3ds_ws_projection_mode(se3ds_ws* ws, int mode, float margin_scale);
+int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_dev[2]);
+
 /* Measurement hooks (bench.py): with profiling enabled se3ds_reproject brackets its three kernel
  * classes with cudaEvents on the caller's stream.  se3ds_ws_profile_read synchronises, returns the
  * accumulated device milliseconds of {splat_depth, splat_feat, resolve} since the last read and the

@@ -37,6 +37,8 @@ SIGNATURES = {
     'se3ds_ws_create': [_i, _sz, _sz, _c.POINTER(_vp)],
     'se3ds_ws_destroy': [_vp],
     'se3ds_ws_bytes': [_vp, _c.POINTER(_sz)],
+    'se3ds_ws_projection_mode': [_vp, _i, _f],
+    'se3ds_ws_verify_read': [_vp, _c.POINTER(_c.c_ulonglong * 3), _c.POINTER(_f * 2)],
     'se3ds_ws_profile': [_vp, _i],
     'se3ds_ws_profile_read': [_vp, _c.POINTER(_f * 3), _c.POINTER(_c.c_ulonglong)],
     'se3ds_mask_pano': [_vp, _i, _i, _i, _i, _i, _d, _d, _vp, _vp],
@@ -137,6 +139,17 @@ class Workspace:
     out = ctypes.c_size_t()
     check(load().se3ds_ws_bytes(self.handle, ctypes.byref(out)))
     return out.value
+
+  def projection_mode(self, mode: int, margin_scale: float = 0.0):
+    """0 canonical only, 1 certified fast path (default), 2 verify (see se3ds_geom.h)."""
+    check(load().se3ds_ws_projection_mode(self.handle, int(mode), float(margin_scale)))
+
+  def verify_read(self):
+    """-> dict(points, certified, wrong, max_dev_x, max_dev_y) accumulated in verify mode."""
+    c = (ctypes.c_ulonglong * 3)()
+    d = (ctypes.c_float * 2)()
+    check(load().se3ds_ws_verify_read(self.handle, ctypes.byref(c), ctypes.byref(d)))
+    return dict(points=c[0], certified=c[1], wrong=c[2], max_dev_x=d[0], max_dev_y=d[1])
 
   def profile(self, enable: bool):
     check(load().se3ds_ws_profile(self.handle, int(enable)))

@@ -62,6 +62,8 @@ struct FusedParams {
   int finalize_bins;  // 1: the bin of an owner pixel is complete when K4 runs
   float* bin_out;     // export mode: no owner pixel, the bin is handed to the caller
   float inv_depth_scale;  // RN(1 / depth_scale), computed on the host with an IEEE division
+  FastProj fast;          // certified fast projection (canon_math.cuh)
+  unsigned long long* dbg;  // verify mode: {points, certified, certified-but-wrong, max |dfx| bits<<32 | max |dfy| bits}
 };
 
 __device__ __forceinline__ bool row_masked(const FusedParams& q, int s, int row) {
@@ -118,25 +120,15 @@ __device__ __forceinline__ void red_max_f16x4(uint2* addr, uint2 v) {
   asm volatile("red.global.max.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
-// Block-aggregated update of the reject bin.  Every thread contributes the reduction of its own
-// points; one barrier decides whether the block has anything to add, then one thread compares with
-// the bin (an L2 read -- bins only grow, so a stale value is a safe filter) and issues the REDG.
-__device__ __forceinline__ void bin_min_depth_block(Bin* bin, bool has, uint32_t zneg) {
-  __shared__ uint32_t sm_z[kThreads / 32];
-  if (!__syncthreads_or(has)) return;
-  const uint32_t v = __reduce_max_sync(0xffffffffu, has ? zneg : 0u);
-  if ((threadIdx.x & 31) == 0) sm_z[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t m = sm_z[0];
-#pragma unroll
-    for (int i = 1; i < kThreads / 32; ++i) m = max(m, sm_z[i]);
-    if (m > __ldcg(&bin->zneg)) atomicMax(&bin->zneg, m);
-  }
+// Reject bin.  Every rejected point of a call lands on flat index 0 in the reference.  Here every
+// block reduces its rejected points (REDUX per warp, shared memory across warps) and one thread
+// issues the REDG only if it can change the bin: same-address atomics serialise at one L2 slice
+// (~50-100 ns each), a plain read does not, and bins only grow, so a stale read is a safe filter.
+__device__ __forceinline__ void bin_update_z(Bin* bin, uint32_t zneg) {
+  if (zneg > __ldcg(&bin->zneg)) atomicMax(&bin->zneg, zneg);
 }
 __device__ __forceinline__ void bin_max_feat_block(Bin* bin, bool has, int3 f) {
   __shared__ int sm_f[kThreads / 32][3];
-  if (!__syncthreads_or(has)) return;
   const int r = __reduce_max_sync(0xffffffffu, has ? f.x : 0);
   const int g = __reduce_max_sync(0xffffffffu, has ? f.y : 0);
   const int b = __reduce_max_sync(0xffffffffu, has ? f.z : 0);
@@ -146,7 +138,7 @@ __device__ __forceinline__ void bin_max_feat_block(Bin* bin, bool has, int3 f) {
     int m = sm_f[0][threadIdx.x];
 #pragma unroll
     for (int i = 1; i < kThreads / 32; ++i) m = max(m, sm_f[i][threadIdx.x]);
-    if (m > __ldcg(&bin->f[threadIdx.x])) atomicMax(&bin->f[threadIdx.x], m);
+    if (m > 0 && m > __ldcg(&bin->f[threadIdx.x])) atomicMax(&bin->f[threadIdx.x], m);
   }
 }
 
@@ -182,17 +174,46 @@ __device__ __forceinline__ void load_rgbn(const RGB_T* rgb, size_t pix0, int3 (&
 // FAST: uint8 RGB with project_void == -1 (every reference caller) and, if the compaction is on,
 // unproject_void == -1: a raw colour can then never equal a void class, so validity is decided by
 // the depth and the row mask alone and the per-channel compares disappear.
-template <typename RGB_T, int PPT, bool FAST>
+// PROJ: 0 = canonical projection for every point, 1 = certified fast path; the few points it cannot
+// certify are queued in shared memory and projected canonically by a dense tail loop (so a single
+// uncertified lane does not drag its whole warp through the slow path), 2 = verify (both
+// projections for every point, disagreements counted into q.dbg; results are the canonical ones).
+template <typename RGB_T, int PPT, bool FAST, int PROJ>
 __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
   const SrcIdx ix = src_index<PPT>(q);
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
-  bool bin_has = false;
-  uint32_t bin_z = 0u;
+  uint32_t bin_z = 0u;  // ~ordered(min depth) of this thread's rejected points, 0 = none
+  // deferred points: every warp appends to its own segment (no shared counter, no init barrier)
+  constexpr int kWarps = kThreads / 32, kSeg = 32 * PPT;
+  __shared__ float4 sq_pt[PROJ == 1 ? kThreads * PPT : 1];     // X, Y, Z, rad
+  __shared__ uint32_t sq_meta[PROJ == 1 ? kThreads * PPT : 1];  // pixel | feature-valid << 30 | depth-valid << 31
+  __shared__ int sq_cnt[kWarps];
+  __shared__ uint32_t sm_z[kWarps];
+  int wq = 0;  // entries this warp has queued (warp-uniform)
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* zb = q.zbuf + (size_t)ix.lj * q.HW;
+  const size_t sc_frame = ((size_t)ix.lj * q.S + ix.s) * q.HW;
+  const uint32_t idx_frame = (uint32_t)(ix.s * q.HW);
+
+  // splat (or reject) one projected point; returns its scratch word
+  auto commit = [&](int tpix, float rad, int pix, bool dvalid, bool fvalid) -> uint32_t {
+    const uint32_t dflag = dvalid ? 0u : kScDepthInv;
+    if (fvalid && tpix >= 0) {
+      atomicMin(zb + tpix, ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | (dvalid ? 0u : 1u));
+      return (uint32_t)tpix | dflag;
+    }
+    bin_z = max(bin_z, ~f32_ordered(rad));
+    return kScInvalid | dflag;
+  };
+
+  // Inactive lanes (past the end of a row) run the loop as dropped points, so that the warp-wide
+  // ballots below always see all 32 lanes.
+  const int pix0 = ix.row * q.W + ix.col0;
+  const size_t frame = (size_t)(ix.n * q.S + ix.s) * q.HW;
+  float d[PPT] = {}, sh[PPT] = {}, ch[PPT] = {};
+  int3 raw[PPT] = {};
+  float se = 0.f, ce = 0.f, sx = 0.f, sy = 0.f, sz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
   if (ix.active) {
-    const int pix0 = ix.row * q.W + ix.col0;
-    const size_t frame = (size_t)(ix.n * q.S + ix.s) * q.HW;
-    float d[PPT], sh[PPT], ch[PPT];
-    int3 raw[PPT];
     const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
     if constexpr (PPT == 4) {
       const float4 dv = __ldg(reinterpret_cast<const float4*>(q.depth + frame + pix0));
@@ -205,61 +226,115 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       d[0] = __ldg(q.depth + frame + pix0); sh[0] = __ldg(sin_h + ix.col0); ch[0] = __ldg(cos_h + ix.col0);
     }
     if constexpr (!FAST) load_rgbn<RGB_T, PPT>(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
-    const float se = __ldg(sin_e + ix.row), ce = __ldg(cos_e + ix.row);
+    se = __ldg(sin_e + ix.row); ce = __ldg(cos_e + ix.row);
     const float* sp = q.src_pos + (size_t)(ix.n * q.S + ix.s) * 3;
     const float* tp = q.tgt_pos + (size_t)ix.job * 3;
-    const float sx = __ldg(sp), sy = __ldg(sp + 1), sz = __ldg(sp + 2);
-    const float tx = __ldg(tp), ty = __ldg(tp + 1), tz = __ldg(tp + 2);
-    const bool masked = row_masked(q, ix.s, ix.row);
-    unsigned long long* zb = q.zbuf + (size_t)ix.lj * q.HW;
-    uint32_t scf[PPT];
-    float scr[PPT];
+    sx = __ldg(sp); sy = __ldg(sp + 1); sz = __ldg(sp + 2);
+    tx = __ldg(tp); ty = __ldg(tp + 1); tz = __ldg(tp + 2);
+  }
+  const bool masked = row_masked(q, ix.s, ix.row);
+  uint32_t scf[PPT];
+  float scr[PPT];
 #pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-      // pano_utils.py:220-236
-      const bool dvalid = d[k] > 0.0f && d[k] < 1.0f;
-      const float rad0 = __fmul_rn(__fmul_rn(d[k], q.depth_scale), dvalid ? 1.0f : 0.0f);
-      const float t = __fmul_rn(rad0, se);
-      const float x = __fmul_rn(t, ch[k]);
-      const float y = __fmul_rn(t, sh[k]);
-      const float z = __fmul_rn(rad0, ce);
-      // models.py:225-226 then :273-275 -- two roundings
-      const float X = __fsub_rn(__fadd_rn(x, sx), tx);
-      const float Y = __fsub_rn(__fadd_rn(y, sy), ty);
-      const float Z = __fsub_rn(__fadd_rn(z, sz), tz);
-      bool dropped, fvalid;
-      if constexpr (FAST) {
-        const bool is_void = !dvalid || masked;  // feature is (uv,uv,uv) or (-1,-1,-1)
-        dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && is_void;
-        fvalid = dvalid ? !masked : (q.uv != -1);
-      } else {
-        const int3 f = point_feat(q, !dvalid, masked, raw[k]);
-        dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
-        fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
-      }
-      float rad;
-      const int tpix = project_pixel(X, Y, Z, q.H, q.W, rad);
-      const bool valid = !dropped && fvalid && tpix >= 0;
-      const uint32_t dflag = dvalid ? 0u : kScDepthInv;
-      if (valid) {
-        const uint32_t idx = (uint32_t)(ix.s * q.HW + pix0 + k);
-        atomicMin(zb + tpix, ((unsigned long long)__float_as_uint(rad) << 32) | (idx << 1) | (dvalid ? 0u : 1u));
-      } else if (!dropped) {
-        bin_has = true;
-        bin_z = max(bin_z, ~f32_ordered(rad));
-      }
-      scf[k] = dropped ? kScDropped : (valid ? (uint32_t)tpix | dflag : kScInvalid | dflag);
-      scr[k] = rad;
-    }
-    const size_t sc0 = ((size_t)ix.lj * q.S + ix.s) * q.HW + pix0;
-    if constexpr (PPT == 4) {
-      __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc0), make_uint4(scf[0], scf[1], scf[2], scf[3]));
-      __stcg(reinterpret_cast<float4*>(q.sc_rad + sc0), make_float4(scr[0], scr[1], scr[2], scr[3]));
+  for (int k = 0; k < PPT; ++k) {
+    // pano_utils.py:220-236
+    const bool dvalid = d[k] > 0.0f && d[k] < 1.0f;
+    const float rad0 = __fmul_rn(__fmul_rn(d[k], q.depth_scale), dvalid ? 1.0f : 0.0f);
+    const float t = __fmul_rn(rad0, se);
+    const float x = __fmul_rn(t, ch[k]);
+    const float y = __fmul_rn(t, sh[k]);
+    const float z = __fmul_rn(rad0, ce);
+    // models.py:225-226 then :273-275 -- two roundings
+    const float X = __fsub_rn(__fadd_rn(x, sx), tx);
+    const float Y = __fsub_rn(__fadd_rn(y, sy), ty);
+    const float Z = __fsub_rn(__fadd_rn(z, sz), tz);
+    bool dropped, fvalid;
+    if constexpr (FAST) {
+      const bool is_void = !dvalid || masked;  // feature is (uv,uv,uv) or (-1,-1,-1)
+      dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && is_void;
+      fvalid = dvalid ? !masked : (q.uv != -1);
     } else {
-      q.sc_flat[sc0] = scf[0]; q.sc_rad[sc0] = scr[0];
+      const int3 f = point_feat(q, !dvalid, masked, raw[k]);
+      dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
+      fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
+    }
+    const bool skip = dropped || !ix.active;
+    const float rad = canon_rad(X, Y, Z);
+    scr[k] = rad;
+    scf[k] = kScDropped;
+    if constexpr (PROJ == 0) {
+      if (!skip) scf[k] = commit(project_pixel_rad(X, Y, Z, q.H, q.W, rad), rad, pix0 + k, dvalid, fvalid);
+    } else {
+      int tpix;
+      float fx, fy;
+      const bool certain = project_pixel_fast(X, Y, Z, rad, q.H, q.W, q.fast, tpix, fx, fy);
+      if constexpr (PROJ == 1) {
+        const bool defer = !skip && !certain;
+        if (!skip && certain) scf[k] = commit(tpix, rad, pix0 + k, dvalid, fvalid);
+        // uncertified points go to the warp's queue segment; the tail loop projects them canonically
+        const unsigned dmask = __ballot_sync(0xffffffffu, defer);
+        if (defer) {
+          const int slot = wid * kSeg + wq + __popc(dmask & ((1u << lane) - 1u));
+          sq_pt[slot] = make_float4(X, Y, Z, rad);
+          sq_meta[slot] = (uint32_t)(pix0 + k) | (fvalid ? 1u << 30 : 0u) | (dvalid ? 1u << 31 : 0u);
+        }
+        wq += __popc(dmask);
+      } else if (!skip) {
+        const int exact = project_pixel_rad(X, Y, Z, q.H, q.W, rad);
+        atomicAdd(q.dbg, 1ull);
+        if (certain) {
+          atomicAdd(q.dbg + 1, 1ull);
+          if (exact != tpix) atomicAdd(q.dbg + 2, 1ull);
+        }
+        if (exact >= 0 && fabsf(Z) < 0.984375f * rad) {  // how far the fast coordinates fall outside the canonical pixel
+          const float cx = (float)(exact % q.W), cy = (float)(exact / q.W);
+          const float ex = fmaxf(fmaxf(cx - fx, fx - (cx + 1.0f)), 0.0f), ey = fmaxf(fmaxf(cy - fy, fy - (cy + 1.0f)), 0.0f);
+          atomicMax(q.dbg + 3, ((unsigned long long)__float_as_uint(ex) << 32) | __float_as_uint(ey));
+        }
+        scf[k] = commit(exact, rad, pix0 + k, dvalid, fvalid);
+      }
     }
   }
-  bin_min_depth_block(bin, bin_has, bin_z);
+  if (ix.active) {
+    if constexpr (PPT == 4) {
+      __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc_frame + pix0), make_uint4(scf[0], scf[1], scf[2], scf[3]));
+      __stcg(reinterpret_cast<float4*>(q.sc_rad + sc_frame + pix0), make_float4(scr[0], scr[1], scr[2], scr[3]));
+    } else {
+      q.sc_flat[sc_frame + pix0] = scf[0]; q.sc_rad[sc_frame + pix0] = scr[0];
+    }
+  }
+  // one barrier: publishes the per-warp reject minima and queue lengths (and orders the scratch
+  // stores above before the tail loop's fix-ups)
+  const uint32_t wz = __reduce_max_sync(0xffffffffu, bin_z);
+  if (lane == 0) { sm_z[wid] = wz; sq_cnt[wid] = wq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t m = sm_z[0];
+#pragma unroll
+    for (int i = 1; i < kWarps; ++i) m = max(m, sm_z[i]);
+    if (m) bin_update_z(bin, m);
+  }
+  if constexpr (PROJ == 1) {
+    int total = 0;
+#pragma unroll
+    for (int j = 0; j < kWarps; ++j) total += sq_cnt[j];
+    for (int i = threadIdx.x; i < total; i += kThreads) {
+      int w = 0, base = 0, acc = 0;  // segment that holds the i-th deferred point
+#pragma unroll
+      for (int j = 0; j < kWarps - 1; ++j) {
+        acc += sq_cnt[j];
+        if (i >= acc) { w = j + 1; base = acc; }
+      }
+      const int slot = w * kSeg + (i - base);
+      const float4 pt = sq_pt[slot];
+      const uint32_t m = sq_meta[slot];
+      const int pix = (int)(m & 0x3FFFFFFFu);
+      const int tpix = project_pixel_rad(pt.x, pt.y, pt.z, q.H, q.W, pt.w);
+      bin_z = 0u;
+      q.sc_flat[sc_frame + pix] = commit(tpix, pt.w, pix, m >> 31, (m >> 30) & 1u);
+      if (bin_z) bin_update_z(bin, bin_z);  // a deferred point that turned out to be rejected (rare)
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

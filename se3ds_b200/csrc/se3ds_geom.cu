@@ -63,6 +63,9 @@ struct se3ds_ws {
   DevBuf s_rgb, s_depth, s_src, s_tgt, s_img, s_dep, s_msk, s_win;
   cudaStream_t hstream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> pipe_ev;  // 2 per batch item: inputs on device, outputs computed
+  float margin_scale = 1.0e-6f;  // certification margin: dx = W * scale, dy = 2 * H * scale pixels
+  int proj_mode = 1;  // 0 canonical only, 1 certified fast path (default), 2 verify
+  DevBuf dbg;
   // measurement hooks
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;  // groups of 4 events per profiled chunk
@@ -177,8 +180,11 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
   // FAST feature mode: see splat_depth_kernel
   const bool fast = std::is_same<RGB_T, uint8_t>::value && q.pv == -1 &&
                     (!(q.flags & SE3DS_FLAG_FILTER_VOID) || q.uv == -1);
-  if (fast) splat_depth_kernel<RGB_T, PPT, true><<<grid, block, 0, st>>>(q);
-  else splat_depth_kernel<RGB_T, PPT, false><<<grid, block, 0, st>>>(q);
+  const int proj = ws->proj_mode;
+#define LAUNCH_K2(F, P) splat_depth_kernel<RGB_T, PPT, F, P><<<grid, block, 0, st>>>(q)
+  if (fast) { if (proj == 0) LAUNCH_K2(true, 0); else if (proj == 1) LAUNCH_K2(true, 1); else LAUNCH_K2(true, 2); }
+  else { if (proj == 0) LAUNCH_K2(false, 0); else if (proj == 1) LAUNCH_K2(false, 1); else LAUNCH_K2(false, 2); }
+#undef LAUNCH_K2
   if (ev) CU(cudaEventRecord(ev[1], st));
   splat_feat_kernel<RGB_T, PPT><<<grid, block, 0, st>>>(q);
   if (ev) CU(cudaEventRecord(ev[2], st));
@@ -231,7 +237,7 @@ int se3ds_ws_destroy(se3ds_ws* ws) {
   if (!ws) return SE3DS_OK;
   cudaSetDevice(ws->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&ws->zbuf, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->s_rgb, &ws->s_depth,
+  for (DevBuf* b : {&ws->zbuf, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->dbg, &ws->s_rgb, &ws->s_depth,
                     &ws->s_src, &ws->s_tgt, &ws->s_img, &ws->s_dep, &ws->s_msk, &ws->s_win})
     if (b->p) cudaFree(b->p);
   for (auto& e : ws->tables) cudaFree(e.dev);
@@ -246,6 +252,30 @@ int se3ds_ws_destroy(se3ds_ws* ws) {
 int se3ds_ws_bytes(const se3ds_ws* ws, size_t* bytes) {
   if (!ws || !bytes) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
   *bytes = ws_total(ws);
+  return SE3DS_OK;
+}
+
+int se3ds_ws_projection_mode(se3ds_ws* ws, int mode, float margin_scale) {
+  if (!ws || mode < 0 || mode > 2) return fail(SE3DS_ERR_BAD_ARG, "mode must be 0, 1 or 2");
+  ws->proj_mode = mode;
+  if (margin_scale > 0.0f) ws->margin_scale = margin_scale;
+  return SE3DS_OK;
+}
+
+int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_dev[2]) {
+  if (!ws || !counts || !max_dev) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  counts[0] = counts[1] = counts[2] = 0;
+  max_dev[0] = max_dev[1] = 0.f;
+  if (!ws->dbg.p) return SE3DS_OK;
+  CU(cudaSetDevice(ws->device));
+  CU(cudaDeviceSynchronize());
+  unsigned long long h[4];
+  CU(cudaMemcpy(h, ws->dbg.p, sizeof(h), cudaMemcpyDeviceToHost));
+  CU(cudaMemset(ws->dbg.p, 0, sizeof(h)));
+  counts[0] = h[0]; counts[1] = h[1]; counts[2] = h[2];
+  const unsigned hi = (unsigned)(h[3] >> 32), lo = (unsigned)h[3];
+  memcpy(&max_dev[0], &hi, 4);
+  memcpy(&max_dev[1], &lo, 4);
   return SE3DS_OK;
 }
 
@@ -456,6 +486,12 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   q.uv = unproject_void; q.pv = project_void; q.flags = flags; q.depth_scale = depth_scale;
   q.finalize_bins = (per_job || nchunks_total == 1) ? 1 : 0;
   q.bin_out = bin_out;
+  if (int rc = grow(ws->dbg, 4 * sizeof(unsigned long long), 0, st)) return rc;
+  q.dbg = (unsigned long long*)ws->dbg.p;
+  q.fast.kx = (float)((double)w / (2.0 * 3.141592653589793));
+  q.fast.ky = (float)((double)h / 3.141592653589793);
+  q.fast.dx = (float)w * ws->margin_scale;
+  q.fast.dy = (float)h * 2.0f * ws->margin_scale;
   {
     volatile float one = 1.0f, ds = depth_scale;
     q.inv_depth_scale = one / ds;  // IEEE single division on the host: RN(1 / depth_scale)

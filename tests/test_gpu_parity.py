@@ -177,6 +177,32 @@ def test_fused_all_invalid_depth(mods):
   assert (out['proj_depth'] == 1).all()
 
 
+@pytest.mark.parametrize('h,dist', [(64, 'rand'), (256, 'room'), (512, 'room'), (512, 'rand'), (1024, 'room')])
+def test_certified_fast_projection(mods, h, dist):
+  """The default projection takes MUFU shortcuts only where their result is certified to equal
+  the canonical one.  Verify mode evaluates both for every point: no certified point may differ,
+  and the observed deviation must stay well inside the certification margin."""
+  g, lib = mods['g'], mods['lib']
+  n = 2 if h < 1024 else 1
+  t = _cuda(mods['synth'].make_inputs(n, 2, 2, h, seed=h, dist=dist, sweep=True))
+  ws = lib.Workspace(0)
+  outs = {}
+  for mode in (0, 1, 2):
+    ws.projection_mode(mode)
+    o = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, return_winner=True, workspace=ws)
+    outs[mode] = {k: v.clone() for k, v in o.items()}
+  v = ws.verify_read()
+  ws.close()
+  assert v['points'] == n * 2 * 2 * h * 2 * h
+  assert v['wrong'] == 0, v
+  assert v['certified'] > 0.5 * v['points'], v
+  # margins: dx = W * 1e-6, dy = 2 * H * 1e-6 pixels
+  assert v['max_dev_x'] < 0.5 * (2 * h) * 1e-6 and v['max_dev_y'] < 0.5 * 2 * h * 1e-6, v
+  for mode in (1, 2):
+    for k in outs[0]:
+      assert torch.equal(outs[0][k], outs[mode][k]), (mode, k)
+
+
 def test_export_and_apply_bin(mods):
   """Multi-GPU bin protocol on one GPU: export per shard, reduce, apply == whole-call result."""
   g = mods['g']

@@ -258,16 +258,24 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
       fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
     }
-    const bool skip = dropped || !ix.active;
+    bool skip = dropped || !ix.active;
     const float rad = canon_rad(X, Y, Z);
     scr[k] = rad;
     scf[k] = kScDropped;
+    if (!skip && !fvalid) {
+      // a void feature rejects the point whatever its pixel is (point_cloud_utils.py:146-149):
+      // only its depth matters (reject bin), so the projection is skipped.  Masked rows are whole
+      // rows = whole blocks, so this is branch-uniform.
+      scf[k] = commit(-1, rad, pix0 + k, dvalid, false);
+      skip = true;
+    }
     if constexpr (PROJ == 0) {
       if (!skip) scf[k] = commit(project_pixel_rad(X, Y, Z, q.H, q.W, rad), rad, pix0 + k, dvalid, fvalid);
     } else {
-      int tpix;
-      float fx, fy;
-      const bool certain = project_pixel_fast(X, Y, Z, rad, q.H, q.W, q.fast, tpix, fx, fy);
+      int tpix = -1;
+      float fx = 0.f, fy = 0.f;
+      bool certain = true;
+      if (!skip) certain = project_pixel_fast(X, Y, Z, rad, q.H, q.W, q.fast, tpix, fx, fy);
       if constexpr (PROJ == 1) {
         const bool defer = !skip && !certain;
         if (!skip && certain) scf[k] = commit(tpix, rad, pix0 + k, dvalid, fvalid);

@@ -125,6 +125,18 @@ int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* d
                     int project_void, unsigned flags, float* proj_image, float* proj_depth,
                     float* proj_mask, int32_t* winner_out, float* bin_out, void* stream);
 
+/* Full SE(3) target poses (the reference only translates points and rotates
+ * afterwards in image space, utils/pano_utils.py:306-341): same as se3ds_reproject, but every point
+ * is additionally rotated into the target camera frame, q = R[n,p] * ((local + src) - tgt), with
+ * tgt_rot (N,P,3,3) f32 row-major on the device.  Canonical arithmetic per row:
+ * fma(r2, z, fma(r1, y, r0 * x)).  tgt_rot == NULL is se3ds_reproject bit for bit. */
+int se3ds_reproject_se3(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
+                        const float* src_pos, const float* tgt_pos, const float* tgt_rot, int n, int s,
+                        int p, int h, int w, float depth_scale, double mask_proportion, int mask_frames,
+                        int unproject_void, int project_void, unsigned flags, float* proj_image,
+                        float* proj_depth, float* proj_mask, int32_t* winner_out, float* bin_out,
+                        void* stream);
+
 /* Multi-GPU support for the global reject bin.  When se3ds_reproject is given bin_out (device,
  * 4 floats) the call's reject bin is NOT applied to job 0's pixel (0,0) but exported as
  * (min depth or +inf, max R, max G, max B); ranks reduce their bins (min / max) and the owner of
@@ -142,6 +154,13 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
                          int unproject_void, int project_void, unsigned flags,
                          float* proj_image_host, float* proj_depth_host, float* proj_mask_host,
                          int32_t* winner_out_host);
+
+/* tensorflow_addons.image.interpolate_bilinear as the reference calls it (utils/pano_utils.py:339
+ * rotate_pano, :412 project_perspective_image, :472 get_perspective_from_equirectangular_image;
+ * SURVEY 8f rank 2).  grid (B,H,W,C) f32, query_points (B,Nq,2) f32 in (y,x) order, or (x,y) when
+ * indexing_xy != 0 -> out (B,Nq,C) f32. */
+int se3ds_interpolate_bilinear(const float* grid, const float* query_points, int b, int h, int w, int c,
+                               long long num_queries, int indexing_xy, float* out, void* stream);
 
 /* inference/perturbation_utils.py:23-71 get_proportion_invalid_for_depth, batched over P offsets.
  * offsets (P,3) f32 device, depth (H,W) f32 device -> out (P,) f32 device. */

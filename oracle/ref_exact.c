@@ -221,6 +221,23 @@ void se3ds_oracle_splat(const float* coords, const float* feats, int N, long lon
   free(zbuf); free(fbuf); free(flat); free(rad); free(isvalid);
 }
 
+/* Full SE(3) extension (no reference counterpart; see include/se3ds_geom.h se3ds_reproject_se3):
+ * rotates J clouds (J,4,M) by rot (J,3,3) row-major, row-wise fma(r2, z, fma(r1, y, r0 * x)). */
+void se3ds_oracle_rotate(const float* coords, const float* rot, int J, long long M, float* out) {
+  for (int j = 0; j < J; ++j) {
+    const float* c = coords + (size_t)j * 4 * (size_t)M;
+    const float* r = rot + (size_t)j * 9;
+    float* o = out + (size_t)j * 4 * (size_t)M;
+    for (long long m = 0; m < M; ++m) {
+      float x = c[m], y = c[M + m], z = c[2 * M + m];
+      o[m] = fmaf(r[2], z, fmaf(r[1], y, r[0] * x));
+      o[M + m] = fmaf(r[5], z, fmaf(r[4], y, r[3] * x));
+      o[2 * M + m] = fmaf(r[8], z, fmaf(r[7], y, r[6] * x));
+      o[3 * M + m] = c[3 * M + m];
+    }
+  }
+}
+
 /* Exhaustive-check helper used by tests: evaluates atan2/acos on arrays. */
 void se3ds_oracle_atan2f_array(const float* y, const float* x, float* out, long long n) {
   for (long long i = 0; i < n; ++i) out[i] = se3ds_oracle_atan2f(y[i], x[i]);

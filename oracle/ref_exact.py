@@ -116,9 +116,18 @@ def project_to_feat(transformed_coords, feats, height, width, depth_scale, input
   return o['depth'], o['feat']
 
 
+def rotate(coords, rot):
+  """coords (J,4,M), rot (J,3,3) -> rotated coords, canonical fma order (SE(3) extension)."""
+  coords = np.ascontiguousarray(coords, F32)
+  rot = np.ascontiguousarray(rot, F32).reshape(coords.shape[0], 9)
+  out = np.empty_like(coords)
+  lib().se3ds_oracle_rotate(_p(coords), _p(rot), ctypes.c_int(coords.shape[0]), ctypes.c_longlong(coords.shape[2]), _p(out))
+  return out
+
+
 def reproject(rgb, depth, src_pos, tgt_pos, depth_scale=ref_numpy.DEPTH_SCALE,
               unproject_void=ref_numpy.INVALID_RGB_VALUE, project_void=ref_numpy.INVALID_RGB_VALUE,
-              mask_first_frame=True, mask_proportion=0.125, per_job_bin=False):
+              mask_first_frame=True, mask_proportion=0.125, per_job_bin=False, tgt_rot=None):
   """Canonical twin of ref_numpy.reproject_trajectory, generalised to P target poses.
 
   rgb (N,S,H,W,3) int; depth (N,S,H,W); src_pos (N,S,3); tgt_pos (N,P,3) or (N,3).
@@ -147,6 +156,8 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale=ref_numpy.DEPTH_SCALE,
   feats = np.concatenate(feats, axis=1).astype(F32)  # (N,S*HW,3)
   t = np.concatenate([tgt_pos, np.zeros((n, p, 1), F32)], axis=2)  # (N,P,4)
   rel = (coords[:, None] - t[..., None]).astype(F32).reshape(n * p, 4, -1)
+  if tgt_rot is not None:
+    rel = rotate(rel, np.asarray(tgt_rot, F32).reshape(n * p, 3, 3))
   featj = np.broadcast_to(feats[:, None], (n, p) + feats.shape[1:]).reshape(n * p, -1, 3)
   if per_job_bin:
     outs = [splat(rel[j:j + 1], featj[j:j + 1], h, w, depth_scale, project_void) for j in range(n * p)]

@@ -452,3 +452,134 @@ def equirectangular_pixel_rays(output_height: int) -> np.ndarray:
   ys = -np.cos(pitch)
   zs = np.sin(pitch) * np.cos(heading)
   return np.stack([xs, ys, zs], axis=0).reshape(3, -1).astype(F32)
+
+
+# --------------------------------------------------------------------------
+# "Next" rows: bilinear resampling functions of utils/pano_utils.py
+# --------------------------------------------------------------------------
+def interpolate_bilinear(grid: np.ndarray, query_points: np.ndarray, indexing: str = 'ij') -> np.ndarray:
+  """tensorflow_addons.image.interpolate_bilinear (tfa 0.16.1, dense_image_warp.py), float32.
+
+  grid (B,H,W,C); query_points (B,N,2) in (y,x) order for 'ij', (x,y) for 'xy'.  Floors are clamped
+  to [0, size-2], alphas to [0,1]; interp = a_y * (bottom - top) + top with top = a_x*(tr-tl)+tl.
+  """
+  grid = np.asarray(grid, F32)
+  q = np.asarray(query_points, F32)
+  b, h, w, c = grid.shape
+  order = [0, 1] if indexing == 'ij' else [1, 0]
+  floors, ceils, alphas = [], [], []
+  for i, dim in enumerate(order):
+    queries = q[..., dim]
+    size = grid.shape[i + 1]
+    floor = np.minimum(np.maximum(F32(0), np.floor(queries)), F32(size - 2)).astype(F32)
+    int_floor = floor.astype(np.int32)
+    floors.append(int_floor)
+    ceils.append(int_floor + 1)
+    alpha = np.minimum(np.maximum(F32(0), (queries - floor).astype(F32)), F32(1))
+    alphas.append(alpha[..., None])
+  bi = np.arange(b)[:, None]
+  tl = grid[bi, floors[0], floors[1]]
+  tr = grid[bi, floors[0], ceils[1]]
+  bl = grid[bi, ceils[0], floors[1]]
+  br = grid[bi, ceils[0], ceils[1]]
+  top = alphas[1] * (tr - tl) + tl
+  bottom = alphas[1] * (br - bl) + bl
+  return (alphas[0] * (bottom - top) + top).astype(F32)
+
+
+def get_world_to_image_transform(image_shape, fov, camera_intrinsics=None, rotations=None, rotation_matrix=None):
+  """utils/pano_utils.py:26-89 (float32)."""
+  if camera_intrinsics is None:
+    height, width = F32(image_shape[0]), F32(image_shape[1])
+    fov_y, fov_x = F32(fov[0]), F32(fov[1])
+    fx = F32(0.5) * (width - F32(1.0)) / np.tan(fov_x / F32(2))
+    fy = F32(0.5) * (height - F32(1.0)) / np.tan(fov_y / F32(2))
+    camera_intrinsics = np.array([[fx, 0, F32(0.5) * (width - 1)], [0, fy, F32(0.5) * (height - 1)], [0, 0, 1]], F32)
+  camera_intrinsics = np.asarray(camera_intrinsics, F32)
+  if rotations is not None:
+    rp, rh = F32(rotations[0]), F32(rotations[1])
+    pitch = np.array([[1, 0, 0], [0, np.cos(-rp), -np.sin(-rp)], [0, np.sin(-rp), np.cos(-rp)]], F32)
+    heading = np.array([[np.cos(-rh), 0, np.sin(-rh)], [0, 1, 0], [-np.sin(-rh), 0, np.cos(-rh)]], F32)
+    extrinsics = (pitch @ heading).astype(F32)
+  elif rotation_matrix is not None:
+    extrinsics = np.asarray(rotation_matrix, F32)
+  else:
+    extrinsics = np.eye(3, dtype=F32)
+  return (camera_intrinsics @ extrinsics).astype(F32)
+
+
+def rotate_pano(pano: np.ndarray, matrix: np.ndarray, output_height: Optional[int] = None) -> np.ndarray:
+  """utils/pano_utils.py:306-341."""
+  pano = np.asarray(pano, F32)
+  n, h, w, c = pano.shape
+  if w != h * 2:
+    raise ValueError('Pano width must be twice height.')
+  oh = h if output_height is None else output_height
+  ow = 2 * oh
+  rays = equirectangular_pixel_rays(oh)
+  rot = np.matmul(np.asarray(matrix, F32), rays[None]).astype(F32)
+  x, y, z = rot[:, 0], rot[:, 1], rot[:, 2]
+  with np.errstate(invalid='ignore'):
+    pitch = np.arccos(-y)
+  heading = np.arctan2(x, z)
+  heading_pixels = (heading / F32(2 * math.pi) + F32(0.5)) * F32(w - 1)
+  pitch_pixels = pitch / F32(math.pi) * F32(h - 1)
+  coords = np.stack([pitch_pixels, heading_pixels], axis=-1).astype(F32)
+  return interpolate_bilinear(pano, coords).reshape(n, oh, ow, c)
+
+
+def project_perspective_image(image, fov, output_height, camera_intrinsics=None, rotations=None,
+                              rotation_matrix=None, pad_mode='constant', pad_value=0.0, round_to_nearest=False):
+  """utils/pano_utils.py:344-417."""
+  assert pad_mode in {'reflect', 'constant', 'mean'}, 'Unsupported pad mode: %s' % pad_mode
+  image = np.asarray(image, F32)[None]
+  output_width = 2 * output_height
+  world = equirectangular_pixel_rays(output_height)
+  w2i = get_world_to_image_transform((image.shape[1], image.shape[2]), fov, camera_intrinsics=camera_intrinsics,
+                                     rotations=rotations, rotation_matrix=rotation_matrix)
+  ic = (w2i @ world).astype(F32).T
+  xy, zs = ic[:, :2], ic[:, 2:]
+  with np.errstate(divide='ignore', invalid='ignore'):
+    ic = np.where(np.broadcast_to(zs > 0, xy.shape), xy / zs, -np.ones_like(xy)).astype(F32)
+  if round_to_nearest:
+    ic = np.round(ic)
+  if pad_mode != 'reflect':
+    cv = F32(image.mean(dtype=np.float64)) if pad_mode == 'mean' else F32(pad_value)
+    image = np.pad(image, ((0, 0), (1, 1), (1, 1), (0, 0)), mode='constant', constant_values=cv)
+    ic = ic + F32(1.0)
+  out = interpolate_bilinear(image, ic[None], indexing='xy')
+  return out.reshape(output_height, output_width, -1)
+
+
+def get_perspective_from_equirectangular_image(image, camera_intrinsics, rotation_matrix, height, width):
+  """utils/pano_utils.py:443-476."""
+  image = np.asarray(image, F32)
+  eq_h, eq_w, channels = image.shape
+  x, y = np.meshgrid(np.arange(width), np.arange(height))
+  xyz = np.stack([x, y, np.ones_like(x)], axis=-1).astype(F32)
+  k_inv = np.linalg.inv(np.asarray(camera_intrinsics, F32)).astype(F32)
+  xyz = ((xyz @ k_inv.T).astype(F32) @ np.asarray(rotation_matrix, F32)).astype(F32)
+  norm = np.sqrt(np.sum(xyz * xyz, axis=-1, keepdims=True, dtype=F32))
+  nrm = xyz / norm
+  lon = np.arctan2(nrm[..., 0:1], nrm[..., 2:])
+  lat = np.arcsin(nrm[..., 1:2])
+  u = (lon / F32(2 * np.pi) + F32(0.5)) * F32(eq_w - 1)
+  v = (lat / F32(np.pi) + F32(0.5)) * F32(eq_h - 1)
+  uv = np.concatenate([u, v], axis=-1).astype(F32).reshape(-1, 2)
+  out = interpolate_bilinear(image[None], uv[None], indexing='xy')
+  return out.reshape(height, width, channels)
+
+
+def crop_pano(pano, proportion: float = 0.125, resize_to_original: bool = False):
+  """utils/pano_utils.py:268-303 (resize_to_original=False only: plain crop)."""
+  pano = np.asarray(pano)
+  if pano.ndim == 3:
+    height = pano.shape[0]
+  elif pano.ndim == 4:
+    height = pano.shape[1]
+  else:
+    raise ValueError(f'pano should be of shape (N, H, W, C), got {pano.shape} instead.')
+  if resize_to_original:
+    raise NotImplementedError('antialiased resize is not restated')
+  mh = int(height * proportion)
+  return pano[..., mh:height - mh, :, :]

@@ -42,6 +42,7 @@ struct FusedParams {
   const float* depth;
   const float* src_pos;
   const float* tgt_pos;
+  const float* tgt_rot;  // (N,P,3,3) row-major or nullptr (translation only, as the reference)
   const float* tab;  // sin_e[H], cos_e[H], sin_h[W], cos_h[W]
   unsigned long long* zbuf;
   uint2* fbuf;
@@ -232,6 +233,12 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     sx = __ldg(sp); sy = __ldg(sp + 1); sz = __ldg(sp + 2);
     tx = __ldg(tp); ty = __ldg(tp + 1); tz = __ldg(tp + 2);
   }
+  float rot[9];
+  const bool rotate = q.tgt_rot != nullptr;
+  if (rotate) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rot[i] = __ldg(q.tgt_rot + (size_t)ix.job * 9 + i);
+  }
   const bool masked = row_masked(q, ix.s, ix.row);
   uint32_t scf[PPT];
   float scr[PPT];
@@ -245,9 +252,15 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     const float y = __fmul_rn(t, sh[k]);
     const float z = __fmul_rn(rad0, ce);
     // models.py:225-226 then :273-275 -- two roundings
-    const float X = __fsub_rn(__fadd_rn(x, sx), tx);
-    const float Y = __fsub_rn(__fadd_rn(y, sy), ty);
-    const float Z = __fsub_rn(__fadd_rn(z, sz), tz);
+    float X = __fsub_rn(__fadd_rn(x, sx), tx);
+    float Y = __fsub_rn(__fadd_rn(y, sy), ty);
+    float Z = __fsub_rn(__fadd_rn(z, sz), tz);
+    if (rotate) {  // into the target camera frame: row-wise fma(r2, z, fma(r1, y, r0 * x))
+      const float a = X, b = Y, c = Z;
+      X = __fmaf_rn(rot[2], c, __fmaf_rn(rot[1], b, __fmul_rn(rot[0], a)));
+      Y = __fmaf_rn(rot[5], c, __fmaf_rn(rot[4], b, __fmul_rn(rot[3], a)));
+      Z = __fmaf_rn(rot[8], c, __fmaf_rn(rot[7], b, __fmul_rn(rot[6], a)));
+    }
     bool dropped, fvalid;
     if constexpr (FAST) {
       const bool is_void = !dvalid || masked;  // feature is (uv,uv,uv) or (-1,-1,-1)
@@ -670,6 +683,33 @@ __global__ void __launch_bounds__(kThreads) cloud_resolve_kernel(const CloudPara
   q.depth_out[i] = __fdiv_rn(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale);
   if (q.winner_out) q.winner_out[i] = (has && radw <= q.depth_scale) ? (int)((uint32_t)key >> 1) : -1;
   q.zbuf[i] = kZArmed;
+}
+
+// tensorflow_addons.image.interpolate_bilinear (called at utils/pano_utils.py:339,412,472):
+// grid (B,H,W,C) f32, queries (B,Nq,2) f32 -> out (B,Nq,C).  xy = 1: queries are (x, y), else (y, x).
+// Floors clamp to [0, size-2], alphas to [0,1]; a_y * (bottom - top) + top, top = a_x * (tr - tl) + tl.
+__global__ void __launch_bounds__(kThreads) interpolate_bilinear_kernel(const float* __restrict__ grid,
+                                                                       const float* __restrict__ queries, int B, int H,
+                                                                       int W, int C, long long Nq, int xy,
+                                                                       float* __restrict__ out) {
+  const long long total = (long long)B * Nq;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int b = (int)(i / Nq);
+    const float2 qq = __ldg(reinterpret_cast<const float2*>(queries) + i);
+    const float qy = xy ? qq.y : qq.x, qx = xy ? qq.x : qq.y;
+    const float fy = fminf(fmaxf(0.0f, floorf(qy)), (float)(H - 2)), fx = fminf(fmaxf(0.0f, floorf(qx)), (float)(W - 2));
+    const float ay = fminf(fmaxf(0.0f, __fsub_rn(qy, fy)), 1.0f), ax = fminf(fmaxf(0.0f, __fsub_rn(qx, fx)), 1.0f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const float* tl = grid + (((size_t)b * H + y0) * W + x0) * C;
+    const float* bl = tl + (size_t)W * C;
+    float* o = out + (size_t)i * C;
+    for (int c = 0; c < C; ++c) {
+      const float vtl = __ldg(tl + c), vtr = __ldg(tl + C + c), vbl = __ldg(bl + c), vbr = __ldg(bl + C + c);
+      const float top = __fadd_rn(__fmul_rn(ax, __fsub_rn(vtr, vtl)), vtl);
+      const float bot = __fadd_rn(__fmul_rn(ax, __fsub_rn(vbr, vbl)), vbl);
+      o[c] = __fadd_rn(__fmul_rn(ay, __fsub_rn(bot, top)), top);
+    }
+  }
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {

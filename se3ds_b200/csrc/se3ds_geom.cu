@@ -425,7 +425,7 @@ struct HostPipe {
 };
 
 int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
-                   const float* src_pos, const float* tgt_pos, int n, int s, int p, int h, int w,
+                   const float* src_pos, const float* tgt_pos, const float* tgt_rot, int n, int s, int p, int h, int w,
                    float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
                    int project_void, unsigned flags, float* proj_image, float* proj_depth,
                    float* proj_mask, int32_t* winner_out, float* bin_out, void* stream, const HostPipe* pipe) {
@@ -476,7 +476,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   if (int rc = get_tables(ws, h, w, st, &tab)) return rc;
 
   FusedParams q{};
-  q.rgb = rgb; q.depth = depth; q.src_pos = src_pos; q.tgt_pos = tgt_pos; q.tab = tab;
+  q.rgb = rgb; q.depth = depth; q.src_pos = src_pos; q.tgt_pos = tgt_pos; q.tgt_rot = tgt_rot; q.tab = tab;
   q.zbuf = (unsigned long long*)ws->zbuf.p; q.fbuf = (uint2*)ws->fbuf.p;
   q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.bins = (Bin*)ws->bins.p;
   q.out_image = proj_image; q.out_depth = proj_depth; q.out_mask = proj_mask; q.out_winner = winner_out;
@@ -547,9 +547,20 @@ int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* d
                     float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
                     int project_void, unsigned flags, float* proj_image, float* proj_depth,
                     float* proj_mask, int32_t* winner_out, float* bin_out, void* stream) {
-  return reproject_core(ws, rgb, rgb_dtype, depth, src_pos, tgt_pos, n, s, p, h, w, depth_scale, mask_proportion,
-                        mask_frames, unproject_void, project_void, flags, proj_image, proj_depth, proj_mask,
-                        winner_out, bin_out, stream, nullptr);
+  return reproject_core(ws, rgb, rgb_dtype, depth, src_pos, tgt_pos, nullptr, n, s, p, h, w, depth_scale,
+                        mask_proportion, mask_frames, unproject_void, project_void, flags, proj_image, proj_depth,
+                        proj_mask, winner_out, bin_out, stream, nullptr);
+}
+
+int se3ds_reproject_se3(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
+                        const float* src_pos, const float* tgt_pos, const float* tgt_rot, int n, int s,
+                        int p, int h, int w, float depth_scale, double mask_proportion, int mask_frames,
+                        int unproject_void, int project_void, unsigned flags, float* proj_image,
+                        float* proj_depth, float* proj_mask, int32_t* winner_out, float* bin_out,
+                        void* stream) {
+  return reproject_core(ws, rgb, rgb_dtype, depth, src_pos, tgt_pos, tgt_rot, n, s, p, h, w, depth_scale,
+                        mask_proportion, mask_frames, unproject_void, project_void, flags, proj_image, proj_depth,
+                        proj_mask, winner_out, bin_out, stream, nullptr);
 }
 
 int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, const float* depth_host,
@@ -598,7 +609,7 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
   HostPipe pipe{ws->d2h_stream, ws->pipe_ev.data(), ws->pipe_ev.data() + n, proj_image_host, proj_depth_host,
                 proj_mask_host, winner_out_host};
   if (int rc = reproject_core(ws, ws->s_rgb.p, rgb_dtype, (const float*)ws->s_depth.p, (const float*)ws->s_src.p,
-                              (const float*)ws->s_tgt.p, n, s, p, h, w, depth_scale, mask_proportion, mask_frames,
+                              (const float*)ws->s_tgt.p, nullptr, n, s, p, h, w, depth_scale, mask_proportion, mask_frames,
                               unproject_void, project_void, flags, (float*)ws->s_img.p, (float*)ws->s_dep.p,
                               (float*)ws->s_msk.p, winner_out_host ? (int32_t*)ws->s_win.p : nullptr, nullptr, st, &pipe))
     return rc;
@@ -612,6 +623,18 @@ int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, floa
   if (!bin || !proj_image || !proj_depth || !proj_mask) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
   apply_bin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bin, depth_scale, proj_image, proj_depth, proj_mask);
   return launch_check("apply_bin_kernel");
+}
+
+int se3ds_interpolate_bilinear(const float* grid, const float* query_points, int b, int h, int w, int c,
+                               long long num_queries, int indexing_xy, float* out, void* stream) {
+  if (!grid || !query_points || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (b < 0 || h < 2 || w < 2 || c <= 0 || num_queries < 0) return fail(SE3DS_ERR_BAD_SHAPE, "Grid must be at least 2x2 with shape (B,H,W,C)");
+  const long long total = (long long)b * num_queries;
+  if (total == 0) return SE3DS_OK;
+  const int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32);
+  interpolate_bilinear_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(grid, query_points, b, h, w, c, num_queries,
+                                                                            indexing_xy, out);
+  return launch_check("interpolate_bilinear_kernel");
 }
 
 int se3ds_proportion_invalid(const float* offsets, int p, const float* depth, int h, int w,

@@ -64,7 +64,7 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
               unproject_void: int = constants.INVALID_RGB_VALUE, project_void: int = constants.INVALID_RGB_VALUE,
               filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
               export_bin: bool = False, out: Optional[Dict[str, torch.Tensor]] = None,
-              workspace: Optional[_lib.Workspace] = None) -> Dict[str, torch.Tensor]:
+              workspace: Optional[_lib.Workspace] = None, tgt_rot=None) -> Dict[str, torch.Tensor]:
   """Re-projects S source RGB-D panos per item onto P target poses per item.
 
   Args:
@@ -74,6 +74,8 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
     mask_frames: the first `mask_frames` frames get mask_pano(., mask_proportion, -1).
     unproject_void / project_void / filter_void: see `Conventions`.
     per_job_bin: every (item,pose) job is its own reference call (batch 1).
+    tgt_rot: optional (N,P,3,3) rotations into the target camera frames (full SE(3) poses; the
+      reference only translates, models/models.py:120-125): q = R (local + src - tgt).
   Returns dict with proj_image (J,H,W,3), proj_depth (J,H,W,1), proj_mask (J,H,W,1),
   blurred_mask (zeros, shares no memory), and optionally winner (J,H,W) int32, bin (4,).
   """
@@ -96,11 +98,14 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
   binb = buf('bin', (4,)) if export_bin else None
   flags = (_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0)
   ws = workspace or _lib.default_workspace(dev)
-  _lib.check(_lib.load().se3ds_reproject(
+  if tgt_rot is not None:
+    tgt_rot = _lib.require_cuda(torch.as_tensor(tgt_rot), 'tgt_rot').to(device=dev, dtype=torch.float32)
+    tgt_rot = tgt_rot.reshape(n, p, 3, 3).contiguous()
+  _lib.check(_lib.load().se3ds_reproject_se3(
       ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
-      n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),
-      int(project_void), flags, _lib.ptr(image), _lib.ptr(pdepth), _lib.ptr(mask), _lib.ptr(winner),
-      _lib.ptr(binb), _lib.stream_handle(dev)))
+      _lib.ptr(tgt_rot), n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames),
+      int(unproject_void), int(project_void), flags, _lib.ptr(image), _lib.ptr(pdepth), _lib.ptr(mask),
+      _lib.ptr(winner), _lib.ptr(binb), _lib.stream_handle(dev)))
   return out
 
 

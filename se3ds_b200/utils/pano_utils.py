@@ -7,7 +7,8 @@ definition of atan2 / acos / sin / cos that both the kernels and the oracle foll
 """
 from __future__ import annotations
 
-from typing import Tuple
+import math
+from typing import Optional, Tuple
 
 import torch
 
@@ -109,3 +110,161 @@ def project_feats_to_equirectangular(feats: torch.Tensor, xyz1: torch.Tensor, he
   """
   return point_cloud_utils._project(xyz1, feats, height, width, depth_scale, void_class, 0, mode=0,
                                     return_winner=return_winner)
+
+
+# ------------------------------------------------------------------------------------------
+# "Next" rows: the bilinear resampling functions of the reference's pano_utils.
+# The gather (the heavy part) is the CUDA kernel behind se3ds_interpolate_bilinear; the per-pixel
+# query coordinates are a handful of elementwise device ops, as in the reference.
+# ------------------------------------------------------------------------------------------
+def _tf_linspace(start: float, stop: float, num: int, device) -> torch.Tensor:
+  """tf.linspace in float32: exact end points, start + delta * i inside."""
+  start_t = torch.tensor(start, dtype=torch.float32, device=device)
+  stop_t = torch.tensor(stop, dtype=torch.float32, device=device)
+  if num == 1:
+    return start_t[None]
+  delta = (stop_t - start_t) / torch.tensor(float(num - 1), dtype=torch.float32, device=device)
+  inner = start_t + delta * torch.arange(1, num - 1, dtype=torch.float32, device=device)
+  return torch.cat([start_t[None], inner, stop_t[None]])
+
+
+def interpolate_bilinear(grid: torch.Tensor, query_points: torch.Tensor, indexing: str = 'ij') -> torch.Tensor:
+  """tensorflow_addons.image.interpolate_bilinear: grid (B,H,W,C), query_points (B,N,2) -> (B,N,C)."""
+  if indexing not in ('ij', 'xy'):
+    raise ValueError("Indexing mode must be 'ij' or 'xy'")
+  grid = _as_tensor(grid, 'grid', validate_only=True)
+  query_points = _as_tensor(query_points, 'query_points', validate_only=True)
+  if grid.dim() != 4:
+    raise ValueError('Grid must be 4D Tensor')
+  if query_points.dim() != 3 or query_points.shape[2] != 2:
+    raise ValueError('Query points must be 3 dimensional and size 2 in dim 2.')
+  if grid.shape[1] < 2 or grid.shape[2] < 2:
+    raise ValueError('Grid must be at least 2x2.')
+  grid = _as_tensor(grid, 'grid').to(torch.float32).contiguous()
+  query_points = _as_tensor(query_points, 'query_points').to(device=grid.device, dtype=torch.float32).contiguous()
+  b, h, w, c = grid.shape
+  nq = query_points.shape[1]
+  out = torch.empty((b, nq, c), dtype=torch.float32, device=grid.device)
+  _lib.check(_lib.load().se3ds_interpolate_bilinear(_lib.ptr(grid), _lib.ptr(query_points), b, h, w, c, nq,
+                                                    int(indexing == 'xy'), _lib.ptr(out),
+                                                    _lib.stream_handle(grid.device)))
+  return out
+
+
+def equirectangular_pixel_rays(output_height: int, device=None) -> torch.Tensor:
+  """Unit-ball point of every equirectangular pixel, (3, H*2H) (reference pano_utils.py:92-114):
+  x right, y down, z forward at the image centre."""
+  device = device or torch.device('cuda', torch.cuda.current_device())
+  output_width = int(float(output_height) * 2)
+  heading = _tf_linspace(-math.pi, math.pi, output_width, device)
+  pitch = _tf_linspace(0.0, math.pi, output_height, device)
+  heading, pitch = heading[None, :], pitch[:, None]
+  xs = torch.sin(pitch) * torch.sin(heading)
+  ys = (-torch.cos(pitch)).expand(output_height, output_width)
+  zs = torch.sin(pitch) * torch.cos(heading)
+  return torch.stack([xs, ys, zs], dim=0).reshape(3, -1)
+
+
+def get_world_to_image_transform(image_shape, fov, camera_intrinsics: Optional[torch.Tensor] = None,
+                                 rotations=None, rotation_matrix: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """3x3 world-to-image transform (reference pano_utils.py:26-89); tiny, evaluated on the host."""
+  f32 = torch.float32
+  if camera_intrinsics is None:
+    height, width = float(image_shape[0]), float(image_shape[1])
+    fov = torch.as_tensor(fov, dtype=f32).cpu()
+    fov_y, fov_x = fov[0], fov[1]
+    fx = 0.5 * (width - 1.0) / torch.tan(fov_x / 2)
+    fy = 0.5 * (height - 1.0) / torch.tan(fov_y / 2)
+    camera_intrinsics = torch.tensor([[fx, 0, 0.5 * (width - 1)], [0, fy, 0.5 * (height - 1)], [0., 0, 1]], dtype=f32)
+  camera_intrinsics = torch.as_tensor(camera_intrinsics, dtype=f32).cpu()
+  if rotations is not None:
+    rot = torch.as_tensor(rotations, dtype=f32).cpu()
+    rp, rh = rot[0], rot[1]
+    pitch = torch.tensor([[1., 0, 0], [0, torch.cos(-rp), -torch.sin(-rp)], [0, torch.sin(-rp), torch.cos(-rp)]], dtype=f32)
+    heading = torch.tensor([[torch.cos(-rh), 0, torch.sin(-rh)], [0., 1, 0], [-torch.sin(-rh), 0, torch.cos(-rh)]], dtype=f32)
+    extrinsics = pitch @ heading
+  elif rotation_matrix is not None:
+    extrinsics = torch.as_tensor(rotation_matrix, dtype=f32).cpu()
+  else:
+    extrinsics = torch.eye(3, dtype=f32)
+  return camera_intrinsics @ extrinsics
+
+
+def crop_pano(pano: torch.Tensor, proportion: float = 0.125, method: str = 'bilinear',
+              resize_to_original: bool = False) -> torch.Tensor:
+  """Removes the top and bottom `proportion` rows (reference pano_utils.py:268-303)."""
+  pano = _as_tensor(pano, 'pano', validate_only=True)
+  if pano.dim() == 3:
+    height = pano.shape[0]
+  elif pano.dim() == 4:
+    height = pano.shape[1]
+  else:
+    raise ValueError(f'pano should be of shape (N, H, W, C), got {tuple(pano.shape)} instead.')
+  if resize_to_original:
+    raise NotImplementedError('crop_pano(resize_to_original=True) needs the antialiased resize; not built yet')
+  masked_height = int(height * proportion)
+  return pano[..., masked_height:height - masked_height, :, :].contiguous()
+
+
+def rotate_pano(pano: torch.Tensor, matrix: torch.Tensor, output_height: Optional[int] = None) -> torch.Tensor:
+  """Rotates an equirectangular pano by (N,3,3) matrices (reference pano_utils.py:306-341)."""
+  pano = _as_tensor(pano, 'pano', validate_only=True)
+  if pano.dim() != 4:
+    raise ValueError(f'pano should be (N, H, W, C), got {tuple(pano.shape)}')
+  n, h, w, c = pano.shape
+  if w != h * 2:
+    raise ValueError('Pano width must be twice height.')
+  pano = _as_tensor(pano, 'pano').to(torch.float32)
+  oh = h if output_height is None else int(output_height)
+  matrix = _as_tensor(matrix, 'matrix').to(device=pano.device, dtype=torch.float32)
+  rays = equirectangular_pixel_rays(oh, pano.device)
+  rot = torch.matmul(matrix, rays[None])
+  x, y, z = rot[:, 0], rot[:, 1], rot[:, 2]
+  pitch = torch.acos(-y)
+  heading = torch.atan2(x, z)
+  heading_pixels = (heading / (2 * math.pi) + 0.5) * (w - 1)
+  pitch_pixels = pitch / math.pi * (h - 1)
+  coords = torch.stack([pitch_pixels, heading_pixels], dim=-1)
+  return interpolate_bilinear(pano, coords).reshape(n, oh, 2 * oh, c)
+
+
+def project_perspective_image(image, fov, output_height, camera_intrinsics=None, rotations=None,
+                              rotation_matrix=None, pad_mode='constant', pad_value=0.0, round_to_nearest=False):
+  """Perspective (h,w,c) -> equirectangular (H,2H,c) (reference pano_utils.py:344-417)."""
+  assert pad_mode in {'reflect', 'constant', 'mean'}, ('Unsupported pad mode: %s' % pad_mode)
+  image = _as_tensor(image, 'image').to(torch.float32)[None]
+  output_width = 2 * output_height
+  world = equirectangular_pixel_rays(output_height, image.device)
+  w2i = get_world_to_image_transform((image.shape[1], image.shape[2]), fov, camera_intrinsics=camera_intrinsics,
+                                     rotations=rotations, rotation_matrix=rotation_matrix).to(image.device)
+  ic = (w2i @ world).t()
+  xy, zs = ic[:, :2], ic[:, 2:]
+  ic = torch.where((zs > 0).expand(-1, 2), xy / zs, -torch.ones_like(xy))
+  if round_to_nearest:
+    ic = torch.round(ic)
+  if pad_mode != 'reflect':
+    cv = float(image.mean()) if pad_mode == 'mean' else float(pad_value)
+    image = torch.nn.functional.pad(image, (0, 0, 1, 1, 1, 1), mode='constant', value=cv)
+    ic = ic + 1.
+  out = interpolate_bilinear(image, ic[None], indexing='xy')
+  return out.reshape(output_height, output_width, -1)
+
+
+def get_perspective_from_equirectangular_image(image, camera_intrinsics, rotation_matrix, height, width):
+  """Equirectangular (He,We,C) -> perspective (height,width,C) (reference pano_utils.py:443-476)."""
+  image = _as_tensor(image, 'image').to(torch.float32)
+  eq_height, eq_width, channels = image.shape
+  dev = image.device
+  y, x = torch.meshgrid(torch.arange(height, device=dev), torch.arange(width, device=dev), indexing='ij')
+  xyz = torch.stack([x, y, torch.ones_like(x)], dim=-1).to(torch.float32)
+  k_inv = torch.linalg.inv(torch.as_tensor(camera_intrinsics, dtype=torch.float32).cpu()).to(dev)
+  rot = torch.as_tensor(rotation_matrix, dtype=torch.float32).to(dev)
+  xyz = (xyz @ k_inv.t()) @ rot
+  nrm = xyz / torch.linalg.norm(xyz, dim=-1, keepdim=True)
+  lon = torch.atan2(nrm[..., 0:1], nrm[..., 2:])
+  lat = torch.asin(nrm[..., 1:2])
+  u = (lon / (2 * math.pi) + 0.5) * (eq_width - 1)
+  v = (lat / math.pi + 0.5) * (eq_height - 1)
+  uv = torch.cat([u, v], dim=-1).reshape(-1, 2)
+  out = interpolate_bilinear(image[None], uv[None], indexing='xy')
+  return out.reshape(height, width, channels)

@@ -159,6 +159,39 @@ def test_fused_chunked_equals_unchunked(mods):
   ws.close(); ws1.close()
 
 
+def _rotations(n, p, seed):
+  rng = np.random.default_rng(seed)
+  a = rng.standard_normal((n * p, 3, 3))
+  qm, _ = np.linalg.qr(a)
+  qm *= np.sign(np.linalg.det(qm))[:, None, None]
+  return qm.reshape(n, p, 3, 3).astype(F32)
+
+
+def test_se3_rotation(mods):
+  """full SE(3) target poses inside the fused kernel.  R = I is the reference path
+  bit for bit; random rotations match the oracle's canonical fma chain bit for bit and the float64
+  rotation to within the usual boundary-case fraction."""
+  g = mods['g']
+  inp = mods['synth'].make_inputs(2, 2, 2, 128, seed=21, dist='room', sweep=True)
+  t = _cuda(inp)
+  eye = np.broadcast_to(np.eye(3, dtype=F32), (2, 2, 3, 3)).copy()
+  base = {k: v.clone() for k, v in g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, return_winner=True).items()}
+  same = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, return_winner=True, tgt_rot=eye)
+  for k in base:
+    assert torch.equal(base[k], same[k]), k
+  rot = _rotations(2, 2, 3)
+  out = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, return_winner=True, tgt_rot=rot)
+  ref = X.reproject(inp['rgb'].astype(np.int32), inp['depth'], inp['src_pos'], inp['tgt_pos'], mask_first_frame=True, tgt_rot=rot)
+  np.testing.assert_array_equal(out['winner'].cpu().numpy(), ref['winner'])
+  np.testing.assert_array_equal(out['proj_depth'].cpu().numpy(), ref['depth'])
+  np.testing.assert_array_equal(out['proj_mask'].cpu().numpy(), ref['mask'])
+  np.testing.assert_array_equal(out['proj_image'].cpu().numpy(), ref['image'])
+  # a rotation moves pixels but keeps every depth: the multiset of hit depths is (almost) unchanged
+  d0 = np.sort(base['proj_depth'].cpu().numpy()[base['winner'].cpu().numpy() >= 0])
+  d1 = np.sort(ref['depth'][ref['winner'] >= 0])
+  assert abs(len(d0) - len(d1)) < 0.2 * len(d0)
+
+
 def test_fused_identity_reprojection(mods):
   """models/models_test.py:64-68: project at the source position => >= 95 % RGB equal."""
   inp = mods['synth'].make_inputs(1, 1, 1, 128, seed=8, dist='rand')

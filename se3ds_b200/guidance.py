@@ -277,6 +277,46 @@ class GuidanceMemory(object):
       out['proj_semantic'] = self._project_semantic(position)
     return out
 
+  def rgb_cloud(self):
+    """Materialises the RGB memory as the reference keeps it: rgb_coords (N,4,M'), rgb (N,M',3) int32
+    after masking, unprojection, offset and compaction (models/models.py:211-245)."""
+    m = self._memory
+    coords, feats = [], []
+    for rgb, depth, pos, masked in zip(m.rgb, m.depth, m.position, m.masked):
+      rgb = rgb.to(torch.int32)
+      if masked:
+        rgb = pano_utils.mask_pano(rgb, masked_region_value=constants.INVALID_RGB_VALUE)
+      xyz1, f = pano_utils.equirectangular_to_pointcloud(rgb, depth, constants.INVALID_RGB_VALUE, self.depth_scale)
+      xyz1 = xyz1 + torch.cat([pos, torch.zeros_like(pos[:, :1])], dim=1)[:, :, None]
+      valid = (f != constants.INVALID_RGB_VALUE).any(dim=0).any(dim=-1)
+      coords.append(xyz1[:, :, valid])
+      feats.append(f[:, valid])
+    if not coords:
+      dev = torch.device('cuda', torch.cuda.current_device())
+      return torch.zeros((self.batch_size, 4, 0), device=dev), torch.zeros((self.batch_size, 0, 3), dtype=torch.int32, device=dev)
+    return torch.cat(coords, dim=2), torch.cat(feats, dim=1)
+
+  def write_memory_as_pointcloud(self, filename):
+    """Writes memory at batch position 0 to an ASCII .ply file, byte for byte in the reference's
+    format (models/models.py:154-178)."""
+    coords, rgb = self.rgb_cloud()
+    xyz_pts = coords[0, 0:3].cpu().numpy().T
+    rgb_pts = rgb[0].cpu().numpy()
+    with open(filename, 'w') as fp:
+      fp.write('ply\n')
+      fp.write('format ascii 1.0 \n')
+      fp.write('element vertex %d\n' % xyz_pts.shape[0])
+      fp.write('property float x\n')
+      fp.write('property float y\n')
+      fp.write('property float z\n')
+      fp.write('property uchar red\n')
+      fp.write('property uchar green\n')
+      fp.write('property uchar blue\n')
+      fp.write('end_header\n')
+      for i in range(xyz_pts.shape[0]):
+        fp.write('{} {} {} {} {} {} \n'.format(xyz_pts[i, 0], xyz_pts[i, 1], xyz_pts[i, 2], rgb_pts[i, 0],
+                                               rgb_pts[i, 1], rgb_pts[i, 2]))
+
   def _project_semantic(self, position):
     """models/models.py:217-219,229-231,276-278 through the materialising compat path."""
     m = self._memory

@@ -452,6 +452,29 @@ def test_guidance_memory_matches_reference_flow(mods):
     g.GuidanceMemory(64, batch_size=2)
 
 
+def test_ply_export(mods, tmp_path):
+  """models/models.py:154-178: the only on-disk format on the path."""
+  g = mods['g']
+  inp = mods['synth'].make_inputs(1, 2, 1, 16, seed=16, dist='room')
+  sem = np.ones((1, 16, 32, 1), np.uint8)
+  mem = g.GuidanceMemory(16)
+  ora = R.SE3DSMemoryOracle(16)
+  for k in range(2):
+    mem.add_to_memory(torch.as_tensor(inp['rgb'][:, k]), torch.as_tensor(sem), torch.as_tensor(inp['depth'][:, k]),
+                      torch.as_tensor(inp['src_pos'][:, k]))
+    ora.add_to_memory(inp['rgb'][:, k], sem, inp['depth'][:, k], inp['src_pos'][:, k])
+  path = tmp_path / 'cloud.ply'
+  mem.write_memory_as_pointcloud(str(path))
+  lines = path.read_text().splitlines()
+  state = ora.get_memory_state()
+  m = state.rgb_coords.shape[2]
+  assert lines[:3] == ['ply', 'format ascii 1.0 ', 'element vertex %d' % m] and lines[9] == 'end_header'
+  assert len(lines) == 10 + m
+  vals = np.array([l.split() for l in lines[10:]], dtype=np.float64)
+  np.testing.assert_allclose(vals[:, :3], state.rgb_coords[0, :3].T, atol=1e-5)
+  np.testing.assert_array_equal(vals[:, 3:].astype(np.int32), state.rgb[0])
+
+
 def test_error_behaviour(mods):
   """Same exception types as the reference (pano_utils.py:190-202, point_cloud_utils.py:120-122)."""
   pano, pc = mods['pano'], mods['pc']

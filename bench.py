@@ -196,6 +196,7 @@ def main():
   ap.add_argument('--e2e-steps', type=int, default=20)
   ap.add_argument('--chunk-mb', type=int, default=0, help='workspace L2 chunk size (0 = library default)')
   ap.add_argument('--n-override', type=int, default=0, help='override the batch size of the config (memory-bounded runs)')
+  ap.add_argument('--key64', action='store_true', help='force the 64-bit packed depth|index z-buffer key')
   ap.add_argument('--proj-mode', type=int, default=1, help='0 canonical projection only, 1 certified fast path (default)')
   args = ap.parse_args()
   cfg = dict(CONFIGS[args.config])
@@ -234,7 +235,8 @@ def main():
     if gen_n < n:
       inp = {k: np.concatenate([v] * (n // gen_n), axis=0) for k, v in inp.items()}
     t = {k: torch.as_tensor(v).to(dev) for k, v in inp.items()}
-    plans.append(guidance.prepare(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, workspace=ws))
+    plans.append(guidance.prepare(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, workspace=ws,
+                                  key64=args.key64))
   host_inp = {k: torch.as_tensor(v).pin_memory() for k, v in inp.items()}
 
   stream = torch.cuda.Stream(dev)
@@ -335,7 +337,7 @@ def main():
         'config': {'workload': workload_name(args.config, cfg, args.dist), 'per_gpu_batch': n,
                    'cache': f'inputs+outputs rotate over a ring of {ring} sets ({ring * set_bytes >> 20} MiB > 2x L2)',
                    'launch': 'cuda_graph_replay' if graphs is not None else 'stream', 'parallelism': f'dp{world}',
-                   'chunk_mb': args.chunk_mb or 'default',
+                   'chunk_mb': args.chunk_mb or 'default', 'zbuffer_key': 'u64 depth|index' if args.key64 else 'u32 depth (no winner index requested)',
                    'projection': 'certified_fast+canonical_fallback' if args.proj_mode == 1 else 'canonical'},
         'mpoints_per_s': mpoints,
         'e2e': {'value': world * n * p / (e2e_ms * 1e-3), 'unit': 'panos/s', 'h2d_bytes_per_step': h2d,

@@ -52,6 +52,11 @@ typedef enum { SE3DS_U8 = 0, SE3DS_I32 = 1, SE3DS_F32 = 2 } se3ds_dtype;
                                      the whole call is one reference call; the global reject bin
                                      (utils/point_cloud_utils.py:150-153) is job 0's pixel (0,0). */
 
+#define SE3DS_FLAG_KEY64 4u       /* always splat with the 64-bit packed depth|point-index key.  By
+                                     default that key is used when winner_out is requested; without
+                                     it a 32-bit depth-only key gives the same guidance tensors
+                                     with half the z-buffer traffic. */
+
 int se3ds_version(void);
 const char* se3ds_status_string(int status);
 const char* se3ds_last_error(void);

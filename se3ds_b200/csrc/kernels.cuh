@@ -44,7 +44,8 @@ struct FusedParams {
   const float* tgt_pos;
   const float* tgt_rot;  // (N,P,3,3) row-major or nullptr (translation only, as the reference)
   const float* tab;  // sin_e[H], cos_e[H], sin_h[W], cos_h[W]
-  unsigned long long* zbuf;
+  unsigned long long* zbuf;  // KEY64: depth_bits << 32 | point_index << 1 | depth_invalid
+  uint32_t* zbuf32;          // !KEY64: depth bits only (no winner index requested)
   uint2* fbuf;
   uint32_t* sc_flat;
   float* sc_rad;
@@ -179,7 +180,10 @@ __device__ __forceinline__ void load_rgbn(const RGB_T* rgb, size_t pix0, int3 (&
 // certify are queued in shared memory and projected canonically by a dense tail loop (so a single
 // uncertified lane does not drag its whole warp through the slow path), 2 = verify (both
 // projections for every point, disagreements counted into q.dbg; results are the canonical ones).
-template <typename RGB_T, int PPT, bool FAST, int PROJ>
+// KEY64: the z-buffer holds the 64-bit packed (depth | point index) key -- the deterministic winner
+// (nearest depth, lowest index).  When the caller does not ask for winner indices the same minimum
+// depth comes from a 32-bit key (depth bits only): half the z-buffer traffic, identical guidance.
+template <typename RGB_T, int PPT, bool FAST, int PROJ, bool KEY64>
 __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
   const SrcIdx ix = src_index<PPT>(q);
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
   int wq = 0;  // entries this warp has queued (warp-uniform)
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long* zb = q.zbuf + (size_t)ix.lj * q.HW;
+  uint32_t* zb32 = q.zbuf32 + (size_t)ix.lj * q.HW;
   const size_t sc_frame = ((size_t)ix.lj * q.S + ix.s) * q.HW;
   const uint32_t idx_frame = (uint32_t)(ix.s * q.HW);
 
@@ -200,7 +205,10 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
   auto commit = [&](int tpix, float rad, int pix, bool dvalid, bool fvalid) -> uint32_t {
     const uint32_t dflag = dvalid ? 0u : kScDepthInv;
     if (fvalid && tpix >= 0) {
-      atomicMin(zb + tpix, ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | (dvalid ? 0u : 1u));
+      if constexpr (KEY64)
+        atomicMin(zb + tpix, ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | (dvalid ? 0u : 1u));
+      else
+        atomicMin(zb32 + tpix, __float_as_uint(rad));
       return (uint32_t)tpix | dflag;
     }
     bin_z = max(bin_z, ~f32_ordered(rad));
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
 // ------------------------------------------------------------------------------------------
 // K3: tolerance test + per-channel max of the surviving features
 // ------------------------------------------------------------------------------------------
-template <typename RGB_T, int PPT>
+template <typename RGB_T, int PPT, bool KEY64>
 __global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams q) {
   const SrcIdx ix = src_index<PPT>(q);
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
@@ -384,13 +392,15 @@ __global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams 
     }
     load_rgbn<RGB_T, PPT>(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
     const unsigned long long* zb = q.zbuf + (size_t)ix.lj * q.HW;
+    const uint32_t* zb32 = q.zbuf32 + (size_t)ix.lj * q.HW;
     uint2* fb = q.fbuf + (size_t)ix.lj * q.HW;
-    // issue the z-buffer gathers first, then consume
-    unsigned long long key[PPT];
+    // issue the z-buffer gathers first, then consume (only the depth half of the key is needed)
+    uint32_t zbits[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       const bool haspix = !(scf[k] & (kScDropped | kScInvalid));
-      key[k] = haspix ? __ldcg(zb + (scf[k] & kScPixMask)) : kZArmed;
+      if constexpr (KEY64) zbits[k] = haspix ? (uint32_t)(__ldcg(zb + (scf[k] & kScPixMask)) >> 32) : 0xFFFFFFFFu;
+      else zbits[k] = haspix ? __ldcg(zb32 + (scf[k] & kScPixMask)) : 0xFFFFFFFFu;
     }
     const bool masked = row_masked(q, ix.s, ix.row);
 #pragma unroll
@@ -401,7 +411,7 @@ __global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams 
       bool rejected = live && !haspix;
       if (haspix) {
         // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
-        const float zmin = fminf(__uint_as_float((uint32_t)(key[k] >> 32)), q.depth_scale);
+        const float zmin = fminf(__uint_as_float(zbits[k]), q.depth_scale);  // armed bits are a NaN: fminf -> depth_scale
         const bool keep = scr[k] < __fadd_rn(zmin, 0.1f);
         if (keep) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
         rejected = !keep;
@@ -428,7 +438,7 @@ __device__ __forceinline__ float clip01_div255(float v) {
   return fminf(fmaxf(q1, 0.0f), 1.0f);
 }
 
-template <int PPT>
+template <int PPT, bool KEY64>
 __global__ void __launch_bounds__(kThreads, 12) resolve_kernel(const FusedParams q) {
   const int lj = blockIdx.z;
   int n, p;
@@ -439,17 +449,25 @@ __global__ void __launch_bounds__(kThreads, 12) resolve_kernel(const FusedParams
   if (col0 >= q.W) return;
   const int pix0 = row * q.W + col0;
   unsigned long long* zb = q.zbuf + (size_t)lj * q.HW + pix0;
+  uint32_t* zb32 = q.zbuf32 + (size_t)lj * q.HW + pix0;
   uint2* fb = q.fbuf + (size_t)lj * q.HW + pix0;
-  unsigned long long key[PPT];
+  unsigned long long key[PPT];  // !KEY64: depth bits in the upper half, index bits all ones
   uint2 fv[PPT];
   if constexpr (PPT == 4) {
-    const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(zb)), b = __ldcg(reinterpret_cast<const ulonglong2*>(zb + 2));
-    key[0] = a.x; key[1] = a.y; key[2] = b.x; key[3] = b.y;
+    if constexpr (KEY64) {
+      const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(zb)), b = __ldcg(reinterpret_cast<const ulonglong2*>(zb + 2));
+      key[0] = a.x; key[1] = a.y; key[2] = b.x; key[3] = b.y;
+    } else {
+      const uint4 a = __ldcg(reinterpret_cast<const uint4*>(zb32));
+      key[0] = ((unsigned long long)a.x << 32) | 0xFFFFFFFFu; key[1] = ((unsigned long long)a.y << 32) | 0xFFFFFFFFu;
+      key[2] = ((unsigned long long)a.z << 32) | 0xFFFFFFFFu; key[3] = ((unsigned long long)a.w << 32) | 0xFFFFFFFFu;
+    }
     const uint4 c = __ldcg(reinterpret_cast<const uint4*>(fb)), e = __ldcg(reinterpret_cast<const uint4*>(fb + 2));
     fv[0] = make_uint2(c.x, c.y); fv[1] = make_uint2(c.z, c.w);
     fv[2] = make_uint2(e.x, e.y); fv[3] = make_uint2(e.z, e.w);
   } else {
-    key[0] = zb[0]; fv[0] = fb[0];
+    key[0] = KEY64 ? zb[0] : (((unsigned long long)zb32[0] << 32) | 0xFFFFFFFFu);
+    fv[0] = fb[0];
   }
   const bool per_job = q.flags & SE3DS_FLAG_BIN_PER_JOB;
   float od[PPT], om[PPT], oi[3 * PPT];
@@ -490,20 +508,22 @@ __global__ void __launch_bounds__(kThreads, 12) resolve_kernel(const FusedParams
     __stcs(im + 2, make_float4(oi[8], oi[9], oi[10], oi[11]));
     if (q.out_winner) __stcs(reinterpret_cast<int4*>(q.out_winner + o), make_int4(ow[0], ow[1], ow[2], ow[3]));
     // re-arm only what was touched (a touched feature buffer entry implies a touched z-buffer entry)
-    const ulonglong2 arm = make_ulonglong2(kZArmed, kZArmed);
-    if (key[0] != kZArmed || key[1] != kZArmed) {
-      *reinterpret_cast<ulonglong2*>(zb) = arm;
-      *reinterpret_cast<uint4*>(fb) = make_uint4(0, 0, 0, 0);
+    const bool t01 = key[0] != kZArmed || key[1] != kZArmed, t23 = key[2] != kZArmed || key[3] != kZArmed;
+    if constexpr (KEY64) {
+      const ulonglong2 arm = make_ulonglong2(kZArmed, kZArmed);
+      if (t01) *reinterpret_cast<ulonglong2*>(zb) = arm;
+      if (t23) *reinterpret_cast<ulonglong2*>(zb + 2) = arm;
+    } else {
+      if (t01 || t23) *reinterpret_cast<uint4*>(zb32) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     }
-    if (key[2] != kZArmed || key[3] != kZArmed) {
-      *reinterpret_cast<ulonglong2*>(zb + 2) = arm;
-      *reinterpret_cast<uint4*>(fb + 2) = make_uint4(0, 0, 0, 0);
-    }
+    if (t01) *reinterpret_cast<uint4*>(fb) = make_uint4(0, 0, 0, 0);
+    if (t23) *reinterpret_cast<uint4*>(fb + 2) = make_uint4(0, 0, 0, 0);
   } else {
     q.out_depth[o] = od[0]; q.out_mask[o] = om[0];
     for (int c = 0; c < 3; ++c) q.out_image[o * 3 + c] = oi[c];
     if (q.out_winner) q.out_winner[o] = ow[0];
-    zb[0] = kZArmed; fb[0] = make_uint2(0, 0);
+    if constexpr (KEY64) zb[0] = kZArmed; else zb32[0] = 0xFFFFFFFFu;
+    fb[0] = make_uint2(0, 0);
   }
 }
 

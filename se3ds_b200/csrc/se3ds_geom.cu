@@ -56,7 +56,7 @@ constexpr size_t kDefaultChunkBytes = (size_t)112 << 20;
 struct se3ds_ws {
   int device = 0;
   size_t max_bytes = kDefaultMaxBytes, chunk_bytes = kDefaultChunkBytes;
-  DevBuf zbuf, fbuf, scf, scr, bins, cbin;
+  DevBuf zbuf, zbuf32, fbuf, scf, scr, bins, cbin;
   std::vector<TableEntry> tables;
   bool dirty = false;  // a pass was enqueued but its resolve (which re-arms) was not
   // staging of the host-buffer entry point
@@ -76,7 +76,7 @@ struct se3ds_ws {
 namespace {
 
 size_t ws_total(const se3ds_ws* ws) {
-  size_t t = ws->zbuf.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->bins.cap + ws->cbin.cap +
+  size_t t = ws->zbuf.cap + ws->zbuf32.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->bins.cap + ws->cbin.cap +
              ws->s_rgb.cap + ws->s_depth.cap + ws->s_src.cap + ws->s_tgt.cap + ws->s_img.cap +
              ws->s_dep.cap + ws->s_msk.cap + ws->s_win.cap;
   for (const auto& e : ws->tables) t += (size_t)(2 * e.h + 2 * e.w) * sizeof(float);
@@ -102,6 +102,7 @@ int grow(DevBuf& b, size_t bytes, int pattern, cudaStream_t stream) {
 
 int rearm(se3ds_ws* ws, cudaStream_t stream) {
   if (ws->zbuf.p) CU(cudaMemsetAsync(ws->zbuf.p, 0xFF, ws->zbuf.cap, stream));
+  if (ws->zbuf32.p) CU(cudaMemsetAsync(ws->zbuf32.p, 0xFF, ws->zbuf32.cap, stream));
   if (ws->fbuf.p) CU(cudaMemsetAsync(ws->fbuf.p, 0, ws->fbuf.cap, stream));
   if (ws->bins.p) CU(cudaMemsetAsync(ws->bins.p, 0, ws->bins.cap, stream));
   if (ws->cbin.p) CU(cudaMemsetAsync(ws->cbin.p, 0, ws->cbin.cap, stream));
@@ -160,7 +161,7 @@ int launch_check(const char* what) {
   return SE3DS_OK;
 }
 
-template <typename RGB_T, int PPT>
+template <typename RGB_T, int PPT, bool KEY64>
 int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st) {
   const int gx = (q.W + kThreads * PPT - 1) / (kThreads * PPT);
   const int jobs = nitems * q.PC;
@@ -181,22 +182,23 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
   const bool fast = std::is_same<RGB_T, uint8_t>::value && q.pv == -1 &&
                     (!(q.flags & SE3DS_FLAG_FILTER_VOID) || q.uv == -1);
   const int proj = ws->proj_mode;
-#define LAUNCH_K2(F, P) splat_depth_kernel<RGB_T, PPT, F, P><<<grid, block, 0, st>>>(q)
+#define LAUNCH_K2(F, P) splat_depth_kernel<RGB_T, PPT, F, P, KEY64><<<grid, block, 0, st>>>(q)
   if (fast) { if (proj == 0) LAUNCH_K2(true, 0); else if (proj == 1) LAUNCH_K2(true, 1); else LAUNCH_K2(true, 2); }
   else { if (proj == 0) LAUNCH_K2(false, 0); else if (proj == 1) LAUNCH_K2(false, 1); else LAUNCH_K2(false, 2); }
 #undef LAUNCH_K2
   if (ev) CU(cudaEventRecord(ev[1], st));
-  splat_feat_kernel<RGB_T, PPT><<<grid, block, 0, st>>>(q);
+  splat_feat_kernel<RGB_T, PPT, KEY64><<<grid, block, 0, st>>>(q);
   if (ev) CU(cudaEventRecord(ev[2], st));
-  resolve_kernel<PPT><<<dim3(gx, q.H, jobs), block, 0, st>>>(q);
+  resolve_kernel<PPT, KEY64><<<dim3(gx, q.H, jobs), block, 0, st>>>(q);
   if (ev) CU(cudaEventRecord(ev[3], st));
   ws->launches += 3;
   return launch_check("fused reprojection kernels");
 }
 
 template <typename RGB_T>
-int run_chunk(se3ds_ws* ws, const FusedParams& q, int nitems, bool vec, cudaStream_t st) {
-  return vec ? run_chunk_t<RGB_T, 4>(ws, q, nitems, st) : run_chunk_t<RGB_T, 1>(ws, q, nitems, st);
+int run_chunk(se3ds_ws* ws, const FusedParams& q, int nitems, bool vec, bool key64, cudaStream_t st) {
+  if (key64) return vec ? run_chunk_t<RGB_T, 4, true>(ws, q, nitems, st) : run_chunk_t<RGB_T, 1, true>(ws, q, nitems, st);
+  return vec ? run_chunk_t<RGB_T, 4, false>(ws, q, nitems, st) : run_chunk_t<RGB_T, 1, false>(ws, q, nitems, st);
 }
 
 }  // namespace
@@ -237,7 +239,7 @@ int se3ds_ws_destroy(se3ds_ws* ws) {
   if (!ws) return SE3DS_OK;
   cudaSetDevice(ws->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&ws->zbuf, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->dbg, &ws->s_rgb, &ws->s_depth,
+  for (DevBuf* b : {&ws->zbuf, &ws->zbuf32, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->dbg, &ws->s_rgb, &ws->s_depth,
                     &ws->s_src, &ws->s_tgt, &ws->s_img, &ws->s_dep, &ws->s_msk, &ws->s_win})
     if (b->p) cudaFree(b->p);
   for (auto& e : ws->tables) cudaFree(e.dev);
@@ -467,7 +469,10 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
 
   if (ws->dirty)
     if (int rc = rearm(ws, st)) return rc;
-  if (int rc = grow(ws->zbuf, (size_t)chunk_jobs * hw * 8, 0xFF, st)) return rc;
+  // 64-bit packed (depth | index) keys when winner indices are wanted (or forced), else depth-only keys
+  const bool key64 = winner_out != nullptr || (flags & SE3DS_FLAG_KEY64);
+  if (key64) { if (int rc = grow(ws->zbuf, (size_t)chunk_jobs * hw * 8, 0xFF, st)) return rc; }
+  else { if (int rc = grow(ws->zbuf32, (size_t)chunk_jobs * hw * 4, 0xFF, st)) return rc; }
   if (int rc = grow(ws->fbuf, (size_t)chunk_jobs * hw * 8, 0, st)) return rc;
   if (int rc = grow(ws->scf, (size_t)chunk_jobs * s * hw * 4, -1, st)) return rc;
   if (int rc = grow(ws->scr, (size_t)chunk_jobs * s * hw * 4, -1, st)) return rc;
@@ -477,7 +482,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
 
   FusedParams q{};
   q.rgb = rgb; q.depth = depth; q.src_pos = src_pos; q.tgt_pos = tgt_pos; q.tgt_rot = tgt_rot; q.tab = tab;
-  q.zbuf = (unsigned long long*)ws->zbuf.p; q.fbuf = (uint2*)ws->fbuf.p;
+  q.zbuf = (unsigned long long*)ws->zbuf.p; q.zbuf32 = (uint32_t*)ws->zbuf32.p; q.fbuf = (uint2*)ws->fbuf.p;
   q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.bins = (Bin*)ws->bins.p;
   q.out_image = proj_image; q.out_depth = proj_depth; q.out_mask = proj_mask; q.out_winner = winner_out;
   q.N = n; q.S = s; q.P = p; q.H = h; q.W = w; q.HW = (int)hw;
@@ -504,7 +509,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
     if (pipe) CU(cudaStreamWaitEvent(st, pipe->in_ready[n0], 0));
     for (int p0 = 0; p0 < p; p0 += PC) {
       q.n0 = n0; q.p0 = p0; q.PC = std::min(PC, p - p0);
-      const int rc = rgb_dtype == SE3DS_U8 ? run_chunk<uint8_t>(ws, q, nitems, vec, st) : run_chunk<int>(ws, q, nitems, vec, st);
+      const int rc = rgb_dtype == SE3DS_U8 ? run_chunk<uint8_t>(ws, q, nitems, vec, key64, st) : run_chunk<int>(ws, q, nitems, vec, key64, st);
       if (rc) return rc;
     }
     if (pipe) {  // items_per_chunk == 1 here: ship item n0's guidance tensors

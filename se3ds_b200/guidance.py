@@ -64,7 +64,7 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
               unproject_void: int = constants.INVALID_RGB_VALUE, project_void: int = constants.INVALID_RGB_VALUE,
               filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
               export_bin: bool = False, out: Optional[Dict[str, torch.Tensor]] = None,
-              workspace: Optional[_lib.Workspace] = None, tgt_rot=None) -> Dict[str, torch.Tensor]:
+              workspace: Optional[_lib.Workspace] = None, tgt_rot=None, key64: bool = False) -> Dict[str, torch.Tensor]:
   """Re-projects S source RGB-D panos per item onto P target poses per item.
 
   Args:
@@ -96,7 +96,8 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
   mask = buf('proj_mask', (j, h, w, 1))
   winner = buf('winner', (j, h, w), torch.int32) if return_winner else None
   binb = buf('bin', (4,)) if export_bin else None
-  flags = (_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0)
+  flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
+           (_lib.FLAG_KEY64 if key64 else 0))
   ws = workspace or _lib.default_workspace(dev)
   if tgt_rot is not None:
     tgt_rot = _lib.require_cuda(torch.as_tensor(tgt_rot), 'tgt_rot').to(device=dev, dtype=torch.float32)
@@ -129,7 +130,7 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
             mask_proportion: float = 0.125, mask_frames: int = 0,
             unproject_void: int = constants.INVALID_RGB_VALUE, project_void: int = constants.INVALID_RGB_VALUE,
             filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
-            workspace: Optional[_lib.Workspace] = None) -> PreparedReprojection:
+            workspace: Optional[_lib.Workspace] = None, key64: bool = False) -> PreparedReprojection:
   """Same arguments as `reproject`; allocates the outputs once and returns a PreparedReprojection."""
   rgb, depth, src_pos, tgt_pos = _prep(rgb, depth, src_pos, tgt_pos, True)
   n, s, h, w, _ = rgb.shape
@@ -140,7 +141,8 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
              proj_mask=torch.empty((j, h, w, 1), device=dev))
   if return_winner:
     out['winner'] = torch.empty((j, h, w), dtype=torch.int32, device=dev)
-  flags = (_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0)
+  flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
+           (_lib.FLAG_KEY64 if key64 else 0))
   ws = workspace or _lib.default_workspace(dev)
   args = (ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
           n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),

@@ -47,6 +47,14 @@ def _check_fused(mods, inp, conv=None, mask_frames=0, per_job_bin=False, ws=None
   np.testing.assert_array_equal(out['proj_depth'].cpu().numpy(), ref['depth'])
   np.testing.assert_array_equal(out['proj_mask'].cpu().numpy(), ref['mask'])
   np.testing.assert_array_equal(out['proj_image'].cpu().numpy(), ref['image'])
+  # without winner indices the z-buffer key is 32-bit (depth only): the guidance must not change
+  for key64 in (False, True):
+    o2 = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=mask_frames,
+                     unproject_void=conv.unproject_void, project_void=conv.project_void,
+                     filter_void=conv.filter_void, per_job_bin=per_job_bin, workspace=ws, key64=key64)
+    assert 'winner' not in o2
+    for k in ('proj_depth', 'proj_mask', 'proj_image'):
+      assert torch.equal(o2[k], out[k]), (k, key64)
   return out, ref
 
 

@@ -70,6 +70,7 @@ class ClockSampler(threading.Thread):
       self.nv = pynvml
       self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
       self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+      pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)  # warm the NVML path up before the timed region
     except Exception:  # pylint: disable=broad-except
       self.nv = None
 
@@ -93,7 +94,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(k)
       except Exception:  # pylint: disable=broad-except
         pass
-      time.sleep(0.002)
+      time.sleep(0.001)
 
   def stop(self):
     self._stop_evt.set()
@@ -186,7 +187,7 @@ def workload_name(name, c, dist):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=1000)
+  ap.add_argument('--steps', type=int, default=2000)
   ap.add_argument('--warmup', type=int, default=20)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))

@@ -294,6 +294,23 @@ def test_full_size_c2_against_oracle(mods):
   assert 0.2 < hit < 1.0
 
 
+def test_full_size_c3_c4_shapes_against_oracle(mods):
+  """BASELINE.json configs[2] / configs[3] at full resolution, reduced batch: 4 prior frames fused
+  into one target (gan_manager conventions), and a 16-pose sweep of one pano."""
+  inp = mods['synth'].make_inputs(3, 4, 1, 512, seed=17, dist='room')
+  _check_fused(mods, inp, conv=mods['g'].GAN_MANAGER, mask_frames=1)
+  inp = mods['synth'].make_inputs(1, 1, 16, 512, seed=18, dist='room', sweep=True)
+  _check_fused(mods, inp, per_job_bin=True)
+
+
+def test_stress_resolution_2048x4096(mods):
+  """BASELINE.json configs[4] resolution (8.4 M pixels per pano, 23-bit pixel indices, one job per
+  chunk), two accumulated frames, against the oracle."""
+  inp = mods['synth'].make_inputs(1, 2, 1, 2048, seed=19, dist='room')
+  out, ref = _check_fused(mods, inp, mask_frames=1)
+  assert (ref['winner'] >= 0).mean() > 0.3
+
+
 # ------------------------------------------------------------------------------------------
 # compat path: the reference's own function signatures
 # ------------------------------------------------------------------------------------------

@@ -93,7 +93,8 @@ int se3ds_mask_pano(const void* pano, int dtype, int n, int h, int w, int c, dou
 
 /* utils/pano_utils.py:164-242  equirectangular_to_pointcloud (size_mult == 1).
  * feats (N,H,W,C) in_dtype, depth (N,H,W) f32 -> xyz1 (N,4,H*W) f32 planar, feats_out (N,H*W,C)
- * out_dtype ('nearest' keeps the dtype, 'bilinear' -> f32).  Requires w == 2*h. */
+ * out_dtype ('nearest' keeps the dtype, 'bilinear' -> f32).  size_mult != 1: resize first with
+ * se3ds_resize, then pass the scaled (h, w). */
 int se3ds_unproject_equirect(se3ds_ws* ws, const void* feats, int in_dtype, const float* depth, int n,
                              int h, int w, int c, double void_class, float depth_scale,
                              float* xyz1_out, void* feats_out, int out_dtype, void* stream);
@@ -159,6 +160,12 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
                          int unproject_void, int project_void, unsigned flags,
                          float* proj_image_host, float* proj_depth_host, float* proj_mask_host,
                          int32_t* winner_out_host);
+
+/* tf.image.resize with half-pixel centres, as utils/pano_utils.py:203-208 uses it when
+ * size_mult != 1: in (N,H,W,C) of `dtype` -> out (N,out_h,out_w,C); bilinear == 0: 'nearest', the
+ * dtype is kept; bilinear != 0: 'bilinear', out is f32. */
+int se3ds_resize(const void* in, int dtype, int n, int h, int w, int c, int out_h, int out_w, int bilinear,
+                 void* out, void* stream);
 
 /* tensorflow_addons.image.interpolate_bilinear as the reference calls it (utils/pano_utils.py:339
  * rotate_pano, :412 project_perspective_image, :472 get_perspective_from_equirectangular_image;

@@ -76,6 +76,10 @@ def equirectangular_to_pointcloud(feats, depth, void_class, depth_scale, size_mu
   # argument validation and feature handling are shared with the literal restatement
   _, ff = ref_numpy.equirectangular_to_pointcloud(feats, depth, void_class, depth_scale, size_mult,
                                                   interpolation_method)
+  depth = np.asarray(depth, F32)
+  if size_mult != 1.0:
+    n, h, w = depth.shape
+    depth = ref_numpy.tf_resize(depth[..., None], (int(h * size_mult), int(w * size_mult)), 'nearest')[..., 0]
   xyz1, _ = unproject(depth, depth_scale)
   return xyz1, ff
 

@@ -111,6 +111,39 @@ def equirect_angle_tables(height: int, width: int) -> Tuple[np.ndarray, np.ndarr
   return elevation, heading
 
 
+def tf_resize(images: np.ndarray, size, method: str) -> np.ndarray:
+  """tf.image.resize (TF 2.x: half_pixel_centers=True) for (N,H,W,C).
+  'nearest': in = min(floor((out + 0.5) * scale), in_size - 1), dtype kept
+  (resize_nearest_neighbor_op.cc, HalfPixelScalerForNN).  'bilinear': in = (out + 0.5) * scale - 0.5,
+  lower = max(floor(in), 0), upper = min(ceil(in), in_size - 1), lerp = in - floor(in); float32 output
+  (resize_bilinear_op.cc, compute_interpolation_weights).  scale = in_size / out_size in float32."""
+  images = np.asarray(images)
+  n, h, w, c = images.shape
+  oh, ow = int(size[0]), int(size[1])
+  sy, sx = F32(h) / F32(oh), F32(w) / F32(ow)
+  if method == 'nearest':
+    iy = np.minimum(np.floor((np.arange(oh, dtype=F32) + F32(0.5)) * sy), h - 1).astype(np.int64)
+    ix = np.minimum(np.floor((np.arange(ow, dtype=F32) + F32(0.5)) * sx), w - 1).astype(np.int64)
+    return images[:, iy][:, :, ix]
+  if method != 'bilinear':
+    raise NotImplementedError(method)
+  def weights(out_size, in_size, scale):
+    pos = ((np.arange(out_size, dtype=F32) + F32(0.5)) * scale - F32(0.5)).astype(F32)
+    fl = np.floor(pos)
+    lower = np.maximum(fl, 0).astype(np.int64)
+    upper = np.minimum(np.ceil(pos), in_size - 1).astype(np.int64)
+    return lower, upper, (pos - fl).astype(F32)
+  ylo, yhi, yl = weights(oh, h, sy)
+  xlo, xhi, xl = weights(ow, w, sx)
+  img = images.astype(F32)
+  tl = img[:, ylo][:, :, xlo]; tr = img[:, ylo][:, :, xhi]
+  bl = img[:, yhi][:, :, xlo]; br = img[:, yhi][:, :, xhi]
+  xl = xl[None, None, :, None]; yl = yl[None, :, None, None]
+  top = tl + (tr - tl) * xl
+  bottom = bl + (br - bl) * xl
+  return (top + (bottom - top) * yl).astype(F32)
+
+
 def equirectangular_to_pointcloud(feats: np.ndarray, depth: np.ndarray, void_class,
                                   depth_scale: float, size_mult: float = 1.0,
                                   interpolation_method: str = 'nearest'):
@@ -124,8 +157,6 @@ def equirectangular_to_pointcloud(feats: np.ndarray, depth: np.ndarray, void_cla
                      f' got {feats.shape} instead.')
   if void_class < 0.0 and feats.dtype in (np.uint8, np.uint16, np.uint32, np.uint64):
     raise ValueError('feats datatype must be signed if the void class is negative')
-  if size_mult != 1.0:
-    raise NotImplementedError('oracle restates size_mult == 1.0 only')
   is_scalar_feat = feats.ndim == 3
   if is_scalar_feat:
     feats = feats[..., None]
@@ -133,6 +164,10 @@ def equirectangular_to_pointcloud(feats: np.ndarray, depth: np.ndarray, void_cla
   assert width == 2 * height, 'Expected equirectangular input images'
   pano_depth = depth.astype(F32)
   pano_feats = feats.astype(F32) if interpolation_method != 'nearest' else feats
+  if size_mult != 1.0:  # pano_utils.py:203-208: depth is resized 'nearest', features with the given method
+    height, width = int(height * size_mult), int(width * size_mult)
+    pano_depth = tf_resize(pano_depth[..., None], (height, width), 'nearest')[..., 0]
+    pano_feats = tf_resize(feats, (height, width), interpolation_method)
   elevation, heading = equirect_angle_tables(height, width)
   depth_mask = np.logical_and(pano_depth > 0, pano_depth < F32(1.0)).astype(F32)
   rad = (pano_depth * F32(depth_scale)) * depth_mask

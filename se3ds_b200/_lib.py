@@ -52,6 +52,7 @@ SIGNATURES = {
     'se3ds_apply_bin': [_vp, _f, _vp, _vp, _vp, _vp],
     'se3ds_reproject_host': [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp,
                              _vp, _vp],
+    'se3ds_resize': [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     'se3ds_interpolate_bilinear': [_vp, _vp, _i, _i, _i, _i, _ll, _i, _vp, _vp],
     'se3ds_proportion_invalid': [_vp, _i, _vp, _i, _i, _f, _f, _vp, _vp],
 }

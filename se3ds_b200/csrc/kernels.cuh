@@ -732,6 +732,39 @@ __global__ void __launch_bounds__(kThreads) interpolate_bilinear_kernel(const fl
   }
 }
 
+// tf.image.resize with half_pixel_centers (TF 2.x), used by equirectangular_to_pointcloud when
+// size_mult != 1 (utils/pano_utils.py:203-208).  NEAREST keeps the dtype:
+// in = min(floor((out + 0.5) * scale), in_size - 1); BILINEAR returns float32:
+// in = (out + 0.5) * scale - 0.5, lower = max(floor(in), 0), upper = min(ceil(in), in_size - 1).
+template <typename TI, typename TO, bool BILINEAR>
+__global__ void __launch_bounds__(kThreads) resize_kernel(const TI* __restrict__ in, int N, int H, int W, int C, int OH,
+                                                         int OW, TO* __restrict__ out) {
+  const float sy = __fdiv_rn((float)H, (float)OH), sx = __fdiv_rn((float)W, (float)OW);
+  const long long total = (long long)N * OH * OW;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int ox = (int)(i % OW), oy = (int)((i / OW) % OH), b = (int)(i / ((long long)OW * OH));
+    const TI* img = in + (size_t)b * H * W * C;
+    TO* o = out + (size_t)i * C;
+    if constexpr (!BILINEAR) {
+      const int iy = min((int)floorf(__fmul_rn(__fadd_rn((float)oy, 0.5f), sy)), H - 1);
+      const int ix = min((int)floorf(__fmul_rn(__fadd_rn((float)ox, 0.5f), sx)), W - 1);
+      for (int c = 0; c < C; ++c) o[c] = (TO)img[((size_t)iy * W + ix) * C + c];
+    } else {
+      const float py = __fsub_rn(__fmul_rn(__fadd_rn((float)oy, 0.5f), sy), 0.5f), px = __fsub_rn(__fmul_rn(__fadd_rn((float)ox, 0.5f), sx), 0.5f);
+      const float fy = floorf(py), fx = floorf(px);
+      const int y0 = max((int)fy, 0), y1 = min((int)ceilf(py), H - 1), x0 = max((int)fx, 0), x1 = min((int)ceilf(px), W - 1);
+      const float ly = __fsub_rn(py, fy), lx = __fsub_rn(px, fx);
+      for (int c = 0; c < C; ++c) {
+        const float tl = (float)img[((size_t)y0 * W + x0) * C + c], tr = (float)img[((size_t)y0 * W + x1) * C + c];
+        const float bl = (float)img[((size_t)y1 * W + x0) * C + c], br = (float)img[((size_t)y1 * W + x1) * C + c];
+        const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+        const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+        o[c] = (TO)__fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+      }
+    }
+  }
+}
+
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -334,8 +334,9 @@ int se3ds_unproject_equirect(se3ds_ws* ws, const void* feats, int in_dtype, cons
                              int h, int w, int c, double void_class, float depth_scale,
                              float* xyz1_out, void* feats_out, int out_dtype, void* stream) {
   if (!ws || !feats || !depth || !xyz1_out || !feats_out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
-  if (n < 0 || h <= 0 || c <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "feats should have shape (N, H, W) or (N, H, W, C)");
-  if (w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "Expected equirectangular input images");
+  if (n < 0 || h <= 0 || w <= 0 || c <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "feats should have shape (N, H, W) or (N, H, W, C)");
+  // W == 2H is asserted by the caller on the *input* image (pano_utils.py:202); after a size_mult
+  // resize the scaled width can be odd, and the angle tables only need (h, w).
   if (void_class < 0.0 && in_dtype == SE3DS_U8)
     return fail(SE3DS_ERR_BAD_DTYPE, "feats datatype must be signed if the void class is negative");
   if (out_dtype != in_dtype && out_dtype != SE3DS_F32) return fail(SE3DS_ERR_BAD_DTYPE, "out dtype must be the input dtype or f32");
@@ -628,6 +629,30 @@ int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, floa
   if (!bin || !proj_image || !proj_depth || !proj_mask) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
   apply_bin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bin, depth_scale, proj_image, proj_depth, proj_mask);
   return launch_check("apply_bin_kernel");
+}
+
+int se3ds_resize(const void* in, int dtype, int n, int h, int w, int c, int out_h, int out_w, int bilinear,
+                 void* out, void* stream) {
+  if (!in || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (n < 0 || h <= 0 || w <= 0 || c <= 0 || out_h <= 0 || out_w <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "images must be (N,H,W,C)");
+  const long long total = (long long)n * out_h * out_w;
+  if (total == 0) return SE3DS_OK;
+  const int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+#define RESIZE(TI, TO, B) resize_kernel<TI, TO, B><<<blocks, kThreads, 0, st>>>((const TI*)in, n, h, w, c, out_h, out_w, (TO*)out)
+  if (bilinear) {
+    if (dtype == SE3DS_U8) RESIZE(uint8_t, float, true);
+    else if (dtype == SE3DS_I32) RESIZE(int, float, true);
+    else if (dtype == SE3DS_F32) RESIZE(float, float, true);
+    else return fail(SE3DS_ERR_BAD_DTYPE, "dtype %d", dtype);
+  } else {
+    if (dtype == SE3DS_U8) RESIZE(uint8_t, uint8_t, false);
+    else if (dtype == SE3DS_I32) RESIZE(int, int, false);
+    else if (dtype == SE3DS_F32) RESIZE(float, float, false);
+    else return fail(SE3DS_ERR_BAD_DTYPE, "dtype %d", dtype);
+  }
+#undef RESIZE
+  return launch_check("resize_kernel");
 }
 
 int se3ds_interpolate_bilinear(const float* grid, const float* query_points, int b, int h, int w, int c,

@@ -37,6 +37,17 @@ def _canon_feats(feats: torch.Tensor) -> torch.Tensor:
   raise ValueError(f'unsupported feature dtype {feats.dtype}')
 
 
+def _resize(images: torch.Tensor, size, method: str) -> torch.Tensor:
+  """tf.image.resize (half-pixel centres) of an (N,H,W,C) device tensor: 'nearest' keeps the dtype,
+  'bilinear' returns float32."""
+  n, h, w, c = images.shape
+  bilinear = method == 'bilinear'
+  out = torch.empty((n, size[0], size[1], c), dtype=torch.float32 if bilinear else images.dtype, device=images.device)
+  _lib.check(_lib.load().se3ds_resize(_lib.ptr(images), _lib.dtype_code(images), n, h, w, c, int(size[0]), int(size[1]),
+                                      int(bilinear), _lib.ptr(out), _lib.stream_handle(images.device)))
+  return out
+
+
 def mask_pano(pano: torch.Tensor, proportion: float = 0.125, masked_region_value=0) -> torch.Tensor:
   """Masks the top and bottom `proportion` rows of a panorama (reference pano_utils.py:245-265).
 
@@ -76,14 +87,19 @@ def equirectangular_to_pointcloud(feats: torch.Tensor, depth: torch.Tensor, void
     feats = feats[..., None]
   batch_size, height, width, channels = feats.shape
   assert width == 2 * height, 'Expected equirectangular input images'
-  if size_mult != 1.0:
-    raise NotImplementedError('size_mult != 1.0 (resized clouds) is not on the accelerated path yet')
+  if interpolation_method not in ('nearest', 'bilinear'):
+    raise NotImplementedError(f"interpolation_method '{interpolation_method}': only 'nearest' and 'bilinear' are built")
   feats = _as_tensor(feats, 'feats')
   orig_dtype = feats.dtype
   feats = _canon_feats(feats.contiguous())
   depth = _as_tensor(depth, 'depth').to(device=feats.device, dtype=torch.float32).contiguous()
   if tuple(depth.shape) != (batch_size, height, width):
     raise ValueError(f'depth should have shape {(batch_size, height, width)}, got {tuple(depth.shape)}')
+  if size_mult != 1.0:  # reference pano_utils.py:203-208: depth 'nearest', features with the given method
+    scaled = (int(height * size_mult), int(width * size_mult))
+    depth = _resize(depth[..., None].contiguous(), scaled, 'nearest')[..., 0].contiguous()
+    feats = _resize(feats, scaled, interpolation_method)
+    height, width = scaled
   out_dtype = feats.dtype if interpolation_method == 'nearest' else torch.float32
   xyz1 = torch.empty((batch_size, 4, height * width), dtype=torch.float32, device=feats.device)
   out = torch.empty((batch_size, height * width, channels), dtype=out_dtype, device=feats.device)

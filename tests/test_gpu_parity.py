@@ -333,6 +333,23 @@ def test_equirectangular_to_pointcloud(mods, batch_size, image_size, multi):
   assert fb.dtype == torch.float32
 
 
+@pytest.mark.parametrize('size_mult,method', [(2.0, 'nearest'), (1.5, 'bilinear'), (0.5, 'nearest'), (0.75, 'bilinear')])
+def test_equirectangular_to_pointcloud_size_mult(mods, size_mult, method):
+  """utils/pano_utils.py:203-208: denser / sparser clouds through tf.image.resize semantics
+  (half-pixel centres; depth 'nearest', features with the given method)."""
+  rng = np.random.default_rng(8)
+  feats = rng.integers(0, 256, (2, 16, 32, 3)).astype(np.int32)
+  depth = rng.uniform(0, 1.05, (2, 16, 32)).astype(F32)
+  xyz1, ff = mods['pano'].equirectangular_to_pointcloud(torch.as_tensor(feats), torch.as_tensor(depth), -1, 20.0,
+                                                        size_mult=size_mult, interpolation_method=method)
+  ex, ef = X.equirectangular_to_pointcloud(feats, depth, -1, 20.0, size_mult=size_mult, interpolation_method=method)
+  m = int(16 * size_mult) * int(32 * size_mult)
+  assert tuple(xyz1.shape) == (2, 4, m) and tuple(ff.shape) == (2, m, 3)
+  assert ff.dtype == (torch.int32 if method == 'nearest' else torch.float32)
+  np.testing.assert_array_equal(xyz1.cpu().numpy(), ex)
+  np.testing.assert_array_equal(ff.cpu().numpy(), ef)
+
+
 @pytest.mark.parametrize('batch_size,image_size', [(2, 64), (1, 128)])
 def test_project_feats_to_equirectangular(mods, batch_size, image_size):
   """utils/pano_utils_test.py:67-87 (random normal cloud, scalar semantic features)."""

@@ -202,3 +202,22 @@ def test_reject_bin_lands_on_pixel_zero():
   np.testing.assert_array_equal(dbg['raw_rgb'][0, 0, 0], expect)
   # batch item 1's pixel (0,0) only sees genuine hits
   assert dbg['raw_rgb'][0, 0, 0].max() >= 250
+
+
+def test_tf_resize_semantics():
+  """tf.image.resize with half-pixel centres: x2 nearest replicates, identity bilinear is exact,
+  x2 bilinear interpolates between neighbours and clamps at the border."""
+  rng = np.random.default_rng(9)
+  img = rng.integers(0, 255, (1, 4, 6, 2)).astype(np.int32)
+  up = R.tf_resize(img, (8, 12), 'nearest')
+  assert up.dtype == np.int32
+  np.testing.assert_array_equal(up[:, ::2, ::2], img)
+  np.testing.assert_array_equal(up[:, 1::2, 1::2], img)
+  np.testing.assert_array_equal(R.tf_resize(img, (4, 6), 'bilinear'), img.astype(F32))
+  row = np.array([0.0, 4.0, 8.0], F32).reshape(1, 1, 3, 1)
+  out = R.tf_resize(row, (1, 6), 'bilinear')[0, 0, :, 0]
+  np.testing.assert_allclose(out, [0, 1, 3, 5, 7, 8], atol=1e-6)
+  down = R.tf_resize(img, (2, 3), 'nearest')
+  np.testing.assert_array_equal(down, img[:, 1::2, 1::2])
+  xyz1, ff = R.equirectangular_to_pointcloud(img[:, :3, :, 0], np.full((1, 3, 6), 0.5, F32), 0, 20.0, size_mult=2.0)
+  assert xyz1.shape == (1, 4, 72) and ff.shape == (1, 72)

@@ -372,6 +372,10 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
 template <typename RGB_T, int PPT, bool KEY64>
 __global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams q) {
   const SrcIdx ix = src_index<PPT>(q);
+  // The feature buffer and the reject bin start at 0 (output_void_class) and only take maxima, so a
+  // point whose channels are all <= 0 changes nothing.  A masked row holds only -1 / unproject_void
+  // features: the whole block (= one row segment) has nothing to do.
+  if (row_masked(q, ix.s, ix.row) && q.uv <= 0) return;
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
   bool bin_has = false;
   int3 bin_f = make_int3(0, 0, 0);

@@ -245,6 +245,33 @@ def test_certified_fast_projection(mods, h, dist):
       assert torch.equal(outs[0][k], outs[mode][k]), (mode, k)
 
 
+def test_non_finite_inputs_do_not_corrupt_memory(mods):
+  """NaN / Inf depth and positions are outside the contract (the reference propagates NaN through
+  `(depth * scale) * mask`), but they must never index out of bounds or poison other items."""
+  g = mods['g']
+  inp = mods['synth'].make_inputs(2, 1, 1, 64, seed=20, dist='room')
+  clean = g.reproject(*(torch.as_tensor(inp[k]).cuda() for k in ('rgb', 'depth', 'src_pos', 'tgt_pos')), per_job_bin=True)
+  clean = {k: v.clone() for k, v in clean.items()}
+  bad = {k: v.copy() for k, v in inp.items()}
+  bad['depth'][0, 0, 10:20, 5:50] = np.nan
+  bad['depth'][0, 0, 30:33, :] = np.inf
+  bad['depth'][0, 0, 40, 7] = -np.inf
+  out = g.reproject(*(torch.as_tensor(bad[k]).cuda() for k in ('rgb', 'depth', 'src_pos', 'tgt_pos')), per_job_bin=True,
+                    return_winner=True)
+  torch.cuda.synchronize()
+  for k in ('proj_image', 'proj_depth', 'proj_mask'):
+    assert torch.equal(out[k][1], clean[k][1]), k  # the untouched item is bit-identical
+  w = out['winner'][0]
+  assert int(w.max()) < 64 * 128 and int(w.min()) >= -1
+  nanpos = {k: v.copy() for k, v in inp.items()}
+  nanpos['tgt_pos'][0, 0, 1] = np.nan
+  out = g.reproject(*(torch.as_tensor(nanpos[k]).cuda() for k in ('rgb', 'depth', 'src_pos', 'tgt_pos')), per_job_bin=True)
+  torch.cuda.synchronize()
+  assert out['proj_mask'][0, 1:].sum().item() == 0  # nothing projects from a NaN pose (pixel (0,0) holds the bin)
+  for k in ('proj_image', 'proj_depth', 'proj_mask'):
+    assert torch.equal(out[k][1], clean[k][1]), k
+
+
 def test_export_and_apply_bin(mods):
   """Multi-GPU bin protocol on one GPU: export per shard, reduce, apply == whole-call result."""
   g = mods['g']

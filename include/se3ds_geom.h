@@ -77,6 +77,11 @@ int se3ds_ws_bytes(const se3ds_ws* ws, size_t* bytes);
  * distance by which a fast coordinate fell outside its canonical pixel (x, y; in pixels) since the
  * last read. */
 int se3ds_ws_projection_mode(se3ds_ws* ws, int mode, float margin_scale);
+
+/* Programmatic dependent launch between the kernels of the fused path (default on): the next
+ * kernel's blocks are scheduled into the tail of the running one and wait on-device for its
+ * completion (griddepcontrol), instead of the stream serialising whole grids. */
+int se3ds_ws_pdl(se3ds_ws* ws, int enable);
 int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_dev[2]);
 
 /* Measurement hooks (bench.py): with profiling enabled se3ds_reproject brackets its three kernel

@@ -30,7 +30,7 @@ except Exception as e:
   print('bench parse failed', e); print(open('gpurun_out/bench_${TAG}_rand.err').read()[-2000:])
 PY
 if [ "$NCU" = ncu ]; then
-  ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 60 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 12 --warmup 3 --no-graph --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launch_${TAG}.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:"splat_depth|splat_feat|resolve" -s 12 -c 3 -o gpurun_out/prof_${TAG} python bench.py --steps 12 --warmup 3 --no-graph --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 60 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 12 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launch_${TAG}.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:"splat_depth|splat_feat|resolve" -s 12 -c 3 -o gpurun_out/prof_${TAG} python bench.py --steps 12 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
 fi
 ls gpurun_out | head -50

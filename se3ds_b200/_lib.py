@@ -39,6 +39,7 @@ SIGNATURES = {
     'se3ds_ws_destroy': [_vp],
     'se3ds_ws_bytes': [_vp, _c.POINTER(_sz)],
     'se3ds_ws_projection_mode': [_vp, _i, _f],
+    'se3ds_ws_pdl': [_vp, _i],
     'se3ds_ws_verify_read': [_vp, _c.POINTER(_c.c_ulonglong * 3), _c.POINTER(_f * 2)],
     'se3ds_ws_profile': [_vp, _i],
     'se3ds_ws_profile_read': [_vp, _c.POINTER(_f * 3), _c.POINTER(_c.c_ulonglong)],
@@ -148,6 +149,10 @@ class Workspace:
   def projection_mode(self, mode: int, margin_scale: float = 0.0):
     """0 canonical only, 1 certified fast path (default), 2 verify (see se3ds_geom.h)."""
     check(load().se3ds_ws_projection_mode(self.handle, int(mode), float(margin_scale)))
+
+  def pdl(self, enable: bool):
+    """Programmatic dependent launch between the fused kernels (default on)."""
+    check(load().se3ds_ws_pdl(self.handle, int(enable)))
 
   def verify_read(self):
     """-> dict(points, certified, wrong, max_dev_x, max_dev_y) accumulated in verify mode."""

@@ -23,6 +23,16 @@
 namespace se3ds {
 
 constexpr int kThreads = 128;
+
+// Programmatic dependent launch: the three kernels of a chunk (and of consecutive calls) are
+// launched with programmatic stream serialization, so the blocks of the next kernel are scheduled
+// into the tail of the running one.  pdl_enter() first lets the *next* grid start launching, then
+// waits until the *previous* grid has completed and its memory is visible -- every dependent
+// access (z-buffer, feature buffer, scratch, bins) comes after it.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 constexpr unsigned long long kZArmed = 0xFFFFFFFFFFFFFFFFull;
 
 // scratch word: pixel index in bits 0..27, flags above
@@ -185,6 +195,7 @@ __device__ __forceinline__ void load_rgbn(const RGB_T* rgb, size_t pix0, int3 (&
 // depth comes from a 32-bit key (depth bits only): half the z-buffer traffic, identical guidance.
 template <typename RGB_T, int PPT, bool FAST, int PROJ, bool KEY64>
 __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
+  pdl_enter();
   const SrcIdx ix = src_index<PPT>(q);
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
   uint32_t bin_z = 0u;  // ~ordered(min depth) of this thread's rejected points, 0 = none
@@ -371,6 +382,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
 // ------------------------------------------------------------------------------------------
 template <typename RGB_T, int PPT, bool KEY64>
 __global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams q) {
+  pdl_enter();
   const SrcIdx ix = src_index<PPT>(q);
   // The feature buffer and the reject bin start at 0 (output_void_class) and only take maxima, so a
   // point whose channels are all <= 0 changes nothing.  A masked row holds only -1 / unproject_void
@@ -444,6 +456,7 @@ __device__ __forceinline__ float clip01_div255(float v) {
 
 template <int PPT, bool KEY64>
 __global__ void __launch_bounds__(kThreads, 12) resolve_kernel(const FusedParams q) {
+  pdl_enter();
   const int lj = blockIdx.z;
   int n, p;
   if (q.PC == 1) { n = q.n0 + lj; p = q.p0; } else { const int a = lj / q.PC; n = q.n0 + a; p = q.p0 + (lj - a * q.PC); }

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "kernels.cuh"
@@ -64,6 +65,7 @@ struct se3ds_ws {
   cudaStream_t hstream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> pipe_ev;  // 2 per batch item: inputs on device, outputs computed
   float margin_scale = 1.0e-6f;  // certification margin: dx = W * scale, dy = 2 * H * scale pixels
+  bool pdl = true;  // programmatic dependent launch between the fused kernels
   int proj_mode = 1;  // 0 canonical only, 1 certified fast path (default), 2 verify
   DevBuf dbg;
   // measurement hooks
@@ -161,6 +163,22 @@ int launch_check(const char* what) {
   return SE3DS_OK;
 }
 
+// Launch with programmatic stream serialization (see pdl_enter in kernels.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <typename RGB_T, int PPT, bool KEY64>
 int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st) {
   const int gx = (q.W + kThreads * PPT - 1) / (kThreads * PPT);
@@ -182,14 +200,15 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
   const bool fast = std::is_same<RGB_T, uint8_t>::value && q.pv == -1 &&
                     (!(q.flags & SE3DS_FLAG_FILTER_VOID) || q.uv == -1);
   const int proj = ws->proj_mode;
-#define LAUNCH_K2(F, P) splat_depth_kernel<RGB_T, PPT, F, P, KEY64><<<grid, block, 0, st>>>(q)
+  const bool pdl = ws->pdl && !ws->profile;
+#define LAUNCH_K2(F, P) CU(launch_pdl(splat_depth_kernel<RGB_T, PPT, F, P, KEY64>, grid, block, st, pdl, q))
   if (fast) { if (proj == 0) LAUNCH_K2(true, 0); else if (proj == 1) LAUNCH_K2(true, 1); else LAUNCH_K2(true, 2); }
   else { if (proj == 0) LAUNCH_K2(false, 0); else if (proj == 1) LAUNCH_K2(false, 1); else LAUNCH_K2(false, 2); }
 #undef LAUNCH_K2
   if (ev) CU(cudaEventRecord(ev[1], st));
-  splat_feat_kernel<RGB_T, PPT, KEY64><<<grid, block, 0, st>>>(q);
+  CU(launch_pdl(splat_feat_kernel<RGB_T, PPT, KEY64>, grid, block, st, pdl, q));
   if (ev) CU(cudaEventRecord(ev[2], st));
-  resolve_kernel<PPT, KEY64><<<dim3(gx, q.H, jobs), block, 0, st>>>(q);
+  CU(launch_pdl(resolve_kernel<PPT, KEY64>, dim3(gx, q.H, jobs), block, st, pdl, q));
   if (ev) CU(cudaEventRecord(ev[3], st));
   ws->launches += 3;
   return launch_check("fused reprojection kernels");
@@ -261,6 +280,12 @@ int se3ds_ws_projection_mode(se3ds_ws* ws, int mode, float margin_scale) {
   if (!ws || mode < 0 || mode > 2) return fail(SE3DS_ERR_BAD_ARG, "mode must be 0, 1 or 2");
   ws->proj_mode = mode;
   if (margin_scale > 0.0f) ws->margin_scale = margin_scale;
+  return SE3DS_OK;
+}
+
+int se3ds_ws_pdl(se3ds_ws* ws, int enable) {
+  if (!ws) return fail(SE3DS_ERR_BAD_ARG, "NULL workspace");
+  ws->pdl = enable != 0;
   return SE3DS_OK;
 }
 

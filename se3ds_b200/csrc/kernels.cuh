@@ -29,9 +29,11 @@ constexpr int kThreads = 128;
 // into the tail of the running one.  pdl_enter() first lets the *next* grid start launching, then
 // waits until the *previous* grid has completed and its memory is visible -- every dependent
 // access (z-buffer, feature buffer, scratch, bins) comes after it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_launch_dependents();
+  pdl_wait();
 }
 constexpr unsigned long long kZArmed = 0xFFFFFFFFFFFFFFFFull;
 
@@ -195,7 +197,9 @@ __device__ __forceinline__ void load_rgbn(const RGB_T* rgb, size_t pix0, int3 (&
 // depth comes from a 32-bit key (depth bits only): half the z-buffer traffic, identical guidance.
 template <typename RGB_T, int PPT, bool FAST, int PROJ, bool KEY64>
 __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
-  pdl_enter();
+  // K2 only reads caller inputs until it touches the z-buffer / scratch / bins, so the wait for the
+  // previous grid (the resolve that re-arms the z-buffer) comes after the projection math.
+  pdl_launch_dependents();
   const SrcIdx ix = src_index<PPT>(q);
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
   uint32_t bin_z = 0u;  // ~ordered(min depth) of this thread's rejected points, 0 = none
@@ -212,18 +216,20 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
   const size_t sc_frame = ((size_t)ix.lj * q.S + ix.s) * q.HW;
   const uint32_t idx_frame = (uint32_t)(ix.s * q.HW);
 
-  // splat (or reject) one projected point; returns its scratch word
+  // classify one projected point: returns its scratch word (target pixel or rejected); the splat
+  // itself (below) is deferred until after pdl_wait()
   auto commit = [&](int tpix, float rad, int pix, bool dvalid, bool fvalid) -> uint32_t {
     const uint32_t dflag = dvalid ? 0u : kScDepthInv;
-    if (fvalid && tpix >= 0) {
-      if constexpr (KEY64)
-        atomicMin(zb + tpix, ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | (dvalid ? 0u : 1u));
-      else
-        atomicMin(zb32 + tpix, __float_as_uint(rad));
-      return (uint32_t)tpix | dflag;
-    }
+    if (fvalid && tpix >= 0) return (uint32_t)tpix | dflag;
     bin_z = max(bin_z, ~f32_ordered(rad));
     return kScInvalid | dflag;
+  };
+  auto splat = [&](uint32_t word, float rad, int pix) {
+    if (word & (kScInvalid | kScDropped)) return;
+    if constexpr (KEY64)
+      atomicMin(zb + (word & kScPixMask), ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | ((word & kScDepthInv) ? 1u : 0u));
+    else
+      atomicMin(zb32 + (word & kScPixMask), __float_as_uint(rad));
   };
 
   // Inactive lanes (past the end of a row) run the loop as dropped points, so that the warp-wide
@@ -335,6 +341,9 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       }
     }
   }
+  pdl_wait();  // from here on: z-buffer, scratch and bins of this workspace
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) splat(scf[k], scr[k], pix0 + k);
   if (ix.active) {
     if constexpr (PPT == 4) {
       __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc_frame + pix0), make_uint4(scf[0], scf[1], scf[2], scf[3]));
@@ -371,7 +380,9 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       const int pix = (int)(m & 0x3FFFFFFFu);
       const int tpix = project_pixel_rad(pt.x, pt.y, pt.z, q.H, q.W, pt.w);
       bin_z = 0u;
-      q.sc_flat[sc_frame + pix] = commit(tpix, pt.w, pix, m >> 31, (m >> 30) & 1u);
+      const uint32_t word = commit(tpix, pt.w, pix, m >> 31, (m >> 30) & 1u);
+      splat(word, pt.w, pix);
+      q.sc_flat[sc_frame + pix] = word;
       if (bin_z) bin_update_z(bin, bin_z);  // a deferred point that turned out to be rejected (rare)
     }
   }

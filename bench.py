@@ -247,7 +247,7 @@ def main():
       inp = {k: np.concatenate([v] * (n // gen_n), axis=0) for k, v in inp.items()}
     t = {k: torch.as_tensor(v).to(dev) for k, v in inp.items()}
     plans.append(guidance.prepare(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, workspace=ws,
-                                  key64=args.key64))
+                                  key64=args.key64, inputs_ready=True))
   host_inp = {k: torch.as_tensor(v).pin_memory() for k, v in inp.items()}
 
   stream = torch.cuda.Stream(dev)
@@ -348,7 +348,7 @@ def main():
         'config': {'workload': workload_name(args.config, cfg, args.dist), 'per_gpu_batch': n,
                    'cache': f'inputs+outputs rotate over a ring of {ring} sets ({ring * set_bytes >> 20} MiB > 2x L2)',
                    'launch': 'cuda_graph_replay' if graphs is not None else 'stream launches (programmatic dependent launch)', 'parallelism': f'dp{world}',
-                   'chunk_mb': args.chunk_mb or 'default', 'pdl': not args.no_pdl, 'zbuffer_key': 'u64 depth|index' if args.key64 else 'u32 depth (no winner index requested)',
+                   'chunk_mb': args.chunk_mb or 'default', 'inputs_ready_flag': True, 'pdl': not args.no_pdl, 'zbuffer_key': 'u64 depth|index' if args.key64 else 'u32 depth (no winner index requested)',
                    'projection': 'certified_fast+canonical_fallback' if args.proj_mode == 1 else 'canonical'},
         'mpoints_per_s': mpoints,
         'e2e': {'value': world * n * p / (e2e_ms * 1e-3), 'unit': 'panos/s', 'h2d_bytes_per_step': h2d,

@@ -57,6 +57,12 @@ typedef enum { SE3DS_U8 = 0, SE3DS_I32 = 1, SE3DS_F32 = 2 } se3ds_dtype;
                                      it a 32-bit depth-only key gives the same guidance tensors
                                      with half the z-buffer traffic. */
 
+#define SE3DS_FLAG_INPUTS_READY 8u /* promise: rgb / depth / positions were complete before the kernel
+                                      that precedes this call on the stream was launched (static or
+                                      long-uploaded buffers).  Lets the projection math of this call
+                                      overlap the tail of that kernel (programmatic dependent launch);
+                                      without the flag the call waits for it first. */
+
 int se3ds_version(void);
 const char* se3ds_status_string(int status);
 const char* se3ds_last_error(void);

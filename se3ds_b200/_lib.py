@@ -21,6 +21,7 @@ U8, I32, F32 = 0, 1, 2
 FLAG_FILTER_VOID = 1
 FLAG_BIN_PER_JOB = 2
 FLAG_KEY64 = 4
+FLAG_INPUTS_READY = 8
 
 _DTYPES = {torch.uint8: U8, torch.int32: I32, torch.float32: F32}
 

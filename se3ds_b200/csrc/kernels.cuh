@@ -197,9 +197,13 @@ __device__ __forceinline__ void load_rgbn(const RGB_T* rgb, size_t pix0, int3 (&
 // depth comes from a 32-bit key (depth bits only): half the z-buffer traffic, identical guidance.
 template <typename RGB_T, int PPT, bool FAST, int PROJ, bool KEY64>
 __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
-  // K2 only reads caller inputs until it touches the z-buffer / scratch / bins, so the wait for the
-  // previous grid (the resolve that re-arms the z-buffer) comes after the projection math.
+  // K2 only reads caller inputs until it touches the z-buffer / scratch / bins.  If the caller
+  // guarantees that those inputs were not produced by the kernel launched just before this call
+  // (SE3DS_FLAG_INPUTS_READY), the wait for the previous grid -- normally the resolve that re-arms
+  // the z-buffer -- is postponed until after the projection math; otherwise it comes first.
   pdl_launch_dependents();
+  const bool late_wait = q.flags & SE3DS_FLAG_INPUTS_READY;
+  if (!late_wait) pdl_wait();
   const SrcIdx ix = src_index<PPT>(q);
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
   uint32_t bin_z = 0u;  // ~ordered(min depth) of this thread's rejected points, 0 = none
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       }
     }
   }
-  pdl_wait();  // from here on: z-buffer, scratch and bins of this workspace
+  if (late_wait) pdl_wait();  // from here on: z-buffer, scratch and bins of this workspace
 #pragma unroll
   for (int k = 0; k < PPT; ++k) splat(scf[k], scr[k], pix0 + k);
   if (ix.active) {

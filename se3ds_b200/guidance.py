@@ -130,8 +130,11 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
             mask_proportion: float = 0.125, mask_frames: int = 0,
             unproject_void: int = constants.INVALID_RGB_VALUE, project_void: int = constants.INVALID_RGB_VALUE,
             filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
-            workspace: Optional[_lib.Workspace] = None, key64: bool = False) -> PreparedReprojection:
-  """Same arguments as `reproject`; allocates the outputs once and returns a PreparedReprojection."""
+            workspace: Optional[_lib.Workspace] = None, key64: bool = False,
+            inputs_ready: bool = False) -> PreparedReprojection:
+  """Same arguments as `reproject`; allocates the outputs once and returns a PreparedReprojection.
+  inputs_ready=True promises that the input tensors are not written by whatever kernel runs right
+  before each `run()` on the stream (SE3DS_FLAG_INPUTS_READY)."""
   rgb, depth, src_pos, tgt_pos = _prep(rgb, depth, src_pos, tgt_pos, True)
   n, s, h, w, _ = rgb.shape
   p = tgt_pos.shape[1]
@@ -142,7 +145,7 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
   if return_winner:
     out['winner'] = torch.empty((j, h, w), dtype=torch.int32, device=dev)
   flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
-           (_lib.FLAG_KEY64 if key64 else 0))
+           (_lib.FLAG_KEY64 if key64 else 0) | (_lib.FLAG_INPUTS_READY if inputs_ready else 0))
   ws = workspace or _lib.default_workspace(dev)
   args = (ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
           n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),

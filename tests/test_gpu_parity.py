@@ -301,6 +301,29 @@ def test_determinism(mods):
       assert torch.equal(first[k], again[k]), k
 
 
+def test_prepared_plans_back_to_back(mods):
+  """PreparedReprojection with SE3DS_FLAG_INPUTS_READY: consecutive runs overlap through programmatic
+  dependent launch (K2's math starts before the previous resolve has finished) and must still give
+  the results of isolated calls, also when two plans share one workspace."""
+  g, lib = mods['g'], mods['lib']
+  ws = lib.Workspace(0)
+  plans, refs = [], []
+  for seed in (31, 32, 33):
+    t = _cuda(mods['synth'].make_inputs(2, 2, 1, 128, seed=seed, dist='rand'))
+    ref = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, return_winner=True)
+    refs.append({k: v.clone() for k, v in ref.items()})
+    plans.append(g.prepare(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, return_winner=True,
+                           workspace=ws, inputs_ready=True))
+  for _ in range(5):
+    for pl in plans:
+      pl.run()
+  torch.cuda.synchronize()
+  for pl, ref in zip(plans, refs):
+    for k in ref:
+      assert torch.equal(pl.out[k], ref[k]), k
+  ws.close()
+
+
 def test_reproject_host_equals_device(mods):
   g = mods['g']
   inp = mods['synth'].make_inputs(2, 2, 1, 64, seed=12)

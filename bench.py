@@ -183,6 +183,49 @@ def workload_name(name, c, dist):
           f"depth={dist}, mask frame 0, void -1/-1")
 
 
+def run_sharded(args, cfg, world, rank, local_rank, dev):
+  """Strong scaling of one call (e.g. c4: 64 poses of one pano): every rank renders its block of the
+  job list, then the finished guidance tensors are all-gathered (NCCL over NVLink) and the reject
+  bin is all-reduced -- all inside the timed step."""
+  import torch
+  import torch.distributed as dist
+  from se3ds_b200 import parallel, synth
+  n, s, p, h = cfg['n'], cfg['s'], cfg['p'], cfg['h']
+  inp = synth.make_inputs(n, s, p, h, seed=7, dist=args.dist, sweep=cfg['sweep'])
+  t = {k: torch.as_tensor(v).to(dev) for k, v in inp.items()}
+  def step():
+    return parallel.reproject_sharded(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1)
+  for _ in range(max(args.warmup, 3)):
+    step()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  steps = min(args.steps, 200)
+  e0.record()
+  for _ in range(steps):
+    out = step()
+  e1.record()
+  torch.cuda.synchronize()
+  ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  if rank == 0:
+    hw = h * 2 * h
+    gathered = sum(v.numel() * v.element_size() for k, v in out.items() if torch.is_tensor(v))
+    print(json.dumps({
+        'metric': 'reprojected panoramas/s', 'value': n * p / (ms.item() * 1e-3), 'unit': 'panos/s', 'n_gpus': world,
+        'steps': steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms.item(), 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.config, cfg, args.dist), 'sharding': 'jobs block-partitioned over ranks',
+                   'collective': 'all_gather_into_tensor of proj_image/proj_depth/proj_mask + 4-float bin all-reduce',
+                   'gathered_bytes_per_rank': gathered},
+        'mpoints_per_s': n * s * p * hw / (ms.item() * 1e-3) / 1e6}), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------
 def main():
   ap = argparse.ArgumentParser()
@@ -201,6 +244,8 @@ def main():
   ap.add_argument('--n-override', type=int, default=0, help='override the batch size of the config (memory-bounded runs)')
   ap.add_argument('--key64', action='store_true', help='force the 64-bit packed depth|index z-buffer key')
   ap.add_argument('--no-pdl', action='store_true', help='disable programmatic dependent launch')
+  ap.add_argument('--sharded', action='store_true', help='strong scaling: shard the jobs of ONE call over the ranks and '
+                  'all-gather the guidance tensors (NCCL) inside the timed step (se3ds_b200.parallel)')
   ap.add_argument('--proj-mode', type=int, default=1, help='0 canonical projection only, 1 certified fast path (default)')
   args = ap.parse_args()
   cfg = dict(CONFIGS[args.config])
@@ -231,6 +276,9 @@ def main():
 
   n, s, p, h = cfg['n'], cfg['s'], cfg['p'], cfg['h']
   w = 2 * h
+  if args.sharded:
+    run_sharded(args, cfg, world, rank, local_rank, dev)
+    return
   src_bytes, out_bytes = alg_bytes(cfg)
   # ring of distinct input/output sets larger than 2x L2, so every step starts cold in L2
   set_bytes = src_bytes + out_bytes

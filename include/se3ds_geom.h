@@ -63,6 +63,11 @@ typedef enum { SE3DS_U8 = 0, SE3DS_I32 = 1, SE3DS_F32 = 2 } se3ds_dtype;
                                       overlap the tail of that kernel (programmatic dependent launch);
                                       without the flag the call waits for it first. */
 
+#define SE3DS_FLAG_RAW_FEATURES 16u /* proj_image receives the raw per-channel maxima (the
+                                       `projected_feat` of point_cloud_utils.py:173-178) instead of
+                                       clip(x / 255, 0, 1): e.g. semantic class ids replicated into
+                                       the three channels (models/models.py:276-278). */
+
 int se3ds_version(void);
 const char* se3ds_status_string(int status);
 const char* se3ds_last_error(void);

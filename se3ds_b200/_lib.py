@@ -22,6 +22,7 @@ FLAG_FILTER_VOID = 1
 FLAG_BIN_PER_JOB = 2
 FLAG_KEY64 = 4
 FLAG_INPUTS_READY = 8
+FLAG_RAW_FEATURES = 16
 
 _DTYPES = {torch.uint8: U8, torch.int32: I32, torch.float32: F32}
 

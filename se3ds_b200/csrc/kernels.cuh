@@ -527,7 +527,11 @@ __global__ void __launch_bounds__(kThreads, 12) resolve_kernel(const FusedParams
     // point_cloud_utils.py:160-162, models.py:282-293
     const float depth = div_rcp(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale, q.inv_depth_scale);
     od[k] = depth;
-    oi[3 * k + 0] = clip01_div255(f.x); oi[3 * k + 1] = clip01_div255(f.y); oi[3 * k + 2] = clip01_div255(f.z);
+    if (q.flags & SE3DS_FLAG_RAW_FEATURES) {
+      oi[3 * k + 0] = f.x; oi[3 * k + 1] = f.y; oi[3 * k + 2] = f.z;
+    } else {
+      oi[3 * k + 0] = clip01_div255(f.x); oi[3 * k + 1] = clip01_div255(f.y); oi[3 * k + 2] = clip01_div255(f.z);
+    }
     om[k] = (depth > 0.0f && depth < 1.0f && f.x != -1.0f && f.y != -1.0f && f.z != -1.0f) ? 1.0f : 0.0f;
   }
   const size_t o = (size_t)job * q.HW + pix0;
@@ -568,7 +572,9 @@ __global__ void patch_owner_kernel(const FusedParams q) {
   *bin = Bin{0u, {0, 0, 0}};
   const float depth = div_rcp(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale, q.inv_depth_scale);
   q.out_depth[0] = depth;
-  q.out_image[0] = clip01_div255(f.x); q.out_image[1] = clip01_div255(f.y); q.out_image[2] = clip01_div255(f.z);
+  const bool raw = q.flags & SE3DS_FLAG_RAW_FEATURES;
+  q.out_image[0] = raw ? f.x : clip01_div255(f.x); q.out_image[1] = raw ? f.y : clip01_div255(f.y);
+  q.out_image[2] = raw ? f.z : clip01_div255(f.z);
   q.out_mask[0] = (depth > 0.0f && depth < 1.0f && f.x != -1.0f && f.y != -1.0f && f.z != -1.0f) ? 1.0f : 0.0f;
 }
 

@@ -64,7 +64,8 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
               unproject_void: int = constants.INVALID_RGB_VALUE, project_void: int = constants.INVALID_RGB_VALUE,
               filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
               export_bin: bool = False, out: Optional[Dict[str, torch.Tensor]] = None,
-              workspace: Optional[_lib.Workspace] = None, tgt_rot=None, key64: bool = False) -> Dict[str, torch.Tensor]:
+              workspace: Optional[_lib.Workspace] = None, tgt_rot=None, key64: bool = False,
+              raw_features: bool = False) -> Dict[str, torch.Tensor]:
   """Re-projects S source RGB-D panos per item onto P target poses per item.
 
   Args:
@@ -74,6 +75,7 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
     mask_frames: the first `mask_frames` frames get mask_pano(., mask_proportion, -1).
     unproject_void / project_void / filter_void: see `Conventions`.
     per_job_bin: every (item,pose) job is its own reference call (batch 1).
+    raw_features: proj_image holds the raw per-channel maxima instead of clip(x/255, 0, 1).
     tgt_rot: optional (N,P,3,3) rotations into the target camera frames (full SE(3) poses; the
       reference only translates, models/models.py:120-125): q = R (local + src - tgt).
   Returns dict with proj_image (J,H,W,3), proj_depth (J,H,W,1), proj_mask (J,H,W,1),
@@ -97,7 +99,7 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
   winner = buf('winner', (j, h, w), torch.int32) if return_winner else None
   binb = buf('bin', (4,)) if export_bin else None
   flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
-           (_lib.FLAG_KEY64 if key64 else 0))
+           (_lib.FLAG_KEY64 if key64 else 0) | (_lib.FLAG_RAW_FEATURES if raw_features else 0))
   ws = workspace or _lib.default_workspace(dev)
   if tgt_rot is not None:
     tgt_rot = _lib.require_cuda(torch.as_tensor(tgt_rot), 'tgt_rot').to(device=dev, dtype=torch.float32)
@@ -323,18 +325,16 @@ class GuidanceMemory(object):
                                                rgb_pts[i, 1], rgb_pts[i, 2]))
 
   def _project_semantic(self, position):
-    """models/models.py:217-219,229-231,276-278 through the materialising compat path."""
+    """models/models.py:217-219,229-231,276-278 through the fused kernels: the class ids are
+    replicated into the three feature channels (void class 0 on both sides, compaction on, no row
+    mask), so validity, the near-min set and the per-channel maximum are those of the scalar
+    feature, and channel 0 of the raw features is proj_semantic."""
     m = self._memory
-    coords, feats = [], []
-    for sem, depth, pos in zip(m.semantic, m.depth, m.position):
-      xyz1, f = pano_utils.equirectangular_to_pointcloud(sem, depth, constants.INVALID_SEM_VALUE, self.depth_scale)
-      xyz1 = xyz1 + torch.cat([pos, torch.zeros_like(pos[:, :1])], dim=1)[:, :, None]
-      valid = (f != constants.INVALID_SEM_VALUE).any(dim=0).any(dim=-1)
-      coords.append(xyz1[:, :, valid])
-      feats.append(f[:, valid, 0])
-    coords = torch.cat(coords, dim=2)
-    feats = torch.cat(feats, dim=1)
-    rel = coords - torch.cat([position, torch.zeros_like(position[:, :1])], dim=1)[:, :, None]
-    _, sem = pano_utils.project_feats_to_equirectangular(feats, rel, self.height, self.width,
-                                                         constants.INVALID_SEM_VALUE, self.depth_scale)
-    return sem.to(torch.uint8)
+    sem = torch.stack([t.reshape(t.shape[0], self.height, self.width) for t in m.semantic], dim=1)  # (N,S,H,W)
+    sem3 = sem[..., None].expand(-1, -1, -1, -1, 3).contiguous()
+    depth = torch.stack(m.depth, dim=1)
+    src = torch.stack(m.position, dim=1)
+    out = reproject(sem3, depth, src, position, self.depth_scale, mask_frames=0,
+                    unproject_void=constants.INVALID_SEM_VALUE, project_void=constants.INVALID_SEM_VALUE,
+                    filter_void=True, per_job_bin=True, raw_features=True)
+    return out['proj_image'][..., 0].to(torch.uint8)

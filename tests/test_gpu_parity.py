@@ -544,6 +544,30 @@ def test_guidance_memory_matches_reference_flow(mods):
     g.GuidanceMemory(64, batch_size=2)
 
 
+def test_fused_semantic_projection(mods):
+  """models/models.py:217-219,229-231,276-278: scalar class ids through the fused kernels (ids
+  replicated into three channels, void class 0, compaction, raw features) against the canonical
+  oracle on the compacted cloud, bit for bit."""
+  g = mods['g']
+  inp = mods['synth'].make_inputs(1, 3, 1, 64, seed=23, dist='room')
+  rng = np.random.default_rng(11)
+  sem = rng.integers(0, R.NUM_MP3D_CLASSES, (1, 3, 64, 128)).astype(np.uint8)  # includes void (0) pixels
+  mem = g.GuidanceMemory(64, project_semantic=True)
+  coords, feats = [], []
+  for k in range(3):
+    mem.add_to_memory(torch.as_tensor(inp['rgb'][:, k]), torch.as_tensor(sem[:, k, ..., None]),
+                      torch.as_tensor(inp['depth'][:, k]), torch.as_tensor(inp['src_pos'][:, k]))
+    xyz1, f = X.equirectangular_to_pointcloud(sem[:, k], inp['depth'][:, k], 0, 20.0)
+    xyz1 = xyz1 + np.concatenate([inp['src_pos'][:, k], np.zeros((1, 1), F32)], 1)[:, :, None]
+    valid = np.any(f != 0, axis=0)
+    coords.append(xyz1[:, :, valid]); feats.append(f[:, valid])
+  out = mem(torch.as_tensor(inp['tgt_pos'][:, 0]))
+  rel = np.concatenate(coords, 2) - np.concatenate([inp['tgt_pos'][:, 0], np.zeros((1, 1), F32)], 1)[:, :, None]
+  want = X.splat(rel, np.concatenate(feats, 1), 64, 128, 20.0, 0.0)['feat']
+  np.testing.assert_array_equal(out['proj_semantic'].cpu().numpy(), want.astype(np.uint8))
+  assert out['proj_semantic'].dtype == torch.uint8 and (want > 0).mean() > 0.2
+
+
 def test_ply_export(mods, tmp_path):
   """models/models.py:154-178: the only on-disk format on the path."""
   g = mods['g']

@@ -77,6 +77,7 @@ struct FusedParams {
   float* bin_out;     // export mode: no owner pixel, the bin is handed to the caller
   float inv_depth_scale;  // RN(1 / depth_scale), computed on the host with an IEEE division
   FastProj fast;          // certified fast projection (canon_math.cuh)
+  int prefilter_z, prefilter_f;  // read-before-reduce filters (several frames per job, L2-resident buffer)
   unsigned long long* dbg;  // verify mode: {points, certified, certified-but-wrong, max |dfx| bits<<32 | max |dfy| bits}
 };
 
@@ -228,12 +229,18 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     bin_z = max(bin_z, ~f32_ordered(rad));
     return kScInvalid | dflag;
   };
+  // With several source frames most points arrive at a pixel that already holds something nearer:
+  // a plain read (the entry only decreases, so a stale value is a safe filter) saves the REDG.
+  const bool prefilter = q.prefilter_z != 0;
   auto splat = [&](uint32_t word, float rad, int pix) {
     if (word & (kScInvalid | kScDropped)) return;
-    if constexpr (KEY64)
-      atomicMin(zb + (word & kScPixMask), ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | ((word & kScDepthInv) ? 1u : 0u));
-    else
-      atomicMin(zb32 + (word & kScPixMask), __float_as_uint(rad));
+    if constexpr (KEY64) {
+      const unsigned long long key = ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | ((word & kScDepthInv) ? 1u : 0u);
+      if (!prefilter || key < __ldcg(zb + (word & kScPixMask))) atomicMin(zb + (word & kScPixMask), key);
+    } else {
+      const uint32_t key = __float_as_uint(rad);
+      if (!prefilter || key < __ldcg(zb32 + (word & kScPixMask))) atomicMin(zb32 + (word & kScPixMask), key);
+    }
   };
 
   // Inactive lanes (past the end of a row) run the loop as dropped points, so that the warp-wide
@@ -444,7 +451,18 @@ __global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams 
         // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
         const float zmin = fminf(__uint_as_float(zbits[k]), q.depth_scale);  // armed bits are a NaN: fminf -> depth_scale
         const bool keep = scr[k] < __fadd_rn(zmin, 0.1f);
-        if (keep) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
+        if (keep) {
+          // With several source frames many points share a pixel and most of them cannot raise the
+          // maximum any more: a plain read (the buffer only grows, a stale value is a safe filter)
+          // saves the reduction.  With one frame, or a workspace that does not fit in L2, the read
+          // costs more than it saves (measured: c3 -25 %, c5 +19 % for K3), so the host decides.
+          bool need = true;
+          if (q.prefilter_f) {
+            const float3 cur = unpack_f16x4(__ldcg(fb + (scf[k] & kScPixMask)));
+            need = (float)f.x > cur.x || (float)f.y > cur.y || (float)f.z > cur.z;
+          }
+          if (need) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
+        }
         rejected = !keep;
       }
       if (rejected) {

@@ -3,7 +3,7 @@
  * The reference (google-research/se3ds) has no FFI: the path sits behind plain
  * Python functions.  Each entry point below names the reference function(s) it
  * replaces (file:line relative to the reference checkout).  The Python shims in
- * se3ds_b200/utils/*.py keep the reference signatures and call these through
+ * se3ds_b200/utils (pano_utils.py, point_cloud_utils.py) keep the reference signatures and call these through
  * ctypes with raw device pointers; INTEGRATION.md shows the binding.
  *
  * Conventions

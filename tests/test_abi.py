@@ -28,6 +28,20 @@ def test_header_symbols_are_exported_and_bound():
   assert sorted(_lib.SIGNATURES) == names
 
 
+def test_header_is_plain_c():
+  """include/se3ds_geom.h must be consumable by a C compiler (cgo / JNI / ctypes-style bindings)."""
+  import subprocess
+  import tempfile
+  with tempfile.NamedTemporaryFile('w', suffix='.c', delete=False) as f:
+    f.write('#include "se3ds_geom.h"\nint main(void) { se3ds_ws* ws = 0; int (*v)(void) = se3ds_version; (void)ws; (void)v; return SE3DS_OK; }\n')
+    path = f.name
+  try:
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-fsyntax-only',
+                           '-I', os.path.join(ROOT, 'include'), path])
+  finally:
+    os.unlink(path)
+
+
 def test_version_and_status_strings():
   lib = _lib.load()
   assert lib.se3ds_version() == 100

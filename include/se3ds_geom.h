@@ -190,6 +190,27 @@ int se3ds_resize(const void* in, int dtype, int n, int h, int w, int c, int out_
 int se3ds_interpolate_bilinear(const float* grid, const float* query_points, int b, int h, int w, int c,
                                long long num_queries, int indexing_xy, float* out, void* stream);
 
+/* Fused forms of the resampling functions (coordinates computed in-kernel, then the same bilinear
+ * sample).  All tensors f32 on the device; the 3x3 matrices of the last two are HOST arrays
+ * (row-major), computed by the caller exactly as the reference computes them.
+ *   se3ds_pixel_rays                 utils/pano_utils.py:92-114  -> out (3, H*2H)
+ *   se3ds_rotate_pano                utils/pano_utils.py:306-341 pano (N,H,W,C), matrix (N,3,3) device
+ *                                    -> out (N,OH,2*OH,C)
+ *   se3ds_project_perspective_image  utils/pano_utils.py:344-417 image (h,w,C), world_to_image =
+ *                                    get_world_to_image_transform(...); pad = 1 for pad_mode
+ *                                    'constant' / 'mean' (pad_value = constant or image mean), 0 for
+ *                                    'reflect' -> out (OH,2*OH,C)
+ *   se3ds_perspective_from_equirect  utils/pano_utils.py:443-476 image (EH,EW,C), kinv_t = inv(K)^T,
+ *                                    rotation -> out (height,width,C) */
+int se3ds_pixel_rays(int output_height, float* out, void* stream);
+int se3ds_rotate_pano(const float* pano, const float* matrix, int n, int h, int w, int c, int output_height,
+                      float* out, void* stream);
+int se3ds_project_perspective_image(const float* image, int h, int w, int c, const float world_to_image[9],
+                                    int output_height, int pad, float pad_value, int round_to_nearest, float* out,
+                                    void* stream);
+int se3ds_perspective_from_equirect(const float* image, int eq_h, int eq_w, int c, const float kinv_t[9],
+                                    const float rotation[9], int height, int width, float* out, void* stream);
+
 /* inference/perturbation_utils.py:23-71 get_proportion_invalid_for_depth, batched over P offsets.
  * offsets (P,3) f32 device, depth (H,W) f32 device -> out (P,) f32 device. */
 int se3ds_proportion_invalid(const float* offsets, int p, const float* depth, int h, int w,

@@ -788,6 +788,129 @@ __global__ void __launch_bounds__(kThreads) interpolate_bilinear_kernel(const fl
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused resampling kernels: query coordinates are computed in-kernel and fed to
+// the same tfa-style bilinear sample, one thread per output pixel.
+// ------------------------------------------------------------------------------------------
+struct Mat3 {
+  float m[9];
+};
+
+// tf.linspace value i of n in float32: exact end points, start + delta * i inside
+__device__ __forceinline__ float linspace_at(float start, float stop, int n, int i) {
+  if (i == 0 || n == 1) return start;
+  if (i == n - 1) return stop;
+  return __fadd_rn(start, __fmul_rn(__fdiv_rn(__fsub_rn(stop, start), (float)(n - 1)), (float)i));
+}
+
+// equirectangular_pixel_rays (utils/pano_utils.py:92-114) for pixel (r, c) of an oh x 2*oh image
+__device__ __forceinline__ float3 pixel_ray(int oh, int r, int c) {
+  const float kPi = 3.14159274101257324f;
+  const float heading = linspace_at(-kPi, kPi, 2 * oh, c), pitch = linspace_at(0.0f, kPi, oh, r);
+  const float sp = sinf(pitch);
+  return make_float3(__fmul_rn(sp, sinf(heading)), -cosf(pitch), __fmul_rn(sp, cosf(heading)));
+}
+
+// tfa interpolate_bilinear of one query on an image with an optional virtual 1-pixel constant
+// border (pad = 1: the image behaves like tf.pad(image, 1, constant_values=pad_value)).
+__device__ __forceinline__ void bilinear_sample(const float* __restrict__ img, int H, int W, int C, float qy, float qx,
+                                                int pad, float pad_value, float* __restrict__ o) {
+  const int PH = H + 2 * pad, PW = W + 2 * pad;
+  const float fy = fminf(fmaxf(0.0f, floorf(qy)), (float)(PH - 2)), fx = fminf(fmaxf(0.0f, floorf(qx)), (float)(PW - 2));
+  const float ay = fminf(fmaxf(0.0f, __fsub_rn(qy, fy)), 1.0f), ax = fminf(fmaxf(0.0f, __fsub_rn(qx, fx)), 1.0f);
+  const int y0 = (int)fy - pad, x0 = (int)fx - pad;
+  for (int c = 0; c < C; ++c) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int y = y0 + (k >> 1), x = x0 + (k & 1);
+      v[k] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + ((size_t)y * W + x) * C + c) : pad_value;
+    }
+    const float top = __fadd_rn(__fmul_rn(ax, __fsub_rn(v[1], v[0])), v[0]);
+    const float bot = __fadd_rn(__fmul_rn(ax, __fsub_rn(v[3], v[2])), v[2]);
+    o[c] = __fadd_rn(__fmul_rn(ay, __fsub_rn(bot, top)), top);
+  }
+}
+
+__device__ __forceinline__ float3 mat3_mul(const float* m, float3 v) {
+  return make_float3(__fadd_rn(__fadd_rn(__fmul_rn(m[0], v.x), __fmul_rn(m[1], v.y)), __fmul_rn(m[2], v.z)),
+                     __fadd_rn(__fadd_rn(__fmul_rn(m[3], v.x), __fmul_rn(m[4], v.y)), __fmul_rn(m[5], v.z)),
+                     __fadd_rn(__fadd_rn(__fmul_rn(m[6], v.x), __fmul_rn(m[7], v.y)), __fmul_rn(m[8], v.z)));
+}
+
+// rotate_pano (utils/pano_utils.py:306-341): pano (N,H,W,C), matrix (N,3,3) -> (N,OH,2*OH,C)
+__global__ void __launch_bounds__(kThreads) rotate_pano_kernel(const float* __restrict__ pano, const float* __restrict__ matrix,
+                                                              int N, int H, int W, int C, int OH, float* __restrict__ out) {
+  const float kPi = 3.14159274101257324f, kTwoPi = 6.28318548202514648f;
+  const int OW = 2 * OH;
+  const long long total = (long long)N * OH * OW;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int c = (int)(i % OW), r = (int)((i / OW) % OH), b = (int)(i / ((long long)OW * OH));
+    const float3 v = mat3_mul(matrix + (size_t)b * 9, pixel_ray(OH, r, c));
+    const float pitch = acosf(-v.y), heading = atan2f(v.x, v.z);
+    const float qx = __fmul_rn(__fadd_rn(__fdiv_rn(heading, kTwoPi), 0.5f), (float)(W - 1));
+    const float qy = __fmul_rn(__fdiv_rn(pitch, kPi), (float)(H - 1));
+    bilinear_sample(pano + (size_t)b * H * W * C, H, W, C, qy, qx, 0, 0.0f, out + (size_t)i * C);
+  }
+}
+
+// project_perspective_image (utils/pano_utils.py:344-417): image (h,w,C) -> equirect (OH,2*OH,C).
+// w2i = world-to-image transform; pad = 1 for the 'constant' / 'mean' modes (virtual border of
+// pad_value), 0 for 'reflect' (no border, clamped sampling).
+__global__ void __launch_bounds__(kThreads) persp_to_equirect_kernel(const float* __restrict__ image, Mat3 w2i, int H, int W,
+                                                                    int C, int OH, int pad, float pad_value, int round_nearest,
+                                                                    float* __restrict__ out) {
+  const int OW = 2 * OH;
+  const long long total = (long long)OH * OW;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int c = (int)(i % OW), r = (int)(i / OW);
+    const float3 p = mat3_mul(w2i.m, pixel_ray(OH, r, c));
+    float qx = -1.0f, qy = -1.0f;
+    if (p.z > 0.0f) { qx = __fdiv_rn(p.x, p.z); qy = __fdiv_rn(p.y, p.z); }
+    if (round_nearest) { qx = rintf(qx); qy = rintf(qy); }  // tf.math.round: half to even
+    if (pad) { qx = __fadd_rn(qx, 1.0f); qy = __fadd_rn(qy, 1.0f); }
+    bilinear_sample(image, H, W, C, qy, qx, pad, pad_value, out + (size_t)i * C);
+  }
+}
+
+// get_perspective_from_equirectangular_image (utils/pano_utils.py:443-476):
+// equirect (EH,EW,C) -> perspective (PH,PW,C); kinv_t = inv(K)^T, rot = rotation matrix, applied as
+// row vectors ((x, y, 1) @ kinv_t) @ rot like the reference.
+__global__ void __launch_bounds__(kThreads) equirect_to_persp_kernel(const float* __restrict__ image, Mat3 kinv_t, Mat3 rot,
+                                                                    int EH, int EW, int C, int PH, int PW,
+                                                                    float* __restrict__ out) {
+  const float kPi = 3.14159274101257324f, kTwoPi = 6.28318548202514648f;
+  const long long total = (long long)PH * PW;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const float x = (float)(i % PW), y = (float)(i / PW);
+    // row vector times matrix: out_j = sum_k v_k * M[k][j]
+    const float* a = kinv_t.m;
+    const float3 t = make_float3(__fadd_rn(__fadd_rn(__fmul_rn(x, a[0]), __fmul_rn(y, a[3])), a[6]),
+                                 __fadd_rn(__fadd_rn(__fmul_rn(x, a[1]), __fmul_rn(y, a[4])), a[7]),
+                                 __fadd_rn(__fadd_rn(__fmul_rn(x, a[2]), __fmul_rn(y, a[5])), a[8]));
+    const float* m = rot.m;
+    float3 v = make_float3(__fadd_rn(__fadd_rn(__fmul_rn(t.x, m[0]), __fmul_rn(t.y, m[3])), __fmul_rn(t.z, m[6])),
+                           __fadd_rn(__fadd_rn(__fmul_rn(t.x, m[1]), __fmul_rn(t.y, m[4])), __fmul_rn(t.z, m[7])),
+                           __fadd_rn(__fadd_rn(__fmul_rn(t.x, m[2]), __fmul_rn(t.y, m[5])), __fmul_rn(t.z, m[8])));
+    const float norm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z)));
+    v.x = __fdiv_rn(v.x, norm); v.y = __fdiv_rn(v.y, norm); v.z = __fdiv_rn(v.z, norm);
+    const float lon = atan2f(v.x, v.z), lat = asinf(v.y);
+    const float qx = __fmul_rn(__fadd_rn(__fdiv_rn(lon, kTwoPi), 0.5f), (float)(EW - 1));
+    const float qy = __fmul_rn(__fadd_rn(__fdiv_rn(lat, kPi), 0.5f), (float)(EH - 1));
+    bilinear_sample(image, EH, EW, C, qy, qx, 0, 0.0f, out + (size_t)i * C);
+  }
+}
+
+// equirectangular_pixel_rays as a tensor (3, OH * 2*OH)
+__global__ void __launch_bounds__(kThreads) pixel_rays_kernel(int OH, float* __restrict__ out) {
+  const int OW = 2 * OH;
+  const long long total = (long long)OH * OW;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const float3 v = pixel_ray(OH, (int)(i / OW), (int)(i % OW));
+    out[i] = v.x; out[total + i] = v.y; out[2 * total + i] = v.z;
+  }
+}
+
 // tf.image.resize with half_pixel_centers (TF 2.x), used by equirectangular_to_pointcloud when
 // size_mult != 1 (utils/pano_utils.py:203-208).  NEAREST keeps the dtype:
 // in = min(floor((out + 0.5) * scale), in_size - 1); BILINEAR returns float32:

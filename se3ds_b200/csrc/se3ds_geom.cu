@@ -660,6 +660,51 @@ int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, floa
   return launch_check("apply_bin_kernel");
 }
 
+int se3ds_pixel_rays(int output_height, float* out, void* stream) {
+  if (!out || output_height <= 0) return fail(SE3DS_ERR_BAD_ARG, "bad argument");
+  const long long total = 2ll * output_height * output_height;
+  pixel_rays_kernel<<<(int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32), kThreads, 0, (cudaStream_t)stream>>>(output_height, out);
+  return launch_check("pixel_rays_kernel");
+}
+
+int se3ds_rotate_pano(const float* pano, const float* matrix, int n, int h, int w, int c, int output_height,
+                      float* out, void* stream) {
+  if (!pano || !matrix || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (n < 0 || h < 2 || c <= 0 || output_height <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "pano must be (N,H,W,C)");
+  if (w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "Pano width must be twice height.");
+  const long long total = (long long)n * output_height * 2 * output_height;
+  if (total == 0) return SE3DS_OK;
+  rotate_pano_kernel<<<(int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32), kThreads, 0, (cudaStream_t)stream>>>(
+      pano, matrix, n, h, w, c, output_height, out);
+  return launch_check("rotate_pano_kernel");
+}
+
+int se3ds_project_perspective_image(const float* image, int h, int w, int c, const float world_to_image[9],
+                                    int output_height, int pad, float pad_value, int round_to_nearest, float* out,
+                                    void* stream) {
+  if (!image || !world_to_image || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (h < 1 || w < 1 || c <= 0 || output_height <= 0 || (!pad && (h < 2 || w < 2))) return fail(SE3DS_ERR_BAD_SHAPE, "image must be (H,W,C)");
+  Mat3 m;
+  memcpy(m.m, world_to_image, sizeof(m.m));
+  const long long total = 2ll * output_height * output_height;
+  persp_to_equirect_kernel<<<(int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32), kThreads, 0, (cudaStream_t)stream>>>(
+      image, m, h, w, c, output_height, pad ? 1 : 0, pad_value, round_to_nearest, out);
+  return launch_check("persp_to_equirect_kernel");
+}
+
+int se3ds_perspective_from_equirect(const float* image, int eq_h, int eq_w, int c, const float kinv_t[9],
+                                    const float rotation[9], int height, int width, float* out, void* stream) {
+  if (!image || !kinv_t || !rotation || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (eq_h < 2 || eq_w < 2 || c <= 0 || height <= 0 || width <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "image must be (H,W,C)");
+  Mat3 a, r;
+  memcpy(a.m, kinv_t, sizeof(a.m));
+  memcpy(r.m, rotation, sizeof(r.m));
+  const long long total = (long long)height * width;
+  equirect_to_persp_kernel<<<(int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32), kThreads, 0, (cudaStream_t)stream>>>(
+      image, a, r, eq_h, eq_w, c, height, width, out);
+  return launch_check("equirect_to_persp_kernel");
+}
+
 int se3ds_resize(const void* in, int dtype, int n, int h, int w, int c, int out_h, int out_w, int bilinear,
                  void* out, void* stream) {
   if (!in || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");

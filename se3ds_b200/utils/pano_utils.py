@@ -130,20 +130,10 @@ def project_feats_to_equirectangular(feats: torch.Tensor, xyz1: torch.Tensor, he
 
 # ------------------------------------------------------------------------------------------
 # "Next" rows: the bilinear resampling functions of the reference's pano_utils.
-# The gather (the heavy part) is the CUDA kernel behind se3ds_interpolate_bilinear; the per-pixel
-# query coordinates are a handful of elementwise device ops, as in the reference.
+# Each function is one fused CUDA kernel (query coordinates computed in-kernel, then the tfa-style
+# bilinear sample); se3ds_interpolate_bilinear exposes the gather on its own.  Only the 3x3 camera
+# matrices are host-side arithmetic, exactly as the reference builds them.
 # ------------------------------------------------------------------------------------------
-def _tf_linspace(start: float, stop: float, num: int, device) -> torch.Tensor:
-  """tf.linspace in float32: exact end points, start + delta * i inside."""
-  start_t = torch.tensor(start, dtype=torch.float32, device=device)
-  stop_t = torch.tensor(stop, dtype=torch.float32, device=device)
-  if num == 1:
-    return start_t[None]
-  delta = (stop_t - start_t) / torch.tensor(float(num - 1), dtype=torch.float32, device=device)
-  inner = start_t + delta * torch.arange(1, num - 1, dtype=torch.float32, device=device)
-  return torch.cat([start_t[None], inner, stop_t[None]])
-
-
 def interpolate_bilinear(grid: torch.Tensor, query_points: torch.Tensor, indexing: str = 'ij') -> torch.Tensor:
   """tensorflow_addons.image.interpolate_bilinear: grid (B,H,W,C), query_points (B,N,2) -> (B,N,C)."""
   if indexing not in ('ij', 'xy'):
@@ -167,18 +157,25 @@ def interpolate_bilinear(grid: torch.Tensor, query_points: torch.Tensor, indexin
   return out
 
 
+def _mat9(m) -> "ctypes.Array":
+  """Row-major 3x3 host matrix as a C float[9]."""
+  import ctypes
+  vals = [float(v) for v in torch.as_tensor(m, dtype=torch.float32).cpu().reshape(-1)]
+  if len(vals) != 9:
+    raise ValueError(f'expected a 3x3 matrix, got {len(vals)} values')
+  return (ctypes.c_float * 9)(*vals)
+
+
 def equirectangular_pixel_rays(output_height: int, device=None) -> torch.Tensor:
   """Unit-ball point of every equirectangular pixel, (3, H*2H) (reference pano_utils.py:92-114):
   x right, y down, z forward at the image centre."""
-  device = device or torch.device('cuda', torch.cuda.current_device())
-  output_width = int(float(output_height) * 2)
-  heading = _tf_linspace(-math.pi, math.pi, output_width, device)
-  pitch = _tf_linspace(0.0, math.pi, output_height, device)
-  heading, pitch = heading[None, :], pitch[:, None]
-  xs = torch.sin(pitch) * torch.sin(heading)
-  ys = (-torch.cos(pitch)).expand(output_height, output_width)
-  zs = torch.sin(pitch) * torch.cos(heading)
-  return torch.stack([xs, ys, zs], dim=0).reshape(3, -1)
+  device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+  if not torch.cuda.is_available():
+    raise _lib.Se3dsError('no CUDA device: the geometric guidance path has no CPU fallback')
+  output_height = int(output_height)
+  out = torch.empty((3, output_height * 2 * output_height), dtype=torch.float32, device=device)
+  _lib.check(_lib.load().se3ds_pixel_rays(output_height, _lib.ptr(out), _lib.stream_handle(device)))
+  return out
 
 
 def get_world_to_image_transform(image_shape, fov, camera_intrinsics: Optional[torch.Tensor] = None,
@@ -230,57 +227,45 @@ def rotate_pano(pano: torch.Tensor, matrix: torch.Tensor, output_height: Optiona
   n, h, w, c = pano.shape
   if w != h * 2:
     raise ValueError('Pano width must be twice height.')
-  pano = _as_tensor(pano, 'pano').to(torch.float32)
+  pano = _as_tensor(pano, 'pano').to(torch.float32).contiguous()
   oh = h if output_height is None else int(output_height)
-  matrix = _as_tensor(matrix, 'matrix').to(device=pano.device, dtype=torch.float32)
-  rays = equirectangular_pixel_rays(oh, pano.device)
-  rot = torch.matmul(matrix, rays[None])
-  x, y, z = rot[:, 0], rot[:, 1], rot[:, 2]
-  pitch = torch.acos(-y)
-  heading = torch.atan2(x, z)
-  heading_pixels = (heading / (2 * math.pi) + 0.5) * (w - 1)
-  pitch_pixels = pitch / math.pi * (h - 1)
-  coords = torch.stack([pitch_pixels, heading_pixels], dim=-1)
-  return interpolate_bilinear(pano, coords).reshape(n, oh, 2 * oh, c)
+  matrix = _as_tensor(matrix, 'matrix').to(device=pano.device, dtype=torch.float32).reshape(n, 3, 3).contiguous()
+  out = torch.empty((n, oh, 2 * oh, c), dtype=torch.float32, device=pano.device)
+  _lib.check(_lib.load().se3ds_rotate_pano(_lib.ptr(pano), _lib.ptr(matrix), n, h, w, c, oh, _lib.ptr(out),
+                                           _lib.stream_handle(pano.device)))
+  return out
 
 
 def project_perspective_image(image, fov, output_height, camera_intrinsics=None, rotations=None,
                               rotation_matrix=None, pad_mode='constant', pad_value=0.0, round_to_nearest=False):
   """Perspective (h,w,c) -> equirectangular (H,2H,c) (reference pano_utils.py:344-417)."""
   assert pad_mode in {'reflect', 'constant', 'mean'}, ('Unsupported pad mode: %s' % pad_mode)
-  image = _as_tensor(image, 'image').to(torch.float32)[None]
-  output_width = 2 * output_height
-  world = equirectangular_pixel_rays(output_height, image.device)
-  w2i = get_world_to_image_transform((image.shape[1], image.shape[2]), fov, camera_intrinsics=camera_intrinsics,
-                                     rotations=rotations, rotation_matrix=rotation_matrix).to(image.device)
-  ic = (w2i @ world).t()
-  xy, zs = ic[:, :2], ic[:, 2:]
-  ic = torch.where((zs > 0).expand(-1, 2), xy / zs, -torch.ones_like(xy))
-  if round_to_nearest:
-    ic = torch.round(ic)
-  if pad_mode != 'reflect':
-    cv = float(image.mean()) if pad_mode == 'mean' else float(pad_value)
-    image = torch.nn.functional.pad(image, (0, 0, 1, 1, 1, 1), mode='constant', value=cv)
-    ic = ic + 1.
-  out = interpolate_bilinear(image, ic[None], indexing='xy')
-  return out.reshape(output_height, output_width, -1)
+  image = _as_tensor(image, 'image', validate_only=True)
+  if image.dim() != 3:
+    raise ValueError(f'image should be (height, width, channels), got {tuple(image.shape)}')
+  image = _as_tensor(image, 'image').to(torch.float32).contiguous()
+  h, w, c = image.shape
+  w2i = get_world_to_image_transform((h, w), fov, camera_intrinsics=camera_intrinsics, rotations=rotations,
+                                     rotation_matrix=rotation_matrix)
+  pad = pad_mode != 'reflect'
+  cv = float(image.mean()) if pad_mode == 'mean' else float(pad_value)
+  out = torch.empty((int(output_height), 2 * int(output_height), c), dtype=torch.float32, device=image.device)
+  _lib.check(_lib.load().se3ds_project_perspective_image(
+      _lib.ptr(image), h, w, c, _mat9(w2i), int(output_height), int(pad), cv if pad else 0.0, int(bool(round_to_nearest)),
+      _lib.ptr(out), _lib.stream_handle(image.device)))
+  return out
 
 
 def get_perspective_from_equirectangular_image(image, camera_intrinsics, rotation_matrix, height, width):
   """Equirectangular (He,We,C) -> perspective (height,width,C) (reference pano_utils.py:443-476)."""
-  image = _as_tensor(image, 'image').to(torch.float32)
+  image = _as_tensor(image, 'image', validate_only=True)
+  if image.dim() != 3:
+    raise ValueError(f'image should be (H, W, C), got {tuple(image.shape)}')
+  image = _as_tensor(image, 'image').to(torch.float32).contiguous()
   eq_height, eq_width, channels = image.shape
-  dev = image.device
-  y, x = torch.meshgrid(torch.arange(height, device=dev), torch.arange(width, device=dev), indexing='ij')
-  xyz = torch.stack([x, y, torch.ones_like(x)], dim=-1).to(torch.float32)
-  k_inv = torch.linalg.inv(torch.as_tensor(camera_intrinsics, dtype=torch.float32).cpu()).to(dev)
-  rot = torch.as_tensor(rotation_matrix, dtype=torch.float32).to(dev)
-  xyz = (xyz @ k_inv.t()) @ rot
-  nrm = xyz / torch.linalg.norm(xyz, dim=-1, keepdim=True)
-  lon = torch.atan2(nrm[..., 0:1], nrm[..., 2:])
-  lat = torch.asin(nrm[..., 1:2])
-  u = (lon / (2 * math.pi) + 0.5) * (eq_width - 1)
-  v = (lat / math.pi + 0.5) * (eq_height - 1)
-  uv = torch.cat([u, v], dim=-1).reshape(-1, 2)
-  out = interpolate_bilinear(image[None], uv[None], indexing='xy')
-  return out.reshape(height, width, channels)
+  k_inv_t = torch.linalg.inv(torch.as_tensor(camera_intrinsics, dtype=torch.float32).cpu()).t().contiguous()
+  out = torch.empty((int(height), int(width), channels), dtype=torch.float32, device=image.device)
+  _lib.check(_lib.load().se3ds_perspective_from_equirect(
+      _lib.ptr(image), eq_height, eq_width, channels, _mat9(k_inv_t), _mat9(rotation_matrix), int(height), int(width),
+      _lib.ptr(out), _lib.stream_handle(image.device)))
+  return out

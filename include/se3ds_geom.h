@@ -190,6 +190,13 @@ int se3ds_resize(const void* in, int dtype, int n, int h, int w, int c, int out_
 int se3ds_interpolate_bilinear(const float* grid, const float* query_points, int b, int h, int w, int c,
                                long long num_queries, int indexing_xy, float* out, void* stream);
 
+/* utils/point_cloud_utils.py:32-87 get_filtered_coords_and_feats (legacy perspective unprojection;
+ * only the reference's tests call it).  feats (N,H,W,C) dtype, depth (N,H,W) f32 -> xyz (N,4,H*W) f32,
+ * feats_out (N,H*W,C) f32; kinv_x / kinv_y = the diagonal of inv(get_intrinsic_matrix(HFOV)). */
+int se3ds_filtered_coords_and_feats(const void* feats, int dtype, const float* depth, int n, int h, int w, int c,
+                                    float depth_scale, float kinv_x, float kinv_y, float* xyz_out, float* feats_out,
+                                    void* stream);
+
 /* Fused forms of the resampling functions (coordinates computed in-kernel, then the same bilinear
  * sample).  All tensors f32 on the device; the 3x3 matrices of the last two are HOST arrays
  * (row-major), computed by the caller exactly as the reference computes them.

@@ -57,6 +57,7 @@ SIGNATURES = {
                              _vp, _vp],
     'se3ds_resize': [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     'se3ds_interpolate_bilinear': [_vp, _vp, _i, _i, _i, _i, _ll, _i, _vp, _vp],
+    'se3ds_filtered_coords_and_feats': [_vp, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp],
     'se3ds_pixel_rays': [_i, _vp, _vp],
     'se3ds_rotate_pano': [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     'se3ds_project_perspective_image': [_vp, _i, _i, _i, _c.POINTER(_f * 9), _i, _i, _f, _i, _vp, _vp],

@@ -944,6 +944,32 @@ __global__ void __launch_bounds__(kThreads) resize_kernel(const TI* __restrict__
   }
 }
 
+// get_filtered_coords_and_feats (utils/point_cloud_utils.py:32-87, legacy perspective unprojection):
+// xs / ys = float32(tf.linspace(-1, 1, n) evaluated in float64), xyz = (xs*d, ys*d, d, 1) * mask,
+// then inv(K) @ xyz with K = diag(k, k, 1, 1); features are zeroed where the depth is invalid.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) filtered_coords_kernel(const T* __restrict__ feats, const float* __restrict__ depth,
+                                                                  int N, int H, int W, int C, float depth_scale, float kinv_x,
+                                                                  float kinv_y, float* __restrict__ xyz, float* __restrict__ out) {
+  const int HW = H * W;
+  const long long total = (long long)N * HW;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int b = (int)(i / HW), pix = (int)(i - (long long)b * HW);
+    const int r = pix / W, c = pix - r * W;
+    const float xs = (c == W - 1 || W == 1) ? (W == 1 ? -1.0f : 1.0f) : (float)(-1.0 + (2.0 / (double)(W - 1)) * (double)c);
+    const float ys = (r == H - 1 || H == 1) ? (H == 1 ? -1.0f : 1.0f) : (float)(-1.0 + (2.0 / (double)(H - 1)) * (double)r);
+    const float d = __fmul_rn(depth[i], depth_scale);
+    const bool valid = d > 0.0f && d < depth_scale;
+    const float m = valid ? 1.0f : 0.0f;
+    float* o = xyz + (size_t)b * 4 * HW + pix;
+    o[0] = __fmul_rn(kinv_x, __fmul_rn(__fmul_rn(xs, d), m));
+    o[HW] = __fmul_rn(kinv_y, __fmul_rn(__fmul_rn(ys, d), m));
+    o[2 * (size_t)HW] = __fmul_rn(d, m);
+    o[3 * (size_t)HW] = m;
+    for (int ch = 0; ch < C; ++ch) out[i * C + ch] = valid ? (float)feats[i * C + ch] : 0.0f;
+  }
+}
+
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -660,6 +660,22 @@ int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, floa
   return launch_check("apply_bin_kernel");
 }
 
+int se3ds_filtered_coords_and_feats(const void* feats, int dtype, const float* depth, int n, int h, int w, int c,
+                                    float depth_scale, float kinv_x, float kinv_y, float* xyz_out, float* feats_out,
+                                    void* stream) {
+  if (!feats || !depth || !xyz_out || !feats_out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (n < 0 || h <= 0 || w <= 0 || c <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "feats should have shape (N, H, W) or (N, H, W, C)");
+  const long long total = (long long)n * h * w;
+  if (total == 0) return SE3DS_OK;
+  const int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SE3DS_U8) filtered_coords_kernel<uint8_t><<<blocks, kThreads, 0, st>>>((const uint8_t*)feats, depth, n, h, w, c, depth_scale, kinv_x, kinv_y, xyz_out, feats_out);
+  else if (dtype == SE3DS_I32) filtered_coords_kernel<int><<<blocks, kThreads, 0, st>>>((const int*)feats, depth, n, h, w, c, depth_scale, kinv_x, kinv_y, xyz_out, feats_out);
+  else if (dtype == SE3DS_F32) filtered_coords_kernel<float><<<blocks, kThreads, 0, st>>>((const float*)feats, depth, n, h, w, c, depth_scale, kinv_x, kinv_y, xyz_out, feats_out);
+  else return fail(SE3DS_ERR_BAD_DTYPE, "dtype %d", dtype);
+  return launch_check("filtered_coords_kernel");
+}
+
 int se3ds_pixel_rays(int output_height, float* out, void* stream) {
   if (!out || output_height <= 0) return fail(SE3DS_ERR_BAD_ARG, "bad argument");
   const long long total = 2ll * output_height * output_height;

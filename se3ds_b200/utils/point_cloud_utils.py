@@ -63,34 +63,27 @@ def project_to_feat(transformed_coords: torch.Tensor, feats: torch.Tensor, heigh
 def get_filtered_coords_and_feats(feats: torch.Tensor, depth: torch.Tensor, depth_scale: float):
   """Legacy perspective unprojection (reference point_cloud_utils.py:32-87).
 
-  Only called from the reference's tests; kept for signature completeness.  It is a handful of
-  elementwise torch ops on the device (K ~ I for HFOV = 90 deg), not part of the accelerated path.
+  Args: feats (N,H,W) or (N,H,W,C) integer features; depth (N,H,W) in [0,1]; depth_scale.
+  Returns: xyz (N,4,H*W) float32; filtered feats (N,H*W[,C]) float32 (zero where depth is invalid).
   """
-  from .pano_utils import _as_tensor
+  from .pano_utils import _as_tensor, _canon_feats
   feats = _as_tensor(feats, 'feats', validate_only=True)
   if feats.dim() != 3 and feats.dim() != 4:
     raise ValueError('feats should have shape (N, H, W) or (N, H, W, C),'
                      f' got {tuple(feats.shape)} instead.')
-  feats = _as_tensor(feats, 'feats')
   is_scalar_feat = feats.dim() == 3
   if is_scalar_feat:
     feats = feats[..., None]
-  depth = _as_tensor(depth, 'depth').to(device=feats.device, dtype=torch.float32)
+  feats = _canon_feats(_as_tensor(feats, 'feats').contiguous())
+  depth = _as_tensor(depth, 'depth').to(device=feats.device, dtype=torch.float32).contiguous()
   batch_size, height, width = depth.shape
   channels = feats.shape[-1]
-  dev = feats.device
-  xs_1d = torch.linspace(-1, 1, width, dtype=torch.float64, device=dev).to(torch.float32)
-  ys_1d = torch.linspace(-1, 1, height, dtype=torch.float64, device=dev).to(torch.float32)
-  ys, xs = torch.meshgrid(ys_1d, xs_1d, indexing='ij')
-  d = (depth * depth_scale)[:, None, :, :]
-  xyz = torch.cat([xs[None, None] * d, ys[None, None] * d, d, torch.ones_like(d)], dim=1)
-  dflat = d.reshape(batch_size, -1)
-  depth_mask = (dflat > 0) & (dflat < depth_scale)
-  filtered = feats.reshape(batch_size, -1, channels) * depth_mask[..., None].to(torch.int32)
-  filtered = filtered.to(torch.float32)
-  k_inv = torch.linalg.inv(get_intrinsic_matrix(constants.HFOV)).to(dev)
-  xyz = xyz.reshape(batch_size, 4, -1) * depth_mask[:, None, :].to(torch.float32)
-  xyz = torch.matmul(k_inv, xyz)
+  k_inv = torch.linalg.inv(get_intrinsic_matrix(constants.HFOV))  # host, 4x4, diagonal
+  xyz = torch.empty((batch_size, 4, height * width), dtype=torch.float32, device=feats.device)
+  out = torch.empty((batch_size, height * width, channels), dtype=torch.float32, device=feats.device)
+  _lib.check(_lib.load().se3ds_filtered_coords_and_feats(
+      _lib.ptr(feats), _lib.dtype_code(feats), _lib.ptr(depth), batch_size, height, width, channels, float(depth_scale),
+      float(k_inv[0, 0]), float(k_inv[1, 1]), _lib.ptr(xyz), _lib.ptr(out), _lib.stream_handle(feats.device)))
   if is_scalar_feat:
-    filtered = filtered[..., 0]
-  return xyz, filtered
+    out = out[..., 0]
+  return xyz, out

@@ -353,8 +353,30 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     }
   }
   if (late_wait) pdl_wait();  // from here on: z-buffer, scratch and bins of this workspace
+  if (prefilter) {
+    // multi-frame jobs: issue the PPT filter reads together, then the reductions that can still win
+    unsigned long long cur[PPT];
 #pragma unroll
-  for (int k = 0; k < PPT; ++k) splat(scf[k], scr[k], pix0 + k);
+    for (int k = 0; k < PPT; ++k) {
+      const bool ok = !(scf[k] & (kScInvalid | kScDropped));
+      if constexpr (KEY64) cur[k] = ok ? __ldcg(zb + (scf[k] & kScPixMask)) : 0ull;
+      else cur[k] = ok ? (unsigned long long)__ldcg(zb32 + (scf[k] & kScPixMask)) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if (scf[k] & (kScInvalid | kScDropped)) continue;
+      if constexpr (KEY64) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(scr[k]) << 32) | ((idx_frame + (uint32_t)(pix0 + k)) << 1) | ((scf[k] & kScDepthInv) ? 1u : 0u);
+        if (key < cur[k]) atomicMin(zb + (scf[k] & kScPixMask), key);
+      } else {
+        const uint32_t key = __float_as_uint(scr[k]);
+        if (key < (uint32_t)cur[k]) atomicMin(zb32 + (scf[k] & kScPixMask), key);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) splat(scf[k], scr[k], pix0 + k);
+  }
   if (ix.active) {
     if constexpr (PPT == 4) {
       __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc_frame + pix0), make_uint4(scf[0], scf[1], scf[2], scf[3]));

@@ -1,18 +1,23 @@
 // kernels.cuh -- sm_100a kernels of the geometric guidance path.
 //
 // Fused path (se3ds_reproject), three launches per job chunk, no point cloud in memory:
-//   K2 splat_depth_kernel : RGB-D planes -> unproject -> +src -tgt -> project -> 64-bit
-//                           (depth bits | point index) REDG.MIN into the z-buffer; the per point
-//                           (pixel, depth) goes to an L2-resident scratch for K3.
-//   K3 splat_feat_kernel  : tolerance test d < dmin + 0.1 against the final z-buffer; surviving
-//                           non-winner points REDG.MAX.F16x4 their RGB into the feature buffer
-//                           (one 8-byte vector reduction = the reference's per-channel scatter-max);
-//                           rejected points are warp-reduced into the reject bin.
-//   K4 resolve_kernel     : per target pixel: gather the winner's RGB, merge with the feature
-//                           buffer and the bin, write proj_image / proj_depth / proj_mask / winner
-//                           once, re-arm z-buffer and feature buffer for the next chunk.
+//   K2 splat_depth_kernel : RGB-D planes -> unproject -> +src -tgt (-> rotate) -> project ->
+//                           REDG.MIN into the z-buffer: the 64-bit packed (depth bits | point
+//                           index) key when winner indices are wanted, the 32-bit depth bits
+//                           otherwise; per point (pixel, depth) goes to a scratch for K3.  The
+//                           projection is a certified MUFU fast path with a canonical (IEEE)
+//                           fallback for the few points it cannot certify.
+//   K3 splat_feat_kernel  : tolerance test d < dmin + 0.1 against the final z-buffer; every
+//                           surviving point REDG.MAX.F16x4 its RGB into the feature buffer (one
+//                           8-byte vector reduction = the reference's per-channel scatter-max);
+//                           rejected points are block-reduced into the reject bin.
+//   K4 resolve_kernel     : per target pixel, streaming: z-buffer + feature buffer (+ bin on the
+//                           owner pixel) -> proj_image / proj_depth / proj_mask / winner, written
+//                           once; re-arms the touched z-buffer / feature entries.
+// The three kernels are chained with programmatic dependent launch (pdl_enter).
 // Compat path (se3ds_unproject_equirect / se3ds_project_cloud) works on materialised clouds with
-// float32 features of any channel count.
+// float32 features of any channel count; the resampling kernels (rotate_pano, perspective <->
+// equirect, tf-style resize, tfa-style bilinear gather) are at the end of the file.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

@@ -144,6 +144,57 @@ def tf_resize(images: np.ndarray, size, method: str) -> np.ndarray:
   return (top + (bottom - top) * yl).astype(F32)
 
 
+def tf_resize_antialias_triangle(images: np.ndarray, size) -> np.ndarray:
+  """tf.image.resize(..., 'bilinear', antialias=True) == ScaleAndTranslate with the triangle kernel
+  (TF 2.8 core/kernels/image/scale_and_translate_op.cc, ComputeSpansCore + GatherSpans; not vendored
+  in /root/reference, restated from the published algorithm -- parity with TF's bits unpinned).
+  Per output coordinate x: sample = (x + 0.5) * in/out, kernel_scale = max(in/out, 1), the span covers
+  the source pixels whose centre lies within kernel_scale of the sample, clipped to the image, and the
+  triangle weights are normalised by their sum.  Used by crop_pano(resize_to_original=True),
+  utils/pano_utils.py:299-301.  Rows first, then columns, float32 throughout."""
+  images = np.asarray(images)
+  n, h, w, c = images.shape
+  oh, ow = int(size[0]), int(size[1])
+  def spans(in_size, out_size):
+    inv_scale = F32(in_size) / F32(out_size)
+    ks = max(inv_scale, F32(1.0))
+    mat = np.zeros((out_size, in_size), dtype=F32)
+    for x in range(out_size):
+      sample = (F32(x) + F32(0.5)) * inv_scale
+      lo = int(np.ceil(sample - ks - F32(0.5)))
+      hi = int(np.floor(sample + ks - F32(0.5)))
+      lo, hi = max(lo, 0), min(hi, in_size - 1)
+      src = np.arange(lo, hi + 1, dtype=F32)
+      wts = np.maximum(F32(0), F32(1) - np.abs((src + F32(0.5) - sample) / ks)).astype(F32)
+      tot = F32(wts.sum(dtype=F32))
+      if abs(tot) >= 1000 * np.finfo(F32).tiny:
+        wts = (wts * (F32(1) / tot)).astype(F32)
+      mat[x, lo:hi + 1] = wts
+    return mat
+  my, mx = spans(h, oh), spans(w, ow)
+  img = images.astype(F32)
+  rows = np.einsum('oh,nhwc->nowc', my, img).astype(F32)
+  return np.einsum('pw,nowc->nopc', mx, rows).astype(F32)
+
+
+def crop_pano(pano: np.ndarray, proportion: float = 0.125, method: str = 'bilinear',
+              resize_to_original: bool = False) -> np.ndarray:
+  """utils/pano_utils.py:268-303: crop int(H*p) rows top and bottom, optionally resize back
+  (antialiased; 'nearest' ignores antialias), cast to the input dtype (truncation for integers)."""
+  pano = np.asarray(pano)
+  squeeze = pano.ndim == 3
+  x = pano[None] if squeeze else pano
+  if x.ndim != 4:
+    raise ValueError(f'pano should be of shape (N, H, W, C), got {pano.shape} instead.')
+  _, h, w, _ = x.shape
+  mh = int(h * proportion)
+  x = x[:, mh:h - mh]
+  if resize_to_original:
+    x = tf_resize(x, (h, w), 'nearest') if method == 'nearest' else tf_resize_antialias_triangle(x, (h, w))
+  x = x.astype(pano.dtype)
+  return x[0] if squeeze else x
+
+
 def equirectangular_to_pointcloud(feats: np.ndarray, depth: np.ndarray, void_class,
                                   depth_scale: float, size_mult: float = 1.0,
                                   interpolation_method: str = 'nearest'):
@@ -605,16 +656,3 @@ def get_perspective_from_equirectangular_image(image, camera_intrinsics, rotatio
   return out.reshape(height, width, channels)
 
 
-def crop_pano(pano, proportion: float = 0.125, resize_to_original: bool = False):
-  """utils/pano_utils.py:268-303 (resize_to_original=False only: plain crop)."""
-  pano = np.asarray(pano)
-  if pano.ndim == 3:
-    height = pano.shape[0]
-  elif pano.ndim == 4:
-    height = pano.shape[1]
-  else:
-    raise ValueError(f'pano should be of shape (N, H, W, C), got {pano.shape} instead.')
-  if resize_to_original:
-    raise NotImplementedError('antialiased resize is not restated')
-  mh = int(height * proportion)
-  return pano[..., mh:height - mh, :, :]

@@ -213,10 +213,21 @@ def crop_pano(pano: torch.Tensor, proportion: float = 0.125, method: str = 'bili
     height = pano.shape[1]
   else:
     raise ValueError(f'pano should be of shape (N, H, W, C), got {tuple(pano.shape)} instead.')
-  if resize_to_original:
-    raise NotImplementedError('crop_pano(resize_to_original=True) needs the antialiased resize; not built yet')
   masked_height = int(height * proportion)
-  return pano[..., masked_height:height - masked_height, :, :].contiguous()
+  cropped = pano[..., masked_height:height - masked_height, :, :].contiguous()
+  if not resize_to_original:
+    return cropped
+  # tf.image.resize(..., antialias=True) back to (H, W): the crop is never taller than the original, so
+  # this is always an enlargement, where the antialiased triangle kernel has scale 1 and its normalised
+  # weights are the bilinear ones (width is unchanged: identity).  'nearest' ignores antialias.
+  if method not in ('bilinear', 'nearest'):
+    raise ValueError(f'Unsupported resize method: {method}')
+  cropped = _as_tensor(cropped, 'pano')
+  batched = cropped if cropped.dim() == 4 else cropped[None]
+  width = batched.shape[2]
+  resized = _resize(_canon_feats(batched).contiguous(), (height, width), method)
+  resized = resized.to(cropped.dtype)          # tf.cast: truncation toward zero for integer dtypes
+  return resized if cropped.dim() == 4 else resized[0]
 
 
 def rotate_pano(pano: torch.Tensor, matrix: torch.Tensor, output_height: Optional[int] = None) -> torch.Tensor:

@@ -67,6 +67,28 @@ def test_oracle_world_to_image_and_crop():
     R.crop_pano(np.zeros((4,)))
 
 
+def test_oracle_antialiased_resize():
+  rng = np.random.default_rng(5)
+  img = rng.uniform(0, 255, size=(2, 24, 32, 3)).astype(np.float32)
+  # same size: identity
+  np.testing.assert_array_equal(R.tf_resize_antialias_triangle(img, (24, 32)), img)
+  # enlargement: kernel scale 1, normalised triangle weights == bilinear weights
+  up = R.tf_resize_antialias_triangle(img, (32, 32))
+  np.testing.assert_allclose(up, R.tf_resize(img, (32, 32), 'bilinear'), rtol=0, atol=255 * 2e-6)
+  # reduction: a real low-pass (constant stays constant, mean preserved, differs from plain bilinear)
+  const = np.full((1, 32, 64, 1), 7.0, np.float32)
+  np.testing.assert_allclose(R.tf_resize_antialias_triangle(const, (8, 16)), 7.0, rtol=1e-6)
+  down = R.tf_resize_antialias_triangle(img, (12, 16))
+  assert abs(down.mean() - img.mean()) < 0.5
+  assert np.abs(down - R.tf_resize(img, (12, 16), 'bilinear')).max() > 1.0
+  # crop_pano back to the original size, dtype restored by truncation
+  pano = rng.integers(0, 256, size=(2, 64, 128, 3)).astype(np.uint8)
+  back = R.crop_pano(pano, resize_to_original=True)
+  assert back.shape == pano.shape and back.dtype == np.uint8
+  near = R.crop_pano(pano, method='nearest', resize_to_original=True)
+  assert set(np.unique(near)) <= set(np.unique(pano[:, 8:56]))
+
+
 # ------------------------------------------------------------------------------------------
 @pytest.fixture(scope='module')
 def gp():
@@ -150,5 +172,20 @@ def test_cuda_crop_and_transform(gp):
   torch, pano = gp
   x = torch.zeros((2, 64, 128, 3), dtype=torch.int32)
   assert tuple(pano.crop_pano(x).shape) == (2, 48, 128, 3)
+  rng = np.random.default_rng(9)
+  for dtype, method in ((np.float32, 'bilinear'), (np.uint8, 'bilinear'), (np.uint8, 'nearest'), (np.int32, 'nearest')):
+    src = rng.uniform(0, 255, size=(2, 64, 128, 3)).astype(dtype)
+    got = pano.crop_pano(torch.from_numpy(src).cuda(), method=method, resize_to_original=True)
+    want = R.crop_pano(src, method=method, resize_to_original=True)
+    assert tuple(got.shape) == src.shape and got.cpu().numpy().dtype == dtype
+    if method == 'nearest':
+      np.testing.assert_array_equal(got.cpu().numpy(), want)
+    elif dtype == np.float32:
+      np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=255 * 2e-6)
+    else:          # truncation can flip where the float result sits within rounding of an integer
+      diff = np.abs(got.cpu().numpy().astype(np.int32) - want.astype(np.int32))
+      assert diff.max() <= 1 and np.mean(diff > 0) < 1e-3
+  single = pano.crop_pano(torch.from_numpy(src[0]).cuda(), method='nearest', resize_to_original=True)
+  assert tuple(single.shape) == src.shape[1:]
   t = pano.get_world_to_image_transform((48, 64), [1.0, 1.2], rotations=[0.2, 0.4]).numpy()
   np.testing.assert_allclose(t, R.get_world_to_image_transform((48, 64), [1.0, 1.2], rotations=[0.2, 0.4]), atol=1e-5)

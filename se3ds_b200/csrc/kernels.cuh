@@ -514,97 +514,146 @@ __device__ __forceinline__ float clip01_div255(float v) {
   return fminf(fmaxf(q1, 0.0f), 1.0f);
 }
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one full 32 B sector per lane.
+__device__ __forceinline__ void ldcg_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void st_256(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// Loads the z-buffer keys and feature maxima of four consecutive pixels (flat entry e, multiple of 4).
+// !KEY64: depth bits go to the upper half, the index bits are all ones.
+template <bool KEY64>
+__device__ __forceinline__ void resolve_load4(const FusedParams& q, size_t e, unsigned long long (&key)[4], uint2 (&fv)[4]) {
+  if constexpr (KEY64) {
+    uint4 a, b;
+    ldcg_256(q.zbuf + e, a, b);
+    key[0] = ((unsigned long long)a.y << 32) | a.x; key[1] = ((unsigned long long)a.w << 32) | a.z;
+    key[2] = ((unsigned long long)b.y << 32) | b.x; key[3] = ((unsigned long long)b.w << 32) | b.z;
+  } else {
+    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(q.zbuf32 + e));
+    key[0] = ((unsigned long long)a.x << 32) | 0xFFFFFFFFu; key[1] = ((unsigned long long)a.y << 32) | 0xFFFFFFFFu;
+    key[2] = ((unsigned long long)a.z << 32) | 0xFFFFFFFFu; key[3] = ((unsigned long long)a.w << 32) | 0xFFFFFFFFu;
+  }
+  uint4 c, d;
+  ldcg_256(q.fbuf + e, c, d);
+  fv[0] = make_uint2(c.x, c.y); fv[1] = make_uint2(c.z, c.w);
+  fv[2] = make_uint2(d.x, d.y); fv[3] = make_uint2(d.z, d.w);
+}
+
+// One target pixel: z-buffer key + feature maxima -> (depth, mask, rgb, winner), including the owner
+// pixel of a reject bin (point_cloud_utils.py:160-162, models.py:282-293).
+__device__ __forceinline__ void resolve_pixel(const FusedParams& q, int job, int pix, unsigned long long key, uint2 fvk,
+                                              float& od, float& om, float* oi, int& ow) {
+  const bool per_job = q.flags & SE3DS_FLAG_BIN_PER_JOB;
+  const bool has = key != kZArmed;
+  const float radw = __uint_as_float((uint32_t)(key >> 32));
+  float zmin = has ? fminf(radw, q.depth_scale) : q.depth_scale;
+  float3 f = unpack_f16x4(fvk);  // per-channel max of every point that passed the tolerance test
+  ow = (has && radw <= q.depth_scale) ? (int)((uint32_t)key >> 1) : -1;
+  if ((pix == 0) && (per_job || job == 0) && q.bin_out == nullptr) {  // owner pixel of a reject bin
+    Bin* bin = q.bins + (per_job ? job : 0);
+    if (q.finalize_bins) {
+      if (bin->zneg) zmin = fminf(zmin, f32_unordered(~bin->zneg));
+      f.x = fmaxf(f.x, (float)bin->f[0]); f.y = fmaxf(f.y, (float)bin->f[1]); f.z = fmaxf(f.z, (float)bin->f[2]);
+      *bin = Bin{0u, {0, 0, 0}};  // re-arm
+    } else {
+      // more chunks will still add to the global bin: park this pixel's own values in it,
+      // patch_owner_kernel finishes the pixel after the last chunk.
+      atomicMax(&bin->zneg, ~f32_ordered(zmin));
+      atomicMax(&bin->f[0], (int)f.x); atomicMax(&bin->f[1], (int)f.y); atomicMax(&bin->f[2], (int)f.z);
+    }
+  }
+  const float depth = div_rcp(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale, q.inv_depth_scale);
+  od = depth;
+  if (q.flags & SE3DS_FLAG_RAW_FEATURES) {
+    oi[0] = f.x; oi[1] = f.y; oi[2] = f.z;
+  } else {
+    oi[0] = clip01_div255(f.x); oi[1] = clip01_div255(f.y); oi[2] = clip01_div255(f.z);
+  }
+  om = (depth > 0.0f && depth < 1.0f && f.x != -1.0f && f.y != -1.0f && f.z != -1.0f) ? 1.0f : 0.0f;
+}
+
+// Re-arms only what was touched (a touched feature buffer entry implies a touched z-buffer entry).
+template <bool KEY64>
+__device__ __forceinline__ void resolve_rearm4(const FusedParams& q, size_t e, const unsigned long long (&key)[4]) {
+  if (key[0] == kZArmed && key[1] == kZArmed && key[2] == kZArmed && key[3] == kZArmed) return;
+  const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), zero = make_uint4(0, 0, 0, 0);
+  if constexpr (KEY64) st_256(q.zbuf + e, ones, ones);
+  else *reinterpret_cast<uint4*>(q.zbuf32 + e) = ones;
+  st_256(q.fbuf + e, zero, zero);
+}
+
 template <int PPT, bool KEY64>
-__global__ void __launch_bounds__(kThreads, 12) resolve_kernel(const FusedParams q) {
+__global__ void __launch_bounds__(kThreads, KEY64 ? 10 : 12) resolve_kernel(const FusedParams q) {
   pdl_enter();
+  constexpr bool STAGED = PPT == 4;  // RGB stores go through shared memory (below)
+  __shared__ float4 stage[STAGED ? kThreads * 3 : 1];
   const int lj = blockIdx.z;
   int n, p;
   if (q.PC == 1) { n = q.n0 + lj; p = q.p0; } else { const int a = lj / q.PC; n = q.n0 + a; p = q.p0 + (lj - a * q.PC); }
   const int job = n * q.P + p;
   const int row = blockIdx.y;
   const int col0 = (blockIdx.x * kThreads + threadIdx.x) * PPT;
-  if (col0 >= q.W) return;
-  const int pix0 = row * q.W + col0;
-  unsigned long long* zb = q.zbuf + (size_t)lj * q.HW + pix0;
-  uint32_t* zb32 = q.zbuf32 + (size_t)lj * q.HW + pix0;
-  uint2* fb = q.fbuf + (size_t)lj * q.HW + pix0;
-  unsigned long long key[PPT];  // !KEY64: depth bits in the upper half, index bits all ones
-  uint2 fv[PPT];
-  if constexpr (PPT == 4) {
-    if constexpr (KEY64) {
-      const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(zb)), b = __ldcg(reinterpret_cast<const ulonglong2*>(zb + 2));
-      key[0] = a.x; key[1] = a.y; key[2] = b.x; key[3] = b.y;
-    } else {
-      const uint4 a = __ldcg(reinterpret_cast<const uint4*>(zb32));
-      key[0] = ((unsigned long long)a.x << 32) | 0xFFFFFFFFu; key[1] = ((unsigned long long)a.y << 32) | 0xFFFFFFFFu;
-      key[2] = ((unsigned long long)a.z << 32) | 0xFFFFFFFFu; key[3] = ((unsigned long long)a.w << 32) | 0xFFFFFFFFu;
+  if constexpr (STAGED) {
+    if (((blockIdx.x * kThreads + (threadIdx.x & ~31)) + 32) * PPT > q.W) {  // ragged warp: plain path
+      if (col0 >= q.W) return;
     }
-    const uint4 c = __ldcg(reinterpret_cast<const uint4*>(fb)), e = __ldcg(reinterpret_cast<const uint4*>(fb + 2));
-    fv[0] = make_uint2(c.x, c.y); fv[1] = make_uint2(c.z, c.w);
-    fv[2] = make_uint2(e.x, e.y); fv[3] = make_uint2(e.z, e.w);
   } else {
-    key[0] = KEY64 ? zb[0] : (((unsigned long long)zb32[0] << 32) | 0xFFFFFFFFu);
-    fv[0] = fb[0];
+    if (col0 >= q.W) return;
   }
-  const bool per_job = q.flags & SE3DS_FLAG_BIN_PER_JOB;
-  float od[PPT], om[PPT], oi[3 * PPT];
-  int ow[PPT];
-#pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    const bool has = key[k] != kZArmed;
-    const float radw = __uint_as_float((uint32_t)(key[k] >> 32));
-    float zmin = has ? fminf(radw, q.depth_scale) : q.depth_scale;
-    float3 f = unpack_f16x4(fv[k]);  // per-channel max of every point that passed the tolerance test
-    ow[k] = (has && radw <= q.depth_scale) ? (int)((uint32_t)key[k] >> 1) : -1;
-    if ((pix0 + k == 0) && (per_job || job == 0) && q.bin_out == nullptr) {  // owner pixel of a reject bin
-      Bin* bin = q.bins + (per_job ? job : 0);
-      if (q.finalize_bins) {
-        if (bin->zneg) zmin = fminf(zmin, f32_unordered(~bin->zneg));
-        f.x = fmaxf(f.x, (float)bin->f[0]); f.y = fmaxf(f.y, (float)bin->f[1]); f.z = fmaxf(f.z, (float)bin->f[2]);
-        *bin = Bin{0u, {0, 0, 0}};  // re-arm
-      } else {
-        // more chunks will still add to the global bin: park this pixel's own values in it,
-        // patch_owner_kernel finishes the pixel after the last chunk.
-        atomicMax(&bin->zneg, ~f32_ordered(zmin));
-        atomicMax(&bin->f[0], (int)f.x); atomicMax(&bin->f[1], (int)f.y); atomicMax(&bin->f[2], (int)f.z);
-      }
-    }
-    // point_cloud_utils.py:160-162, models.py:282-293
-    const float depth = div_rcp(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale, q.inv_depth_scale);
-    od[k] = depth;
-    if (q.flags & SE3DS_FLAG_RAW_FEATURES) {
-      oi[3 * k + 0] = f.x; oi[3 * k + 1] = f.y; oi[3 * k + 2] = f.z;
-    } else {
-      oi[3 * k + 0] = clip01_div255(f.x); oi[3 * k + 1] = clip01_div255(f.y); oi[3 * k + 2] = clip01_div255(f.z);
-    }
-    om[k] = (depth > 0.0f && depth < 1.0f && f.x != -1.0f && f.y != -1.0f && f.z != -1.0f) ? 1.0f : 0.0f;
-  }
+  const int pix0 = row * q.W + col0;
+  const size_t e = (size_t)lj * q.HW + pix0;
   const size_t o = (size_t)job * q.HW + pix0;
   if constexpr (PPT == 4) {
+    unsigned long long key[4];
+    uint2 fv[4];
+    resolve_load4<KEY64>(q, e, key, fv);
+    float od[4], om[4], oi[12];
+    int ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) resolve_pixel(q, job, pix0 + k, key[k], fv[k], od[k], om[k], oi + 3 * k, ow[k]);
     __stcs(reinterpret_cast<float4*>(q.out_depth + o), make_float4(od[0], od[1], od[2], od[3]));
     __stcs(reinterpret_cast<float4*>(q.out_mask + o), make_float4(om[0], om[1], om[2], om[3]));
     float4* im = reinterpret_cast<float4*>(q.out_image + o * 3);
-    __stcs(im, make_float4(oi[0], oi[1], oi[2], oi[3]));
-    __stcs(im + 1, make_float4(oi[4], oi[5], oi[6], oi[7]));
-    __stcs(im + 2, make_float4(oi[8], oi[9], oi[10], oi[11]));
-    if (q.out_winner) __stcs(reinterpret_cast<int4*>(q.out_winner + o), make_int4(ow[0], ow[1], ow[2], ow[3]));
-    // re-arm only what was touched (a touched feature buffer entry implies a touched z-buffer entry)
-    const bool t01 = key[0] != kZArmed || key[1] != kZArmed, t23 = key[2] != kZArmed || key[3] != kZArmed;
-    if constexpr (KEY64) {
-      const ulonglong2 arm = make_ulonglong2(kZArmed, kZArmed);
-      if (t01) *reinterpret_cast<ulonglong2*>(zb) = arm;
-      if (t23) *reinterpret_cast<ulonglong2*>(zb + 2) = arm;
-    } else {
-      if (t01 || t23) *reinterpret_cast<uint4*>(zb32) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    bool direct = true;
+    if constexpr (STAGED) {
+      // a full warp holds 128 consecutive pixels of one row: pass the RGB (48 B per lane) through
+      // shared memory so that each store instruction writes 512 contiguous bytes
+      const unsigned lane = threadIdx.x & 31u;
+      if (((blockIdx.x * kThreads + (threadIdx.x & ~31)) + 32) * PPT <= q.W) {
+        direct = false;
+        float4* wstage = stage + (threadIdx.x >> 5) * 96;
+        wstage[lane * 3 + 0] = make_float4(oi[0], oi[1], oi[2], oi[3]);
+        wstage[lane * 3 + 1] = make_float4(oi[4], oi[5], oi[6], oi[7]);
+        wstage[lane * 3 + 2] = make_float4(oi[8], oi[9], oi[10], oi[11]);
+        __syncwarp();
+        float4* im0 = im - lane * 3;
+        __stcs(im0 + lane, wstage[lane]);
+        __stcs(im0 + 32 + lane, wstage[32 + lane]);
+        __stcs(im0 + 64 + lane, wstage[64 + lane]);
+      }
     }
-    if (t01) *reinterpret_cast<uint4*>(fb) = make_uint4(0, 0, 0, 0);
-    if (t23) *reinterpret_cast<uint4*>(fb + 2) = make_uint4(0, 0, 0, 0);
+    if (direct) {
+      __stcs(im, make_float4(oi[0], oi[1], oi[2], oi[3]));
+      __stcs(im + 1, make_float4(oi[4], oi[5], oi[6], oi[7]));
+      __stcs(im + 2, make_float4(oi[8], oi[9], oi[10], oi[11]));
+    }
+    if (q.out_winner) __stcs(reinterpret_cast<int4*>(q.out_winner + o), make_int4(ow[0], ow[1], ow[2], ow[3]));
+    resolve_rearm4<KEY64>(q, e, key);
   } else {
-    q.out_depth[o] = od[0]; q.out_mask[o] = om[0];
+    const unsigned long long key = KEY64 ? q.zbuf[e] : (((unsigned long long)q.zbuf32[e] << 32) | 0xFFFFFFFFu);
+    float od, om, oi[3];
+    int ow;
+    resolve_pixel(q, job, pix0, key, q.fbuf[e], od, om, oi, ow);
+    q.out_depth[o] = od; q.out_mask[o] = om;
     for (int c = 0; c < 3; ++c) q.out_image[o * 3 + c] = oi[c];
-    if (q.out_winner) q.out_winner[o] = ow[0];
-    if constexpr (KEY64) zb[0] = kZArmed; else zb32[0] = 0xFFFFFFFFu;
-    fb[0] = make_uint2(0, 0);
+    if (q.out_winner) q.out_winner[o] = ow;
+    if constexpr (KEY64) q.zbuf[e] = kZArmed; else q.zbuf32[e] = 0xFFFFFFFFu;
+    q.fbuf[e] = make_uint2(0, 0);
   }
 }
 

@@ -55,7 +55,7 @@ constexpr size_t kDefaultChunkBytes = (size_t)112 << 20;
 }  // namespace
 
 struct se3ds_ws {
-  int device = 0;
+  int device = 0, sm_count = 148;
   size_t max_bytes = kDefaultMaxBytes, chunk_bytes = kDefaultChunkBytes;
   DevBuf zbuf, zbuf32, fbuf, scf, scr, bins, cbin;
   std::vector<TableEntry> tables;
@@ -248,6 +248,7 @@ int se3ds_ws_create(int device, size_t max_bytes, size_t l2_chunk_bytes, se3ds_w
   CU(cudaSetDevice(device));
   se3ds_ws* ws = new se3ds_ws();
   ws->device = device;
+  cudaDeviceGetAttribute(&ws->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (max_bytes) ws->max_bytes = max_bytes;
   if (l2_chunk_bytes) ws->chunk_bytes = l2_chunk_bytes;
   *out = ws;

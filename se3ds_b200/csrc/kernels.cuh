@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
 // K3: tolerance test + per-channel max of the surviving features
 // ------------------------------------------------------------------------------------------
 template <typename RGB_T, int PPT, bool KEY64>
-__global__ void __launch_bounds__(kThreads) splat_feat_kernel(const FusedParams q) {
+__global__ void __launch_bounds__(kThreads, 16) splat_feat_kernel(const FusedParams q) {
   pdl_enter();
   const SrcIdx ix = src_index<PPT>(q);
   // The feature buffer and the reject bin start at 0 (output_void_class) and only take maxima, so a

@@ -243,6 +243,10 @@ def main():
   ap.add_argument('--chunk-mb', type=int, default=0, help='workspace L2 chunk size (0 = library default)')
   ap.add_argument('--n-override', type=int, default=0, help='override the batch size of the config (memory-bounded runs)')
   ap.add_argument('--key64', action='store_true', help='force the 64-bit packed depth|index z-buffer key')
+  ap.add_argument('--streams', type=int, default=1, help='independent batches alternate between this many (workspace, stream) '
+                  'pairs, the way a server overlaps independent requests; 1 = every step on one stream')
+  ap.add_argument('--lanes', type=int, default=0, help='concurrent chunk lanes of one call (0 = library default, 2)')
+  ap.add_argument('--lane-chunks', type=int, default=0, help='minimum chunks per lane (0 = library default, 2)')
   ap.add_argument('--no-pdl', action='store_true', help='disable programmatic dependent launch')
   ap.add_argument('--sharded', action='store_true', help='strong scaling: shard the jobs of ONE call over the ranks and '
                   'all-gather the guidance tensors (NCCL) inside the timed step (se3ds_b200.parallel)')
@@ -283,9 +287,16 @@ def main():
   # ring of distinct input/output sets larger than 2x L2, so every step starts cold in L2
   set_bytes = src_bytes + out_bytes
   ring = max(2, min(16, -(-2 * L2_BYTES // set_bytes) + 1))
-  ws = _lib.Workspace(local_rank, 0, args.chunk_mb << 20)
-  ws.projection_mode(args.proj_mode)
-  ws.pdl(not args.no_pdl)
+  nst = 1 if args.graph else max(1, args.streams)
+  wss = []
+  for _ in range(nst):
+    w_ = _lib.Workspace(local_rank, 0, args.chunk_mb << 20)
+    w_.projection_mode(args.proj_mode)
+    w_.pdl(not args.no_pdl)
+    if args.lanes:
+      w_.lanes(args.lanes, 0, args.lane_chunks)
+    wss.append(w_)
+  ws = wss[0]
   plans = []
   for r in range(ring):
     # every set differs only in its seed; large configs reuse one generated item per set
@@ -294,34 +305,43 @@ def main():
     if gen_n < n:
       inp = {k: np.concatenate([v] * (n // gen_n), axis=0) for k, v in inp.items()}
     t = {k: torch.as_tensor(v).to(dev) for k, v in inp.items()}
-    plans.append(guidance.prepare(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, workspace=ws,
-                                  key64=args.key64, inputs_ready=True))
+    plans.append([guidance.prepare(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, workspace=w_,
+                                   key64=args.key64, inputs_ready=True) for w_ in wss])
   host_inp = {k: torch.as_tensor(v).pin_memory() for k, v in inp.items()}
 
-  stream = torch.cuda.Stream(dev)
+  streams = [torch.cuda.Stream(dev) for _ in range(nst)]
+  stream = streams[0]
+
+  def launches_so_far():
+    return sum(w_.profile_read()[1] for w_ in wss)
+
   with torch.cuda.stream(stream):
-    for pl in plans:  # grows the workspace, uploads tables
-      pl.run()
+    for row in plans:  # grows the workspaces, uploads tables
+      for pl in row:
+        pl.run()
     stream.synchronize()
     graphs = None
     if args.graph:
       graphs = []
-      for pl in plans:
+      for row in plans:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=stream):
-          pl.run()
+          row[0].run()
         graphs.append(g)
-    launches_a = ws.profile_read()[1]
-    plans[0].run()
+    launches_a = launches_so_far()
+    plans[0][0].run()
     stream.synchronize()
-    launches0 = ws.profile_read()[1]
+    launches0 = launches_so_far()
     launches_per_step = launches0 - launches_a
 
     def step(i):
       if graphs is not None:
         graphs[i % ring].replay()
+      elif nst == 1:
+        plans[i % ring][0].run()
       else:
-        plans[i % ring].run()
+        with torch.cuda.stream(streams[i % nst]):
+          plans[i % ring][i % nst].run()
 
     def barrier():
       stream.synchronize()
@@ -336,19 +356,25 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    for k in range(1, nst):
+      streams[k].wait_event(e0)
     for i in range(args.steps):
       step(i)
+    for k in range(1, nst):  # the timed region ends when every stream has finished its steps
+      done = torch.cuda.Event()
+      done.record(streams[k])
+      stream.wait_event(done)
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
-    launches_timed = ws.profile_read()[1] - launches0 if graphs is None else None
+    launches_timed = launches_so_far() - launches0 if graphs is None else None
 
     # per-kernel durations (cudaEvents between the launches, plain stream launches)
     ws.profile(True)
     prof_steps = min(args.steps, 200)
     for i in range(prof_steps):
-      plans[i % ring].run()
+      plans[i % ring][0].run()
     kms, _ = ws.profile_read()
     ws.profile(False)
     kms = [x / prof_steps for x in kms]
@@ -396,7 +422,7 @@ def main():
         'config': {'workload': workload_name(args.config, cfg, args.dist), 'per_gpu_batch': n,
                    'cache': f'inputs+outputs rotate over a ring of {ring} sets ({ring * set_bytes >> 20} MiB > 2x L2)',
                    'launch': 'cuda_graph_replay' if graphs is not None else 'stream launches (programmatic dependent launch)', 'parallelism': f'dp{world}',
-                   'chunk_mb': args.chunk_mb or 'default', 'inputs_ready_flag': True, 'pdl': not args.no_pdl, 'zbuffer_key': 'u64 depth|index' if args.key64 else 'u32 depth (no winner index requested)',
+                   'chunk_mb': args.chunk_mb or 'default', 'streams': nst, 'lanes': args.lanes or 'default', 'inputs_ready_flag': True, 'pdl': not args.no_pdl, 'zbuffer_key': 'u64 depth|index' if args.key64 else 'u32 depth (no winner index requested)',
                    'projection': 'certified_fast+canonical_fallback' if args.proj_mode == 1 else 'canonical'},
         'mpoints_per_s': mpoints,
         'e2e': {'value': world * n * p / (e2e_ms * 1e-3), 'unit': 'panos/s', 'h2d_bytes_per_step': h2d,

@@ -93,6 +93,16 @@ int se3ds_ws_projection_mode(se3ds_ws* ws, int mode, float margin_scale);
  * kernel's blocks are scheduled into the tail of the running one and wait on-device for its
  * completion (griddepcontrol), instead of the stream serialising whole grids. */
 int se3ds_ws_pdl(se3ds_ws* ws, int enable);
+
+/* Concurrent chunk lanes (1..4, default 2): the job chunks of one se3ds_reproject call are dealt
+ * round-robin to `lanes` streams (the caller's stream plus internal ones, forked and joined with
+ * events, so the call still behaves as one unit of work on the caller's stream).  The projection
+ * kernel is bound by instruction issue, the other two by memory: chunks in different phases overlap.
+ * Every lane has its own slice of the workspace; the L2 budget is shared between the lanes.  A call
+ * uses fewer lanes when it cannot give each one `min_chunks_per_lane` chunks (0 = default, 2) of at
+ * least `min_points_per_lane` source points (0 = default, 2^20); se3ds_reproject_host and profiled
+ * calls run on one lane. */
+int se3ds_ws_lanes(se3ds_ws* ws, int lanes, long long min_points_per_lane, int min_chunks_per_lane);
 int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_dev[2]);
 
 /* Measurement hooks (bench.py): with profiling enabled se3ds_reproject brackets its three kernel

@@ -42,6 +42,7 @@ SIGNATURES = {
     'se3ds_ws_bytes': [_vp, _c.POINTER(_sz)],
     'se3ds_ws_projection_mode': [_vp, _i, _f],
     'se3ds_ws_pdl': [_vp, _i],
+    'se3ds_ws_lanes': [_vp, _i, _ll, _i],
     'se3ds_ws_verify_read': [_vp, _c.POINTER(_c.c_ulonglong * 3), _c.POINTER(_f * 2)],
     'se3ds_ws_profile': [_vp, _i],
     'se3ds_ws_profile_read': [_vp, _c.POINTER(_f * 3), _c.POINTER(_c.c_ulonglong)],
@@ -160,6 +161,10 @@ class Workspace:
   def pdl(self, enable: bool):
     """Programmatic dependent launch between the fused kernels (default on)."""
     check(load().se3ds_ws_pdl(self.handle, int(enable)))
+
+  def lanes(self, lanes: int, min_points_per_lane: int = 0, min_chunks_per_lane: int = 0):
+    """Concurrent chunk lanes of one reproject call (1..4, default 2; 0 = default lane minima)."""
+    check(load().se3ds_ws_lanes(self.handle, int(lanes), int(min_points_per_lane), int(min_chunks_per_lane)))
 
   def verify_read(self):
     """-> dict(points, certified, wrong, max_dev_x, max_dev_y) accumulated in verify mode."""

@@ -167,6 +167,34 @@ def test_fused_chunked_equals_unchunked(mods):
   ws.close(); ws1.close()
 
 
+@pytest.mark.parametrize('lanes', [1, 2, 3, 4])
+def test_fused_concurrent_lanes(mods, lanes):
+  """Chunks dealt to concurrent streams (se3ds_ws_lanes) must not change a bit: global bin parked by
+  every chunk and patched after the join, per-job bins, winner indices (64-bit keys), repeated calls
+  on the same workspace, and a chunk count that is not a multiple of the lane count."""
+  inp = mods['synth'].make_inputs(5, 2, 3, 32, seed=11, dist='rand')
+  ws = mods['lib'].Workspace(0, 0, 32 * 64 * (16 + 16) * 2 * lanes)  # two jobs per chunk and lane
+  ws.lanes(lanes, 1, 1)
+  for _ in range(2):
+    _check_fused(mods, inp, mask_frames=1, ws=ws)
+  _check_fused(mods, inp, per_job_bin=True, ws=ws)
+  room = mods['synth'].make_inputs(4, 1, 1, 64, seed=12, dist='room')
+  _check_fused(mods, room, mask_frames=1, ws=ws)
+  ws.close()
+
+
+def test_fused_lanes_argument_checks(mods):
+  ws = mods['lib'].Workspace(0, 0, 0)
+  for bad in (0, 5, -1):
+    with pytest.raises(ValueError):
+      ws.lanes(bad)
+  with pytest.raises(ValueError):
+    ws.lanes(2, -1)
+  with pytest.raises(ValueError):
+    ws.lanes(2, 0, -1)
+  ws.close()
+
+
 def _rotations(n, p, seed):
   rng = np.random.default_rng(seed)
   a = rng.standard_normal((n * p, 3, 3))

@@ -236,7 +236,7 @@ def main():
   ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
   ap.add_argument('--dist', default='room', choices=['room', 'rand'])
   ap.add_argument('--graph', action='store_true', help='CUDA-graph replay instead of stream launches (measured slower: '
-                  'stream launches keep the programmatic dependent launch overlap, 77.9 vs 79.6 us)')
+                  'stream launches keep the programmatic dependent launch overlap)')
   ap.add_argument('--no-graph', action='store_true', help='(default) plain stream launches')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--e2e-steps', type=int, default=20)

@@ -99,23 +99,21 @@ __device__ __forceinline__ int3 load_rgb1(const int* rgb, size_t pix) {
   return make_int3(p[0], p[1], p[2]);
 }
 
-// 4 consecutive pixels, 16-byte aligned vector loads.
-__device__ __forceinline__ void load_rgb4(const uint8_t* rgb, size_t pix0, int3 (&o)[4]) {
-  const uint32_t* p = reinterpret_cast<const uint32_t*>(rgb + pix0 * 3);
-  const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-  o[0] = make_int3(a & 255, (a >> 8) & 255, (a >> 16) & 255);
-  o[1] = make_int3(a >> 24, b & 255, (b >> 8) & 255);
-  o[2] = make_int3((b >> 16) & 255, b >> 24, c & 255);
-  o[3] = make_int3((c >> 8) & 255, (c >> 16) & 255, c >> 24);
-}
-__device__ __forceinline__ void load_rgb4(const int* rgb, size_t pix0, int3 (&o)[4]) {
-  const int4* p = reinterpret_cast<const int4*>(rgb + pix0 * 3);
-  const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-  o[0] = make_int3(a.x, a.y, a.z);
-  o[1] = make_int3(a.w, b.x, b.y);
-  o[2] = make_int3(b.z, b.w, c.x);
-  o[3] = make_int3(c.y, c.z, c.w);
-}
+// A pixel's raw colour held in registers: uint8 sources stay packed in one word until they are used.
+template <typename RGB_T> struct RawRGB;
+template <> struct RawRGB<uint8_t> {
+  uint32_t v = 0;
+  __device__ __forceinline__ void load(const uint8_t* rgb, size_t pix) {
+    const uint8_t* p = rgb + pix * 3;
+    v = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+  }
+  __device__ __forceinline__ int3 get() const { return make_int3(v & 255u, (v >> 8) & 255u, v >> 16); }
+};
+template <> struct RawRGB<int> {
+  int3 v = {0, 0, 0};
+  __device__ __forceinline__ void load(const int* rgb, size_t pix) { v = load_rgb1(rgb, pix); }
+  __device__ __forceinline__ int3 get() const { return v; }
+};
 
 // Feature of a source pixel as the reference sees it after mask_pano + unprojection
 // (pano_utils.py:225,262-265): depth-invalid -> unproject_void, masked row -> -1, else RGB.
@@ -162,13 +160,18 @@ __device__ __forceinline__ void bin_max_feat_block(Bin* bin, bool has, int3 f) {
   }
 }
 
-// Launch geometry shared by K2 / K3: blockIdx.y = source row, blockIdx.x * kThreads + tid = group
-// of PPT consecutive columns, blockIdx.z = local job * S + frame.  PPT = 4 is the vector path
-// (W % 4 == 0, 16-byte aligned planes), PPT = 1 the generic one.
+// Launch geometry shared by K2 / K3: blockIdx.y = source row, blockIdx.z = local job * S + frame, a
+// block covers kThreads * PPT consecutive columns and a warp 32 * PPT of them.  Point k of a lane
+// sits at column col0 + 32 * k, i.e. every load, store and -- what matters -- every reduction
+// instruction of a warp covers 32 *consecutive* source pixels: neighbouring source pixels mostly
+// land on neighbouring target pixels, and the memory system merges the lanes of one instruction
+// that fall into the same line (measured, scripts/micro/scatter_micro.cu: a thread owning 4
+// consecutive points instead costs 1.2-1.5x more for the same REDG / gather traffic on the room
+// workload, 2.5x on an identity map).
 struct SrcIdx {
   int lj, s, n, p, job, row, col0;
-  bool active;
 };
+constexpr int kLaneStride = 32;  // column distance between consecutive points of one thread
 template <int PPT>
 __device__ __forceinline__ SrcIdx src_index(const FusedParams& q) {
   SrcIdx i;
@@ -177,16 +180,10 @@ __device__ __forceinline__ SrcIdx src_index(const FusedParams& q) {
   if (q.PC == 1) { i.n = q.n0 + i.lj; i.p = q.p0; } else { const int a = i.lj / q.PC; i.n = q.n0 + a; i.p = q.p0 + (i.lj - a * q.PC); }
   i.job = i.n * q.P + i.p;
   i.row = blockIdx.y;
-  i.col0 = (blockIdx.x * kThreads + threadIdx.x) * PPT;
-  i.active = i.col0 < q.W;
+  i.col0 = blockIdx.x * (kThreads * PPT) + (threadIdx.x >> 5) * (32 * PPT) + (threadIdx.x & 31);
   return i;
 }
 
-template <typename RGB_T, int PPT>
-__device__ __forceinline__ void load_rgbn(const RGB_T* rgb, size_t pix0, int3 (&o)[PPT]) {
-  if constexpr (PPT == 4) load_rgb4(rgb, pix0, o);
-  else o[0] = load_rgb1(rgb, pix0);
-}
 
 // ------------------------------------------------------------------------------------------
 // K2: fused unproject + translate + project + depth splat
@@ -248,32 +245,28 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     }
   };
 
-  // Inactive lanes (past the end of a row) run the loop as dropped points, so that the warp-wide
-  // ballots below always see all 32 lanes.
-  const int pix0 = ix.row * q.W + ix.col0;
+  // Points past the end of a row run the loop as dropped points, so that the warp-wide ballots
+  // below always see all 32 lanes.
+  const int pix0 = ix.row * q.W + ix.col0;  // point k: pixel pix0 + kLaneStride * k
   const size_t frame = (size_t)(ix.n * q.S + ix.s) * q.HW;
   float d[PPT] = {}, sh[PPT] = {}, ch[PPT] = {};
-  int3 raw[PPT] = {};
-  float se = 0.f, ce = 0.f, sx = 0.f, sy = 0.f, sz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
-  if (ix.active) {
-    const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
-    if constexpr (PPT == 4) {
-      const float4 dv = __ldg(reinterpret_cast<const float4*>(q.depth + frame + pix0));
-      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sin_h + ix.col0));
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cos_h + ix.col0));
-      d[0] = dv.x; d[1] = dv.y; d[2] = dv.z; d[3] = dv.w;
-      sh[0] = s4.x; sh[1] = s4.y; sh[2] = s4.z; sh[3] = s4.w;
-      ch[0] = c4.x; ch[1] = c4.y; ch[2] = c4.z; ch[3] = c4.w;
-    } else {
-      d[0] = __ldg(q.depth + frame + pix0); sh[0] = __ldg(sin_h + ix.col0); ch[0] = __ldg(cos_h + ix.col0);
+  RawRGB<RGB_T> raw[PPT];
+  bool act[PPT];
+  const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int col = ix.col0 + kLaneStride * k;
+    act[k] = col < q.W;
+    if (act[k]) {
+      d[k] = __ldg(q.depth + frame + pix0 + kLaneStride * k); sh[k] = __ldg(sin_h + col); ch[k] = __ldg(cos_h + col);
+      if constexpr (!FAST) raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k);
     }
-    if constexpr (!FAST) load_rgbn<RGB_T, PPT>(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
-    se = __ldg(sin_e + ix.row); ce = __ldg(cos_e + ix.row);
-    const float* sp = q.src_pos + (size_t)(ix.n * q.S + ix.s) * 3;
-    const float* tp = q.tgt_pos + (size_t)ix.job * 3;
-    sx = __ldg(sp); sy = __ldg(sp + 1); sz = __ldg(sp + 2);
-    tx = __ldg(tp); ty = __ldg(tp + 1); tz = __ldg(tp + 2);
   }
+  const float se = __ldg(sin_e + ix.row), ce = __ldg(cos_e + ix.row);
+  const float* sp = q.src_pos + (size_t)(ix.n * q.S + ix.s) * 3;
+  const float* tp = q.tgt_pos + (size_t)ix.job * 3;
+  const float sx = __ldg(sp), sy = __ldg(sp + 1), sz = __ldg(sp + 2);
+  const float tx = __ldg(tp), ty = __ldg(tp + 1), tz = __ldg(tp + 2);
   float rot[9];
   const bool rotate = q.tgt_rot != nullptr;
   if (rotate) {
@@ -308,11 +301,11 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && is_void;
       fvalid = dvalid ? !masked : (q.uv != -1);
     } else {
-      const int3 f = point_feat(q, !dvalid, masked, raw[k]);
+      const int3 f = point_feat(q, !dvalid, masked, raw[k].get());
       dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
       fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
     }
-    bool skip = dropped || !ix.active;
+    bool skip = dropped || !act[k];
     const float rad = canon_rad(X, Y, Z);
     scr[k] = rad;
     scf[k] = kScDropped;
@@ -320,11 +313,11 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       // a void feature rejects the point whatever its pixel is (point_cloud_utils.py:146-149):
       // only its depth matters (reject bin), so the projection is skipped.  Masked rows are whole
       // rows = whole blocks, so this is branch-uniform.
-      scf[k] = commit(-1, rad, pix0 + k, dvalid, false);
+      scf[k] = commit(-1, rad, pix0 + kLaneStride * k, dvalid, false);
       skip = true;
     }
     if constexpr (PROJ == 0) {
-      if (!skip) scf[k] = commit(project_pixel_rad(X, Y, Z, q.H, q.W, rad), rad, pix0 + k, dvalid, fvalid);
+      if (!skip) scf[k] = commit(project_pixel_rad(X, Y, Z, q.H, q.W, rad), rad, pix0 + kLaneStride * k, dvalid, fvalid);
     } else {
       int tpix = -1;
       float fx = 0.f, fy = 0.f;
@@ -332,13 +325,13 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       if (!skip) certain = project_pixel_fast(X, Y, Z, rad, q.H, q.W, q.fast, tpix, fx, fy);
       if constexpr (PROJ == 1) {
         const bool defer = !skip && !certain;
-        if (!skip && certain) scf[k] = commit(tpix, rad, pix0 + k, dvalid, fvalid);
+        if (!skip && certain) scf[k] = commit(tpix, rad, pix0 + kLaneStride * k, dvalid, fvalid);
         // uncertified points go to the warp's queue segment; the tail loop projects them canonically
         const unsigned dmask = __ballot_sync(0xffffffffu, defer);
         if (defer) {
           const int slot = wid * kSeg + wq + __popc(dmask & ((1u << lane) - 1u));
           sq_pt[slot] = make_float4(X, Y, Z, rad);
-          sq_meta[slot] = (uint32_t)(pix0 + k) | (fvalid ? 1u << 30 : 0u) | (dvalid ? 1u << 31 : 0u);
+          sq_meta[slot] = (uint32_t)(pix0 + kLaneStride * k) | (fvalid ? 1u << 30 : 0u) | (dvalid ? 1u << 31 : 0u);
         }
         wq += __popc(dmask);
       } else if (!skip) {
@@ -353,7 +346,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
           const float ex = fmaxf(fmaxf(cx - fx, fx - (cx + 1.0f)), 0.0f), ey = fmaxf(fmaxf(cy - fy, fy - (cy + 1.0f)), 0.0f);
           atomicMax(q.dbg + 3, ((unsigned long long)__float_as_uint(ex) << 32) | __float_as_uint(ey));
         }
-        scf[k] = commit(exact, rad, pix0 + k, dvalid, fvalid);
+        scf[k] = commit(exact, rad, pix0 + kLaneStride * k, dvalid, fvalid);
       }
     }
   }
@@ -371,7 +364,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     for (int k = 0; k < PPT; ++k) {
       if (scf[k] & (kScInvalid | kScDropped)) continue;
       if constexpr (KEY64) {
-        const unsigned long long key = ((unsigned long long)__float_as_uint(scr[k]) << 32) | ((idx_frame + (uint32_t)(pix0 + k)) << 1) | ((scf[k] & kScDepthInv) ? 1u : 0u);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(scr[k]) << 32) | ((idx_frame + (uint32_t)(pix0 + kLaneStride * k)) << 1) | ((scf[k] & kScDepthInv) ? 1u : 0u);
         if (key < cur[k]) atomicMin(zb + (scf[k] & kScPixMask), key);
       } else {
         const uint32_t key = __float_as_uint(scr[k]);
@@ -380,16 +373,14 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < PPT; ++k) splat(scf[k], scr[k], pix0 + k);
+    for (int k = 0; k < PPT; ++k) splat(scf[k], scr[k], pix0 + kLaneStride * k);
   }
-  if (ix.active) {
-    if constexpr (PPT == 4) {
-      __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc_frame + pix0), make_uint4(scf[0], scf[1], scf[2], scf[3]));
-      __stcg(reinterpret_cast<float4*>(q.sc_rad + sc_frame + pix0), make_float4(scr[0], scr[1], scr[2], scr[3]));
-    } else {
-      q.sc_flat[sc_frame + pix0] = scf[0]; q.sc_rad[sc_frame + pix0] = scr[0];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k)
+    if (act[k]) {
+      __stcg(q.sc_flat + sc_frame + pix0 + kLaneStride * k, scf[k]);
+      __stcg(q.sc_rad + sc_frame + pix0 + kLaneStride * k, scr[k]);
     }
-  }
   // one barrier: publishes the per-warp reject minima and queue lengths (and orders the scratch
   // stores above before the tail loop's fix-ups)
   const uint32_t wz = __reduce_max_sync(0xffffffffu, bin_z);
@@ -440,22 +431,23 @@ __global__ void __launch_bounds__(kThreads, 16) splat_feat_kernel(const FusedPar
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
   bool bin_has = false;
   int3 bin_f = make_int3(0, 0, 0);
-  if (ix.active) {
-    const int pix0 = ix.row * q.W + ix.col0;
+  if (ix.col0 < q.W) {
+    const int pix0 = ix.row * q.W + ix.col0;  // point k: pixel pix0 + kLaneStride * k
     const size_t frame = (size_t)(ix.n * q.S + ix.s) * q.HW;
     const size_t sc0 = ((size_t)ix.lj * q.S + ix.s) * q.HW + pix0;
     uint32_t scf[PPT];
     float scr[PPT];
-    int3 raw[PPT];
-    if constexpr (PPT == 4) {
-      const uint4 a = __ldcg(reinterpret_cast<const uint4*>(q.sc_flat + sc0));
-      const float4 b = __ldcg(reinterpret_cast<const float4*>(q.sc_rad + sc0));
-      scf[0] = a.x; scf[1] = a.y; scf[2] = a.z; scf[3] = a.w;
-      scr[0] = b.x; scr[1] = b.y; scr[2] = b.z; scr[3] = b.w;
-    } else {
-      scf[0] = q.sc_flat[sc0]; scr[0] = q.sc_rad[sc0];
+    RawRGB<RGB_T> raw[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if (ix.col0 + kLaneStride * k < q.W) {
+        scf[k] = __ldcg(q.sc_flat + sc0 + kLaneStride * k);
+        scr[k] = __ldcg(q.sc_rad + sc0 + kLaneStride * k);
+        raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k);
+      } else {  // past the end of the row
+        scf[k] = kScDropped; scr[k] = 0.0f;
+      }
     }
-    load_rgbn<RGB_T, PPT>(static_cast<const RGB_T*>(q.rgb), frame + pix0, raw);
     const unsigned long long* zb = q.zbuf + (size_t)ix.lj * q.HW;
     const uint32_t* zb32 = q.zbuf32 + (size_t)ix.lj * q.HW;
     uint2* fb = q.fbuf + (size_t)ix.lj * q.HW;
@@ -472,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 16) splat_feat_kernel(const FusedPar
     for (int k = 0; k < PPT; ++k) {
       const bool live = !(scf[k] & kScDropped);
       const bool haspix = live && !(scf[k] & kScInvalid);
-      const int3 f = point_feat(q, scf[k] & kScDepthInv, masked, raw[k]);
+      const int3 f = point_feat(q, scf[k] & kScDepthInv, masked, raw[k].get());
       bool rejected = live && !haspix;
       if (haspix) {
         // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)

@@ -99,19 +99,46 @@ __device__ __forceinline__ int3 load_rgb1(const int* rgb, size_t pix) {
   return make_int3(p[0], p[1], p[2]);
 }
 
+// L2 eviction-priority hint (createpolicy + .L2::cache_hint): the streams that are read exactly once
+// (input depth and colour, the per-point scratch) are marked evict_first so that they do not push the
+// z-buffer / feature buffer out of L2 between the kernels (measured: K3 27.0 -> 24.8 us).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint32_t ldcg_u32_stream(const void* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32_stream(const void* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_u8_stream(const void* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 // A pixel's raw colour held in registers: uint8 sources stay packed in one word until they are used.
 template <typename RGB_T> struct RawRGB;
 template <> struct RawRGB<uint8_t> {
   uint32_t v = 0;
-  __device__ __forceinline__ void load(const uint8_t* rgb, size_t pix) {
+  __device__ __forceinline__ void load(const uint8_t* rgb, size_t pix, uint64_t pol) {
     const uint8_t* p = rgb + pix * 3;
-    v = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+    v = ldg_u8_stream(p, pol) | (ldg_u8_stream(p + 1, pol) << 8) | (ldg_u8_stream(p + 2, pol) << 16);
   }
   __device__ __forceinline__ int3 get() const { return make_int3(v & 255u, (v >> 8) & 255u, v >> 16); }
 };
 template <> struct RawRGB<int> {
   int3 v = {0, 0, 0};
-  __device__ __forceinline__ void load(const int* rgb, size_t pix) { v = load_rgb1(rgb, pix); }
+  __device__ __forceinline__ void load(const int* rgb, size_t pix, uint64_t pol) {
+    const int* p = rgb + pix * 3;
+    v = make_int3((int)ldg_u32_stream(p, pol), (int)ldg_u32_stream(p + 1, pol), (int)ldg_u32_stream(p + 2, pol));
+  }
   __device__ __forceinline__ int3 get() const { return v; }
 };
 
@@ -253,13 +280,15 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
   RawRGB<RGB_T> raw[PPT];
   bool act[PPT];
   const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
+  const uint64_t stream_pol = l2_policy_evict_first();
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
     const int col = ix.col0 + kLaneStride * k;
     act[k] = col < q.W;
     if (act[k]) {
-      d[k] = __ldg(q.depth + frame + pix0 + kLaneStride * k); sh[k] = __ldg(sin_h + col); ch[k] = __ldg(cos_h + col);
-      if constexpr (!FAST) raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k);
+      d[k] = __uint_as_float(ldg_u32_stream(q.depth + frame + pix0 + kLaneStride * k, stream_pol));
+      sh[k] = __ldg(sin_h + col); ch[k] = __ldg(cos_h + col);
+      if constexpr (!FAST) raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k, stream_pol);
     }
   }
   const float se = __ldg(sin_e + ix.row), ce = __ldg(cos_e + ix.row);
@@ -438,12 +467,13 @@ __global__ void __launch_bounds__(kThreads, 16) splat_feat_kernel(const FusedPar
     uint32_t scf[PPT];
     float scr[PPT];
     RawRGB<RGB_T> raw[PPT];
+    const uint64_t stream_pol = l2_policy_evict_first();  // last use of the scratch, only use of the colours
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       if (ix.col0 + kLaneStride * k < q.W) {
-        scf[k] = __ldcg(q.sc_flat + sc0 + kLaneStride * k);
-        scr[k] = __ldcg(q.sc_rad + sc0 + kLaneStride * k);
-        raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k);
+        scf[k] = ldcg_u32_stream(q.sc_flat + sc0 + kLaneStride * k, stream_pol);
+        scr[k] = __uint_as_float(ldcg_u32_stream(q.sc_rad + sc0 + kLaneStride * k, stream_pol));
+        raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k, stream_pol);
       } else {  // past the end of the row
         scf[k] = kScDropped; scr[k] = 0.0f;
       }

@@ -117,6 +117,11 @@ __device__ __forceinline__ uint32_t ldg_u32_stream(const void* p, uint64_t pol) 
   asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ uint4 ldg_u128_stream(const void* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ uint32_t ldg_u8_stream(const void* p, uint64_t pol) {
   uint32_t v;
   asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
@@ -198,8 +203,11 @@ __device__ __forceinline__ void bin_max_feat_block(Bin* bin, bool has, int3 f) {
 struct SrcIdx {
   int lj, s, n, p, job, row, col0;
 };
-constexpr int kLaneStride = 32;  // column distance between consecutive points of one thread
-template <int PPT>
+// K3 uses that mapping (STRIDE = 32).  K2 is bound by instruction issue, its reductions are hidden
+// behind the projection math: it keeps 4 consecutive pixels per thread (STRIDE = 1) for the 128-bit
+// depth / table loads and scratch stores (c3: K2 699 us against 735 us with the strided mapping).
+// The scratch is indexed by source pixel, so the two kernels need not agree.
+template <int PPT, int STRIDE>
 __device__ __forceinline__ SrcIdx src_index(const FusedParams& q) {
   SrcIdx i;
   const int z = blockIdx.z;
@@ -207,7 +215,8 @@ __device__ __forceinline__ SrcIdx src_index(const FusedParams& q) {
   if (q.PC == 1) { i.n = q.n0 + i.lj; i.p = q.p0; } else { const int a = i.lj / q.PC; i.n = q.n0 + a; i.p = q.p0 + (i.lj - a * q.PC); }
   i.job = i.n * q.P + i.p;
   i.row = blockIdx.y;
-  i.col0 = blockIdx.x * (kThreads * PPT) + (threadIdx.x >> 5) * (32 * PPT) + (threadIdx.x & 31);
+  if constexpr (STRIDE == 1) i.col0 = (blockIdx.x * kThreads + threadIdx.x) * PPT;
+  else i.col0 = blockIdx.x * (kThreads * PPT) + (threadIdx.x >> 5) * (32 * PPT) + (threadIdx.x & 31);
   return i;
 }
 
@@ -234,7 +243,8 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
   pdl_launch_dependents();
   const bool late_wait = q.flags & SE3DS_FLAG_INPUTS_READY;
   if (!late_wait) pdl_wait();
-  const SrcIdx ix = src_index<PPT>(q);
+  constexpr int kLaneStride = 1;
+  const SrcIdx ix = src_index<PPT, kLaneStride>(q);
   Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
   uint32_t bin_z = 0u;  // ~ordered(min depth) of this thread's rejected points, 0 = none
   // deferred points: every warp appends to its own segment (no shared counter, no init barrier)
@@ -282,14 +292,29 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
   const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
   const uint64_t stream_pol = l2_policy_evict_first();
 #pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    const int col = ix.col0 + kLaneStride * k;
-    act[k] = col < q.W;
-    if (act[k]) {
-      d[k] = __uint_as_float(ldg_u32_stream(q.depth + frame + pix0 + kLaneStride * k, stream_pol));
-      sh[k] = __ldg(sin_h + col); ch[k] = __ldg(cos_h + col);
-      if constexpr (!FAST) raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k, stream_pol);
+  for (int k = 0; k < PPT; ++k) act[k] = ix.col0 + kLaneStride * k < q.W;
+  if constexpr (PPT == 4 && kLaneStride == 1) {  // W % 4 == 0: the four points are active together
+    if (act[0]) {
+      const uint4 dv = ldg_u128_stream(q.depth + frame + pix0, stream_pol);
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sin_h + ix.col0));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cos_h + ix.col0));
+      d[0] = __uint_as_float(dv.x); d[1] = __uint_as_float(dv.y); d[2] = __uint_as_float(dv.z); d[3] = __uint_as_float(dv.w);
+      sh[0] = s4.x; sh[1] = s4.y; sh[2] = s4.z; sh[3] = s4.w;
+      ch[0] = c4.x; ch[1] = c4.y; ch[2] = c4.z; ch[3] = c4.w;
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+      if (act[k]) {
+        const int col = ix.col0 + kLaneStride * k;
+        d[k] = __uint_as_float(ldg_u32_stream(q.depth + frame + pix0 + kLaneStride * k, stream_pol));
+        sh[k] = __ldg(sin_h + col); ch[k] = __ldg(cos_h + col);
+      }
+  }
+  if constexpr (!FAST) {
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+      if (act[k]) raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k, stream_pol);
   }
   const float se = __ldg(sin_e + ix.row), ce = __ldg(cos_e + ix.row);
   const float* sp = q.src_pos + (size_t)(ix.n * q.S + ix.s) * 3;
@@ -404,12 +429,19 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
 #pragma unroll
     for (int k = 0; k < PPT; ++k) splat(scf[k], scr[k], pix0 + kLaneStride * k);
   }
-#pragma unroll
-  for (int k = 0; k < PPT; ++k)
-    if (act[k]) {
-      __stcg(q.sc_flat + sc_frame + pix0 + kLaneStride * k, scf[k]);
-      __stcg(q.sc_rad + sc_frame + pix0 + kLaneStride * k, scr[k]);
+  if constexpr (PPT == 4 && kLaneStride == 1) {
+    if (act[0]) {
+      __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc_frame + pix0), make_uint4(scf[0], scf[1], scf[2], scf[3]));
+      __stcg(reinterpret_cast<float4*>(q.sc_rad + sc_frame + pix0), make_float4(scr[0], scr[1], scr[2], scr[3]));
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+      if (act[k]) {
+        __stcg(q.sc_flat + sc_frame + pix0 + kLaneStride * k, scf[k]);
+        __stcg(q.sc_rad + sc_frame + pix0 + kLaneStride * k, scr[k]);
+      }
+  }
   // one barrier: publishes the per-warp reject minima and queue lengths (and orders the scratch
   // stores above before the tail loop's fix-ups)
   const uint32_t wz = __reduce_max_sync(0xffffffffu, bin_z);
@@ -452,7 +484,8 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
 template <typename RGB_T, int PPT, bool KEY64>
 __global__ void __launch_bounds__(kThreads, 16) splat_feat_kernel(const FusedParams q) {
   pdl_enter();
-  const SrcIdx ix = src_index<PPT>(q);
+  constexpr int kLaneStride = PPT == 1 ? 1 : 32;
+  const SrcIdx ix = src_index<PPT, kLaneStride>(q);
   // The feature buffer and the reject bin start at 0 (output_void_class) and only take maxima, so a
   // point whose channels are all <= 0 changes nothing.  A masked row holds only -1 / unproject_void
   // features: the whole block (= one row segment) has nothing to do.

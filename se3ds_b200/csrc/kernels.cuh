@@ -234,7 +234,7 @@ __device__ __forceinline__ SrcIdx src_index(const FusedParams& q) {
 // KEY64: the z-buffer holds the 64-bit packed (depth | point index) key -- the deterministic winner
 // (nearest depth, lowest index).  When the caller does not ask for winner indices the same minimum
 // depth comes from a 32-bit key (depth bits only): half the z-buffer traffic, identical guidance.
-template <typename RGB_T, int PPT, bool FAST, int PROJ, bool KEY64>
+template <typename RGB_T, int PPT, bool FAST, int PROJ, bool KEY64, bool ROT>
 __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
   // K2 only reads caller inputs until it touches the z-buffer / scratch / bins.  If the caller
   // guarantees that those inputs were not produced by the kernel launched just before this call
@@ -321,9 +321,8 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
   const float* tp = q.tgt_pos + (size_t)ix.job * 3;
   const float sx = __ldg(sp), sy = __ldg(sp + 1), sz = __ldg(sp + 2);
   const float tx = __ldg(tp), ty = __ldg(tp + 1), tz = __ldg(tp + 2);
-  float rot[9];
-  const bool rotate = q.tgt_rot != nullptr;
-  if (rotate) {
+  float rot[ROT ? 9 : 1];  // ROT: full SE(3) target pose (q.tgt_rot != nullptr), a separate instantiation
+  if constexpr (ROT) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) rot[i] = __ldg(q.tgt_rot + (size_t)ix.job * 9 + i);
   }
@@ -343,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     float X = __fsub_rn(__fadd_rn(x, sx), tx);
     float Y = __fsub_rn(__fadd_rn(y, sy), ty);
     float Z = __fsub_rn(__fadd_rn(z, sz), tz);
-    if (rotate) {  // into the target camera frame: row-wise fma(r2, z, fma(r1, y, r0 * x))
+    if constexpr (ROT) {  // into the target camera frame: row-wise fma(r2, z, fma(r1, y, r0 * x))
       const float a = X, b = Y, c = Z;
       X = __fmaf_rn(rot[2], c, __fmaf_rn(rot[1], b, __fmul_rn(rot[0], a)));
       Y = __fmaf_rn(rot[5], c, __fmaf_rn(rot[4], b, __fmul_rn(rot[3], a)));

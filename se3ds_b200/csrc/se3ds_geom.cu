@@ -208,7 +208,11 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
                     (!(q.flags & SE3DS_FLAG_FILTER_VOID) || q.uv == -1);
   const int proj = ws->proj_mode;
   const bool pdl = ws->pdl && !ws->profile;
-#define LAUNCH_K2(F, P) CU(launch_pdl(splat_depth_kernel<RGB_T, PPT, F, P, KEY64>, grid, block, st, pdl, q))
+#define LAUNCH_K2(F, P)                                                                                        \
+  do {                                                                                                        \
+    if (q.tgt_rot) CU(launch_pdl(splat_depth_kernel<RGB_T, PPT, F, P, KEY64, true>, grid, block, st, pdl, q)); \
+    else CU(launch_pdl(splat_depth_kernel<RGB_T, PPT, F, P, KEY64, false>, grid, block, st, pdl, q));          \
+  } while (0)
   if (fast) { if (proj == 0) LAUNCH_K2(true, 0); else if (proj == 1) LAUNCH_K2(true, 1); else LAUNCH_K2(true, 2); }
   else { if (proj == 0) LAUNCH_K2(false, 0); else if (proj == 1) LAUNCH_K2(false, 1); else LAUNCH_K2(false, 2); }
 #undef LAUNCH_K2

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
   const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
   const uint64_t stream_pol = l2_policy_evict_first();
 #pragma unroll
-  for (int k = 0; k < PPT; ++k) act[k] = ix.col0 + kLaneStride * k < q.W;
+  for (int k = 0; k < PPT; ++k) act[k] = ix.col0 + kLaneStride * (PPT == 4 && kLaneStride == 1 ? 0 : k) < q.W;  // W % 4 == 0 on the PPT = 4 path
   if constexpr (PPT == 4 && kLaneStride == 1) {  // W % 4 == 0: the four points are active together
     if (act[0]) {
       const uint4 dv = ldg_u128_stream(q.depth + frame + pix0, stream_pol);
@@ -327,6 +327,15 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
     for (int i = 0; i < 9; ++i) rot[i] = __ldg(q.tgt_rot + (size_t)ix.job * 9 + i);
   }
   const bool masked = row_masked(q, ix.s, ix.row);
+  // FAST: the feature of a point is (uv,uv,uv) for an invalid depth, (-1,-1,-1) on a masked row, else a
+  // raw colour that equals no void class -- its fate follows from the depth validity and the row alone
+  int a_void = 2, a_row = 2;
+  if constexpr (FAST) {
+    const bool filt = q.flags & SE3DS_FLAG_FILTER_VOID;
+    a_void = filt ? 0 : (q.uv != -1 ? 2 : 1);
+    a_row = masked ? (filt ? 0 : 1) : 2;
+    if (PPT == 4 && kLaneStride == 1 && !act[0]) a_void = a_row = 0;  // the thread's four points lie past the row end together
+  }
   uint32_t scf[PPT];
   float scr[PPT];
 #pragma unroll
@@ -348,27 +357,24 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       Y = __fmaf_rn(rot[5], c, __fmaf_rn(rot[4], b, __fmul_rn(rot[3], a)));
       Z = __fmaf_rn(rot[8], c, __fmaf_rn(rot[7], b, __fmul_rn(rot[6], a)));
     }
-    bool dropped, fvalid;
+    // what happens to the point: 0 dropped (compaction, or past the end of the row), 1 rejected (void
+    // feature: only its depth feeds the reject bin, point_cloud_utils.py:146-149, no projection),
+    // 2 projected
+    int action;
     if constexpr (FAST) {
-      const bool is_void = !dvalid || masked;  // feature is (uv,uv,uv) or (-1,-1,-1)
-      dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && is_void;
-      fvalid = dvalid ? !masked : (q.uv != -1);
+      action = (PPT == 4 && kLaneStride == 1) ? (dvalid ? a_row : a_void) : (act[k] ? (dvalid ? a_row : a_void) : 0);
     } else {
       const int3 f = point_feat(q, !dvalid, masked, raw[k].get());
-      dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
-      fvalid = f.x != q.pv && f.y != q.pv && f.z != q.pv;
+      const bool dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
+      const bool fv = f.x != q.pv && f.y != q.pv && f.z != q.pv;
+      action = (dropped || !act[k]) ? 0 : (fv ? 2 : 1);
     }
-    bool skip = dropped || !act[k];
+    const bool skip = action != 2;
+    constexpr bool fvalid = true;  // wherever it is still consulted below, the point is being projected
     const float rad = canon_rad(X, Y, Z);
     scr[k] = rad;
     scf[k] = kScDropped;
-    if (!skip && !fvalid) {
-      // a void feature rejects the point whatever its pixel is (point_cloud_utils.py:146-149):
-      // only its depth matters (reject bin), so the projection is skipped.  Masked rows are whole
-      // rows = whole blocks, so this is branch-uniform.
-      scf[k] = commit(-1, rad, pix0 + kLaneStride * k, dvalid, false);
-      skip = true;
-    }
+    if (action == 1) scf[k] = commit(-1, rad, pix0 + kLaneStride * k, dvalid, false);  // masked rows: branch-uniform
     if constexpr (PROJ == 0) {
       if (!skip) scf[k] = commit(project_pixel_rad(X, Y, Z, q.H, q.W, rad), rad, pix0 + kLaneStride * k, dvalid, fvalid);
     } else {
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
       if (!skip) certain = project_pixel_fast(X, Y, Z, rad, q.H, q.W, q.fast, tpix, fx, fy);
       if constexpr (PROJ == 1) {
         const bool defer = !skip && !certain;
-        if (!skip && certain) scf[k] = commit(tpix, rad, pix0 + kLaneStride * k, dvalid, fvalid);
+        if (!skip && certain) scf[k] = (uint32_t)tpix | (dvalid ? 0u : kScDepthInv);  // fvalid holds here, tpix is inside the image
         // uncertified points go to the warp's queue segment; the tail loop projects them canonically
         const unsigned dmask = __ballot_sync(0xffffffffu, defer);
         if (defer) {

@@ -170,12 +170,14 @@ int se3ds_reproject_se3(se3ds_ws* ws, const void* rgb, int rgb_dtype, const floa
                         void* stream);
 
 /* Multi-GPU support for the global reject bin.  When se3ds_reproject is given bin_out (device,
- * 4 floats) the call's reject bin is NOT applied to job 0's pixel (0,0) but exported as
- * (min depth or +inf, max R, max G, max B); ranks reduce their bins (min / max) and the owner of
- * global job 0 applies the result with se3ds_apply_bin.  clip() and the divisions are monotone,
- * so patching the finished outputs is bit-identical to the single-call result. */
+ * 5 floats) the call's reject bin is NOT applied to job 0's pixel (0,0) but exported as
+ * (min depth or +inf, max R, max G, max B, depth of that pixel's own winner or +inf); ranks reduce
+ * the first four (min / max), the owner of global job 0 keeps its own fifth value and applies the
+ * result with se3ds_apply_bin.  clip() and the divisions are monotone, so patching the finished
+ * outputs is bit-identical to the single-call result; `winner` (job 0's winner plane, may be NULL)
+ * gets -1 at the pixel when a rejected point is nearer than its own winner. */
 int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, float* proj_depth,
-                    float* proj_mask, void* stream);
+                    float* proj_mask, int32_t* winner, void* stream);
 
 /* Same as se3ds_reproject with HOST buffers (pinned memory recommended): copies the inputs to the
  * device, runs the fused path and copies the guidance tensors back, pipelined over batch items on

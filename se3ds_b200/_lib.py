@@ -53,7 +53,7 @@ SIGNATURES = {
                         _vp, _vp, _vp],
     'se3ds_reproject_se3': [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp,
                             _vp, _vp, _vp, _vp],
-    'se3ds_apply_bin': [_vp, _f, _vp, _vp, _vp, _vp],
+    'se3ds_apply_bin': [_vp, _f, _vp, _vp, _vp, _vp, _vp],
     'se3ds_reproject_host': [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp,
                              _vp, _vp],
     'se3ds_resize': [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],

@@ -52,6 +52,7 @@ constexpr uint32_t kScDropped = 1u << 30;   // removed by the compaction (FILTER
 struct Bin {
   uint32_t zneg;
   int f[3];
+  uint32_t own1;  // depth bits + 1 of the owner pixel's own winner (0 = none), where the bin is applied later
 };
 
 struct FusedParams {
@@ -614,17 +615,27 @@ __device__ __forceinline__ void resolve_pixel(const FusedParams& q, int job, int
   float zmin = has ? fminf(radw, q.depth_scale) : q.depth_scale;
   float3 f = unpack_f16x4(fvk);  // per-channel max of every point that passed the tolerance test
   ow = (has && radw <= q.depth_scale) ? (int)((uint32_t)key >> 1) : -1;
-  if ((pix == 0) && (per_job || job == 0) && q.bin_out == nullptr) {  // owner pixel of a reject bin
+  if ((pix == 0) && (per_job || job == 0)) {  // owner pixel of a reject bin
+    // A rejected point that is nearer than every valid point of this pixel takes the pixel's depth
+    // (scatter-min over all points, point_cloud_utils.py:157-159): then no valid point is the winner.
     Bin* bin = q.bins + (per_job ? job : 0);
-    if (q.finalize_bins) {
-      if (bin->zneg) zmin = fminf(zmin, f32_unordered(~bin->zneg));
+    const uint32_t own1 = ow >= 0 ? (uint32_t)(key >> 32) + 1u : 0u;
+    if (q.bin_out != nullptr) {
+      bin->own1 = own1;  // export mode: the reduced bin is applied by se3ds_apply_bin
+    } else if (q.finalize_bins) {
+      if (bin->zneg) {
+        const float bz = f32_unordered(~bin->zneg);
+        zmin = fminf(zmin, bz);
+        if (bz < radw) ow = -1;
+      }
       f.x = fmaxf(f.x, (float)bin->f[0]); f.y = fmaxf(f.y, (float)bin->f[1]); f.z = fmaxf(f.z, (float)bin->f[2]);
-      *bin = Bin{0u, {0, 0, 0}};  // re-arm
+      *bin = Bin{0u, {0, 0, 0}, 0u};  // re-arm
     } else {
       // more chunks will still add to the global bin: park this pixel's own values in it,
       // patch_owner_kernel finishes the pixel after the last chunk.
       atomicMax(&bin->zneg, ~f32_ordered(zmin));
       atomicMax(&bin->f[0], (int)f.x); atomicMax(&bin->f[1], (int)f.y); atomicMax(&bin->f[2], (int)f.z);
+      bin->own1 = own1;
     }
   }
   const float depth = div_rcp(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale, q.inv_depth_scale);
@@ -723,7 +734,8 @@ __global__ void patch_owner_kernel(const FusedParams q) {
   Bin* bin = q.bins;
   const float zmin = bin->zneg ? f32_unordered(~bin->zneg) : q.depth_scale;
   const float3 f = make_float3((float)bin->f[0], (float)bin->f[1], (float)bin->f[2]);
-  *bin = Bin{0u, {0, 0, 0}};
+  if (q.out_winner && bin->own1 && zmin < __uint_as_float(bin->own1 - 1u)) q.out_winner[0] = -1;  // a rejected point is nearer
+  *bin = Bin{0u, {0, 0, 0}, 0u};
   const float depth = div_rcp(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale, q.inv_depth_scale);
   q.out_depth[0] = depth;
   const bool raw = q.flags & SE3DS_FLAG_RAW_FEATURES;
@@ -738,12 +750,14 @@ __global__ void export_bin_kernel(const FusedParams q) {
   Bin* bin = q.bins;
   q.bin_out[0] = bin->zneg ? f32_unordered(~bin->zneg) : __int_as_float(0x7f800000);
   q.bin_out[1] = (float)bin->f[0]; q.bin_out[2] = (float)bin->f[1]; q.bin_out[3] = (float)bin->f[2];
-  *bin = Bin{0u, {0, 0, 0}};
+  q.bin_out[4] = bin->own1 ? __uint_as_float(bin->own1 - 1u) : __int_as_float(0x7f800000);  // depth of the owner pixel's own winner
+  *bin = Bin{0u, {0, 0, 0}, 0u};
 }
 
 // Applies a (reduced) bin to pixel (0,0) of the first job of finished guidance tensors.
-__global__ void apply_bin_kernel(const float* bin, float depth_scale, float* image, float* depth, float* mask) {
+__global__ void apply_bin_kernel(const float* bin, float depth_scale, float* image, float* depth, float* mask, int32_t* winner) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (winner && bin[0] < bin[4]) winner[0] = -1;  // a rejected point is nearer than the pixel's own winner
   const float d = fminf(depth[0], __fdiv_rn(fminf(fmaxf(bin[0], 0.0f), depth_scale), depth_scale));
   depth[0] = d;
   float f[3];

@@ -630,6 +630,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
       CU(cudaMemcpyAsync(pipe->image_host, proj_image, 12, cudaMemcpyDeviceToHost, pipe->d2h));
       CU(cudaMemcpyAsync(pipe->depth_host, proj_depth, 4, cudaMemcpyDeviceToHost, pipe->d2h));
       CU(cudaMemcpyAsync(pipe->mask_host, proj_mask, 4, cudaMemcpyDeviceToHost, pipe->d2h));
+      if (pipe->winner_host) CU(cudaMemcpyAsync(pipe->winner_host, winner_out, 4, cudaMemcpyDeviceToHost, pipe->d2h));
     }
   }
   ws->dirty = false;
@@ -717,9 +718,9 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
 }
 
 int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, float* proj_depth,
-                    float* proj_mask, void* stream) {
+                    float* proj_mask, int32_t* winner, void* stream) {
   if (!bin || !proj_image || !proj_depth || !proj_mask) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
-  apply_bin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bin, depth_scale, proj_image, proj_depth, proj_mask);
+  apply_bin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bin, depth_scale, proj_image, proj_depth, proj_mask, winner);
   return launch_check("apply_bin_kernel");
 }
 

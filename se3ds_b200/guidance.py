@@ -97,7 +97,7 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
   pdepth = buf('proj_depth', (j, h, w, 1))
   mask = buf('proj_mask', (j, h, w, 1))
   winner = buf('winner', (j, h, w), torch.int32) if return_winner else None
-  binb = buf('bin', (4,)) if export_bin else None
+  binb = buf('bin', (5,)) if export_bin else None
   flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
            (_lib.FLAG_KEY64 if key64 else 0) | (_lib.FLAG_RAW_FEATURES if raw_features else 0))
   ws = workspace or _lib.default_workspace(dev)
@@ -157,11 +157,16 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
 
 
 def apply_bin(bin_values: torch.Tensor, out: Dict[str, torch.Tensor], depth_scale: float = constants.DEPTH_SCALE):
-  """Applies a reduced reject bin to pixel (0,0) of job 0 of `out` (see se3ds_apply_bin)."""
+  """Applies a reduced reject bin to pixel (0,0) of job 0 of `out` (see se3ds_apply_bin).
+
+  bin_values: (5,) = reduced (min depth, max R, G, B) followed by the owner call's own fifth value
+  (depth of that pixel's own winner, as exported)."""
   dev = out['proj_image'].device
+  assert bin_values.numel() == 5, 'bin is (min depth, max R, max G, max B, own winner depth)'
   _lib.check(_lib.load().se3ds_apply_bin(_lib.ptr(bin_values.contiguous()), float(depth_scale),
                                          _lib.ptr(out['proj_image']), _lib.ptr(out['proj_depth']),
-                                         _lib.ptr(out['proj_mask']), _lib.stream_handle(dev)))
+                                         _lib.ptr(out['proj_mask']), _lib.ptr(out.get('winner')),
+                                         _lib.stream_handle(dev)))
 
 
 def reproject_host(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_SCALE,

@@ -110,15 +110,15 @@ def reproject_sharded(rgb, depth, src_pos, tgt_pos, *, group=None, bin_mode: str
   if bin_mode in ('call', 'shard'):
     if bins:
       b = torch.stack(bins)
-      red = torch.cat([(-b[:, :1]).max(dim=0).values, b[:, 1:].max(dim=0).values])
+      red = torch.cat([(-b[:, :1]).max(dim=0).values, b[:, 1:4].max(dim=0).values])
     else:
       red = torch.tensor([-float('inf'), 0.0, 0.0, 0.0], device=dev)
     if bin_mode == 'call' and world > 1:
       dist.all_reduce(red, op=dist.ReduceOp.MAX, group=group)
     owner = (lo == 0 and hi > 0) if bin_mode == 'call' else hi > lo
     if owner:
-      red = red.clone()
-      red[0] = -red[0]
+      # fifth value: depth of the owner pixel's own winner, from the call that rendered this rank's first job
+      red = torch.cat([-red[:1], red[1:], bins[0][4:5].to(red.device)])
       apply_bin_fn(red, local, depth_scale)
 
   result = dict(local)

@@ -183,6 +183,25 @@ def test_fused_concurrent_lanes(mods, lanes):
   ws.close()
 
 
+def test_fused_winner_at_owner_pixel(mods):
+  """A rejected point nearer than every valid point of the reject bin's owner pixel takes that pixel's
+  depth: no valid point is its winner then (-1).  Found by scripts/gpu_fuzz.py (gan_manager voids, a
+  masked frame: many rejected points with small depths).  Single chunk, per-job bins, and the
+  multi-chunk path where the owner pixel is patched after the last chunk."""
+  g = mods['g']
+  hit = 0
+  for seed in range(6):
+    inp = mods['synth'].make_inputs(2, 3, 1, 16, seed=100 + seed, dist='rand')
+    for per_job in (False, True):
+      _, ref = _check_fused(mods, inp, conv=g.GAN_MANAGER, mask_frames=1, per_job_bin=per_job)
+      hit += int((ref['winner'][:, 0, 0] < 0).any() and (ref['depth'][:, 0, 0, 0] < 1).any())
+    ws = mods['lib'].Workspace(0, 0, 1)  # one job per chunk: global bin parked, owner pixel patched at the end
+    ws.lanes(2, 1, 1)
+    _check_fused(mods, inp, conv=g.GAN_MANAGER, mask_frames=1, ws=ws)
+    ws.close()
+  assert hit > 0, 'no case exercised the owner-pixel rule'
+
+
 def test_fused_lanes_argument_checks(mods):
   ws = mods['lib'].Workspace(0, 0, 0)
   for bad in (0, 5, -1):
@@ -308,12 +327,13 @@ def test_export_and_apply_bin(mods):
   t = _cuda(inp)
   parts, bins = [], []
   for lo, hi in ((0, 2), (2, 4)):
-    o = g.reproject(t['rgb'][lo:hi], t['depth'][lo:hi], t['src_pos'][lo:hi], t['tgt_pos'][lo:hi], export_bin=True)
+    o = g.reproject(t['rgb'][lo:hi], t['depth'][lo:hi], t['src_pos'][lo:hi], t['tgt_pos'][lo:hi], export_bin=True,
+                    return_winner=True)
     bins.append(o['bin'].clone()); parts.append({k: v.clone() for k, v in o.items()})
   b = torch.stack(bins)
-  red = torch.cat([b[:, :1].min(dim=0).values, b[:, 1:].max(dim=0).values])
+  red = torch.cat([b[:, :1].min(dim=0).values, b[:, 1:4].max(dim=0).values, bins[0][4:5]])
   g.apply_bin(red, parts[0])
-  for k, r in (('proj_image', 'image'), ('proj_depth', 'depth'), ('proj_mask', 'mask')):
+  for k, r in (('proj_image', 'image'), ('proj_depth', 'depth'), ('proj_mask', 'mask'), ('winner', 'winner')):
     got = torch.cat([parts[0][k], parts[1][k]]).cpu().numpy()
     np.testing.assert_array_equal(got, ref[r])
 

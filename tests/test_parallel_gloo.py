@@ -45,7 +45,18 @@ def oracle_compute(rgb, depth, src_pos, tgt_pos, depth_scale=20.0, per_job_bin=F
     out['proj_depth'][0, 0, 0, 0] = d0
     out['proj_image'][0, 0, 0] = np.clip(f0 / F32(255), 0, 1)
     out['proj_mask'][0, 0, 0, 0] = F32(0 < d0 < 1)
-    out['bin'] = np.array([binz, *binf], F32)
+    # the owner pixel's own winner ignores the (not yet reduced) reject bin; its depth travels with the bin
+    own = np.inf
+    if at0.any() and rad[at0].min() <= F32(depth_scale):
+      own = rad[at0].min()
+      if return_winner:
+        m = o['flat'].reshape(j, -1).shape[1]
+        out['winner'] = out['winner'].copy()
+        out['winner'][0, 0, 0] = int(np.flatnonzero(at0 & (rad == own))[0] % m)
+    elif return_winner:
+      out['winner'] = out['winner'].copy()
+      out['winner'][0, 0, 0] = -1
+    out['bin'] = np.array([binz, *binf, own], F32)
   return {k: torch.as_tensor(v) for k, v in out.items()}
 
 
@@ -53,9 +64,11 @@ def oracle_apply_bin(bin_values, out, depth_scale=20.0):
   b = bin_values.numpy().astype(F32)
   d = min(out['proj_depth'][0, 0, 0, 0].item(), float(np.clip(b[0], 0, F32(depth_scale)) / F32(depth_scale)))
   out['proj_depth'][0, 0, 0, 0] = d
-  img = np.maximum(out['proj_image'][0, 0, 0].numpy(), np.clip(b[1:] / F32(255), 0, 1))
+  img = np.maximum(out['proj_image'][0, 0, 0].numpy(), np.clip(b[1:4] / F32(255), 0, 1))
   out['proj_image'][0, 0, 0] = torch.as_tensor(img)
   out['proj_mask'][0, 0, 0, 0] = float(0 < d < 1)
+  if 'winner' in out and b[0] < b[4]:
+    out['winner'][0, 0, 0] = -1
 
 
 def _worker(rank, world, port, n, p, bin_mode, q):

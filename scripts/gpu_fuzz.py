@@ -12,12 +12,18 @@ from oracle import ref_exact as X, ref_numpy as R
 from se3ds_b200 import _lib, guidance as g, synth
 
 
-def oracle(inp, conv, mask_frames, per_job_bin):
+def oracle(inp, conv, mask_frames, per_job_bin, rot=None):
   rgb = inp['rgb'].astype(np.int32).copy()
   for k in range(mask_frames):
     rgb[:, k] = R.mask_pano(rgb[:, k], masked_region_value=-1)
   return X.reproject(rgb, inp['depth'], inp['src_pos'], inp['tgt_pos'], unproject_void=conv.unproject_void,
-                     project_void=conv.project_void, mask_first_frame=False, per_job_bin=per_job_bin)
+                     project_void=conv.project_void, mask_first_frame=False, per_job_bin=per_job_bin, tgt_rot=rot)
+
+
+def rotations(rng, n, p):
+  qm, _ = np.linalg.qr(rng.standard_normal((n * p, 3, 3)))
+  qm *= np.sign(np.linalg.det(qm))[:, None, None]
+  return qm.reshape(n, p, 3, 3).astype(np.float32)
 
 
 def main(budget=40.0, seed=0):
@@ -38,16 +44,24 @@ def main(budget=40.0, seed=0):
     if rng.integers(0, 4) == 0:  # degenerate depths: zeros, ones, out-of-range, a NaN
       d = inp['depth']
       d[rng.random(d.shape) < 0.2] = rng.choice([0.0, 1.0, -0.5, 1.5, np.nan])
+    if rng.integers(0, 4) == 0:  # int32 colours with void values in them (the generic, non-FAST kernels)
+      rgb = inp['rgb'].astype(np.int32)
+      rgb[rng.random(rgb.shape) < 0.05] = -1
+      rgb[rng.random(rgb.shape[:-1]) < 0.03] = conv.unproject_void
+      inp['rgb'] = rgb
+    rot = rotations(rng, n, p) if rng.integers(0, 4) == 0 else None
     ws = _lib.Workspace(0, 0, h * 2 * h * (16 + 8 * s) * chunk_jobs * lanes)
     ws.lanes(lanes, 1, 1)
     t = {k: torch.as_tensor(v).cuda() for k, v in inp.items()}
-    want = oracle(inp, conv, mask_frames, per_job)
+    trot = None if rot is None else torch.as_tensor(rot).cuda()
+    want = oracle(inp, conv, mask_frames, per_job, rot)
     for key64, winner in ((False, False), (True, False), (True, True)):
       out = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=mask_frames,
                         unproject_void=conv.unproject_void, project_void=conv.project_void, filter_void=False,
-                        per_job_bin=per_job, return_winner=winner, workspace=ws, key64=key64)
+                        per_job_bin=per_job, return_winner=winner, workspace=ws, key64=key64, tgt_rot=trot)
       torch.cuda.synchronize()
-      tag = (h, n, s, p, dist, conv.unproject_void, conv.project_void, mask_frames, per_job, lanes, chunk_jobs, key64, winner)
+      tag = (h, n, s, p, dist, conv.unproject_void, conv.project_void, mask_frames, per_job, lanes, chunk_jobs, key64, winner,
+             str(inp['rgb'].dtype), rot is not None)
       for name, ref in (('proj_depth', 'depth'), ('proj_mask', 'mask'), ('proj_image', 'image')):
         a, b = out[name].cpu().numpy(), want[ref]
         assert np.array_equal(a, b, equal_nan=True), (name, tag, int(np.sum(a != b)))

@@ -7,14 +7,22 @@
 //                           otherwise; per point (pixel, depth) goes to a scratch for K3.  The
 //                           projection is a certified MUFU fast path with a canonical (IEEE)
 //                           fallback for the few points it cannot certify.
+//                           A thread owns 4 consecutive source pixels (128-bit loads / stores);
+//                           the kernel is bound by instruction issue, its time follows its
+//                           instruction count (rotation is a separate instantiation for that reason).
 //   K3 splat_feat_kernel  : tolerance test d < dmin + 0.1 against the final z-buffer; every
 //                           surviving point REDG.MAX.F16x4 its RGB into the feature buffer (one
 //                           8-byte vector reduction = the reference's per-channel scatter-max);
-//                           rejected points are block-reduced into the reject bin.
+//                           rejected points are block-reduced into the reject bin.  Instruction k
+//                           of a warp covers 32 consecutive source pixels, so the lanes of a
+//                           gather / reduction that share a cache line are merged.
 //   K4 resolve_kernel     : per target pixel, streaming: z-buffer + feature buffer (+ bin on the
 //                           owner pixel) -> proj_image / proj_depth / proj_mask / winner, written
-//                           once; re-arms the touched z-buffer / feature entries.
-// The three kernels are chained with programmatic dependent launch (pdl_enter).
+//                           once (RGB staged through shared memory for 512-byte store
+//                           instructions, 256-bit loads); re-arms the touched z-buffer / feature
+//                           entries.
+// The three kernels are chained with programmatic dependent launch (pdl_enter); the streams that are
+// read once carry L2 evict_first hints.
 // Compat path (se3ds_unproject_equirect / se3ds_project_cloud) works on materialised clouds with
 // float32 features of any channel count; the resampling kernels (rotate_pano, perspective <->
 // equirect, tf-style resize, tfa-style bilinear gather) are at the end of the file.

@@ -103,6 +103,12 @@ int se3ds_ws_pdl(se3ds_ws* ws, int enable);
  * least `min_points_per_lane` source points (0 = default, 2^20); se3ds_reproject_host and profiled
  * calls run on one lane. */
 int se3ds_ws_lanes(se3ds_ws* ws, int lanes, long long min_points_per_lane, int min_chunks_per_lane);
+
+/* The chunk / lane plan se3ds_reproject would use for a call of this shape with these knobs (0 = the
+ * defaults of se3ds_ws_create / se3ds_ws_lanes); pure host arithmetic, no device needed.
+ * plan = {lanes used, batch items per chunk, poses per chunk, jobs per chunk, number of chunks}. */
+int se3ds_plan_chunks(size_t l2_chunk_bytes, int lanes, long long min_points_per_lane, int min_chunks_per_lane,
+                      int n, int s, int p, int h, int w, long long plan[5]);
 int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_dev[2]);
 
 /* Measurement hooks (bench.py): with profiling enabled se3ds_reproject brackets its three kernel

@@ -43,6 +43,7 @@ SIGNATURES = {
     'se3ds_ws_projection_mode': [_vp, _i, _f],
     'se3ds_ws_pdl': [_vp, _i],
     'se3ds_ws_lanes': [_vp, _i, _ll, _i],
+    'se3ds_plan_chunks': [_sz, _i, _ll, _i, _i, _i, _i, _i, _i, _c.POINTER(_ll * 5)],
     'se3ds_ws_verify_read': [_vp, _c.POINTER(_c.c_ulonglong * 3), _c.POINTER(_f * 2)],
     'se3ds_ws_profile': [_vp, _i],
     'se3ds_ws_profile_read': [_vp, _c.POINTER(_f * 3), _c.POINTER(_c.c_ulonglong)],
@@ -196,6 +197,15 @@ class Workspace:
 
 
 _default_ws: Dict[int, Workspace] = {}
+
+
+def plan_chunks(n: int, s: int, p: int, h: int, l2_chunk_bytes: int = 0, lanes: int = 2, min_points_per_lane: int = 0,
+                min_chunks_per_lane: int = 0) -> dict:
+  """The chunk / lane plan of a reproject call of this shape (host arithmetic only, works without a GPU)."""
+  out = (_ll * 5)()
+  check(load().se3ds_plan_chunks(int(l2_chunk_bytes), int(lanes), int(min_points_per_lane), int(min_chunks_per_lane),
+                                 int(n), int(s), int(p), int(h), int(2 * h), ctypes.byref(out)))
+  return dict(lanes=out[0], items_per_chunk=out[1], poses_per_chunk=out[2], chunk_jobs=out[3], nchunks=out[4])
 
 
 def default_workspace(device) -> Workspace:

@@ -92,6 +92,44 @@ size_t ws_total(const se3ds_ws* ws) {
   return t;
 }
 
+// Job chunking: a chunk's z-buffer + feature buffer + scratch (16 + 8 S bytes per target pixel) should
+// sit in L2.  The chunks are dealt round-robin to `lanes` concurrent streams which share that budget; a
+// call that cannot give every lane min_lane_chunks chunks of at least min_lane_points source points
+// uses fewer lanes (measured: c3 -4.4 %, c4 -8 % with two lanes; c2 would split into one chunk per lane
+// and lose 1.3 us to the fork and join).  A chunk is a block of whole batch items with all their
+// poses, or -- when one item's poses do not fit -- a block of poses of one item.
+struct ChunkPlan {
+  int lanes, items_per_chunk, poses_per_chunk;
+  long long chunk_jobs, nchunks;
+};
+void plan_chunks(size_t budget_bytes, int lanes, long long min_lane_points, int min_lane_chunks, bool per_item, int n,
+                 int s, int p, int h, int w, ChunkPlan* out) {
+  const long long hw = (long long)h * w, J = (long long)n * p;
+  const size_t job_bytes = (size_t)hw * (16 + 8 * (size_t)s);
+  lanes = std::max(1, lanes);
+  int items_per_chunk = 1, PC = 1;
+  long long chunk_jobs = 1, nchunks_total = 1;
+  for (;; --lanes) {
+    long long jpc = std::max<long long>(1, (long long)(budget_bytes / lanes / job_bytes));
+    jpc = std::min(jpc, (J + lanes - 1) / lanes);
+    jpc = std::min<long long>(jpc, std::max(1, 65535 / s));
+    if (per_item) jpc = std::min<long long>(jpc, p);  // one batch item per chunk: finest copy/compute overlap
+    if (jpc >= p) {
+      const long long nchunks = (n + (jpc / p) - 1) / (jpc / p);
+      items_per_chunk = (int)((n + nchunks - 1) / nchunks);
+      PC = p;
+    } else {
+      const long long pchunks = (p + jpc - 1) / jpc;
+      items_per_chunk = 1;
+      PC = (int)((p + pchunks - 1) / pchunks);
+    }
+    chunk_jobs = (long long)items_per_chunk * PC;
+    nchunks_total = (long long)((n + items_per_chunk - 1) / items_per_chunk) * ((p + PC - 1) / PC);
+    if (lanes == 1 || (nchunks_total >= (long long)lanes * min_lane_chunks && chunk_jobs * s * hw >= min_lane_points)) break;
+  }
+  *out = ChunkPlan{lanes, items_per_chunk, PC, chunk_jobs, nchunks_total};
+}
+
 // Grow-only device buffer; armed buffers are (re)initialised with `pattern` on `stream`.
 int grow(DevBuf& b, size_t bytes, int pattern, cudaStream_t stream) {
   if (bytes <= b.cap) return SE3DS_OK;
@@ -320,6 +358,18 @@ int se3ds_ws_lanes(se3ds_ws* ws, int lanes, long long min_points_per_lane, int m
   return SE3DS_OK;
 }
 
+int se3ds_plan_chunks(size_t l2_chunk_bytes, int lanes, long long min_points_per_lane, int min_chunks_per_lane, int n,
+                      int s, int p, int h, int w, long long plan[5]) {
+  if (!plan) return fail(SE3DS_ERR_BAD_ARG, "plan is NULL");
+  if (n <= 0 || s <= 0 || p <= 0 || h <= 0 || w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "bad shape");
+  if (lanes < 1 || lanes > se3ds_ws::kMaxLanes) return fail(SE3DS_ERR_BAD_ARG, "lanes must be in [1, %d]", se3ds_ws::kMaxLanes);
+  ChunkPlan c;
+  plan_chunks(l2_chunk_bytes ? l2_chunk_bytes : kDefaultChunkBytes, lanes, min_points_per_lane ? min_points_per_lane : (1ll << 20),
+              min_chunks_per_lane ? min_chunks_per_lane : 2, false, n, s, p, h, w, &c);
+  plan[0] = c.lanes; plan[1] = c.items_per_chunk; plan[2] = c.poses_per_chunk; plan[3] = c.chunk_jobs; plan[4] = c.nchunks;
+  return SE3DS_OK;
+}
+
 int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_dev[2]) {
   if (!ws || !counts || !max_dev) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
   counts[0] = counts[1] = counts[2] = 0;
@@ -502,34 +552,13 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(ws->device));
 
-  // job chunking: a chunk's z-buffer + feature buffer + scratch should sit in L2
-  // The chunks are dealt round-robin to `lanes` concurrent streams which share that L2 budget; a call
-  // that cannot give every lane min_lane_chunks chunks of at least min_lane_points source points uses
-  // fewer lanes (measured: c3 -4.4 %, c4 -8 % with two lanes; c2 would split into one chunk per lane
-  // and lose 1.3 us to the fork and join).
+  // job chunking and lanes (plan_chunks below)
   const long long J = (long long)n * p;
-  const size_t job_bytes = (size_t)hw * (16 + 8 * (size_t)s);
-  int lanes = (pipe || ws->profile) ? 1 : ws->lanes;
-  int items_per_chunk = 1, PC = 1;
-  long long chunk_jobs = 1, nchunks_total = 1;
-  for (;; --lanes) {
-    long long jpc = std::max<long long>(1, (long long)(std::min(ws->chunk_bytes, ws->max_bytes) / lanes / job_bytes));
-    jpc = std::min(jpc, (J + lanes - 1) / lanes);
-    jpc = std::min<long long>(jpc, std::max(1, 65535 / s));
-    if (pipe) jpc = std::min<long long>(jpc, p);  // one batch item per chunk: finest copy/compute overlap
-    if (jpc >= p) {
-      const long long nchunks = (n + (jpc / p) - 1) / (jpc / p);
-      items_per_chunk = (int)((n + nchunks - 1) / nchunks);
-      PC = p;
-    } else {
-      const long long pchunks = (p + jpc - 1) / jpc;
-      items_per_chunk = 1;
-      PC = (int)((p + pchunks - 1) / pchunks);
-    }
-    chunk_jobs = (long long)items_per_chunk * PC;
-    nchunks_total = (long long)((n + items_per_chunk - 1) / items_per_chunk) * ((p + PC - 1) / PC);
-    if (lanes == 1 || (nchunks_total >= (long long)lanes * ws->min_lane_chunks && chunk_jobs * s * hw >= ws->min_lane_points)) break;
-  }
+  ChunkPlan plan;
+  plan_chunks(std::min(ws->chunk_bytes, ws->max_bytes), (pipe || ws->profile) ? 1 : ws->lanes, ws->min_lane_points,
+              ws->min_lane_chunks, pipe != nullptr, n, s, p, h, w, &plan);
+  const int lanes = plan.lanes, items_per_chunk = plan.items_per_chunk, PC = plan.poses_per_chunk;
+  const long long chunk_jobs = plan.chunk_jobs, nchunks_total = plan.nchunks;
   const bool per_job = flags & SE3DS_FLAG_BIN_PER_JOB;
   if (bin_out && per_job) return fail(SE3DS_ERR_BAD_ARG, "bin_out needs the per-call bin mode");
 

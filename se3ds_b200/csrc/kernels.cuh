@@ -615,6 +615,7 @@ __device__ __forceinline__ void resolve_load4(const FusedParams& q, size_t e, un
 
 // One target pixel: z-buffer key + feature maxima -> (depth, mask, rgb, winner), including the owner
 // pixel of a reject bin (point_cloud_utils.py:160-162, models.py:282-293).
+template <bool KEY64>
 __device__ __forceinline__ void resolve_pixel(const FusedParams& q, int job, int pix, unsigned long long key, uint2 fvk,
                                               float& od, float& om, float* oi, int& ow) {
   const bool per_job = q.flags & SE3DS_FLAG_BIN_PER_JOB;
@@ -622,19 +623,19 @@ __device__ __forceinline__ void resolve_pixel(const FusedParams& q, int job, int
   const float radw = __uint_as_float((uint32_t)(key >> 32));
   float zmin = has ? fminf(radw, q.depth_scale) : q.depth_scale;
   float3 f = unpack_f16x4(fvk);  // per-channel max of every point that passed the tolerance test
-  ow = (has && radw <= q.depth_scale) ? (int)((uint32_t)key >> 1) : -1;
+  ow = (KEY64 && has && radw <= q.depth_scale) ? (int)((uint32_t)key >> 1) : -1;  // winner indices exist with 64-bit keys only
   if ((pix == 0) && (per_job || job == 0)) {  // owner pixel of a reject bin
     // A rejected point that is nearer than every valid point of this pixel takes the pixel's depth
     // (scatter-min over all points, point_cloud_utils.py:157-159): then no valid point is the winner.
     Bin* bin = q.bins + (per_job ? job : 0);
-    const uint32_t own1 = ow >= 0 ? (uint32_t)(key >> 32) + 1u : 0u;
+    const uint32_t own1 = (KEY64 && ow >= 0) ? (uint32_t)(key >> 32) + 1u : 0u;
     if (q.bin_out != nullptr) {
       bin->own1 = own1;  // export mode: the reduced bin is applied by se3ds_apply_bin
     } else if (q.finalize_bins) {
       if (bin->zneg) {
         const float bz = f32_unordered(~bin->zneg);
         zmin = fminf(zmin, bz);
-        if (bz < radw) ow = -1;
+        if (KEY64 && bz < radw) ow = -1;
       }
       f.x = fmaxf(f.x, (float)bin->f[0]); f.y = fmaxf(f.y, (float)bin->f[1]); f.z = fmaxf(f.z, (float)bin->f[2]);
       *bin = Bin{0u, {0, 0, 0}, 0u};  // re-arm
@@ -694,7 +695,7 @@ __global__ void __launch_bounds__(kThreads, KEY64 ? 10 : 12) resolve_kernel(cons
     float od[4], om[4], oi[12];
     int ow[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) resolve_pixel(q, job, pix0 + k, key[k], fv[k], od[k], om[k], oi + 3 * k, ow[k]);
+    for (int k = 0; k < 4; ++k) resolve_pixel<KEY64>(q, job, pix0 + k, key[k], fv[k], od[k], om[k], oi + 3 * k, ow[k]);
     __stcs(reinterpret_cast<float4*>(q.out_depth + o), make_float4(od[0], od[1], od[2], od[3]));
     __stcs(reinterpret_cast<float4*>(q.out_mask + o), make_float4(om[0], om[1], om[2], om[3]));
     float4* im = reinterpret_cast<float4*>(q.out_image + o * 3);
@@ -721,16 +722,18 @@ __global__ void __launch_bounds__(kThreads, KEY64 ? 10 : 12) resolve_kernel(cons
       __stcs(im + 1, make_float4(oi[4], oi[5], oi[6], oi[7]));
       __stcs(im + 2, make_float4(oi[8], oi[9], oi[10], oi[11]));
     }
-    if (q.out_winner) __stcs(reinterpret_cast<int4*>(q.out_winner + o), make_int4(ow[0], ow[1], ow[2], ow[3]));
+    if constexpr (KEY64)
+      if (q.out_winner) __stcs(reinterpret_cast<int4*>(q.out_winner + o), make_int4(ow[0], ow[1], ow[2], ow[3]));
     resolve_rearm4<KEY64>(q, e, key);
   } else {
     const unsigned long long key = KEY64 ? q.zbuf[e] : (((unsigned long long)q.zbuf32[e] << 32) | 0xFFFFFFFFu);
     float od, om, oi[3];
     int ow;
-    resolve_pixel(q, job, pix0, key, q.fbuf[e], od, om, oi, ow);
+    resolve_pixel<KEY64>(q, job, pix0, key, q.fbuf[e], od, om, oi, ow);
     q.out_depth[o] = od; q.out_mask[o] = om;
     for (int c = 0; c < 3; ++c) q.out_image[o * 3 + c] = oi[c];
-    if (q.out_winner) q.out_winner[o] = ow;
+    if constexpr (KEY64)
+      if (q.out_winner) q.out_winner[o] = ow;
     if constexpr (KEY64) q.zbuf[e] = kZArmed; else q.zbuf32[e] = 0xFFFFFFFFu;
     q.fbuf[e] = make_uint2(0, 0);
   }

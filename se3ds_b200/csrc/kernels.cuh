@@ -410,8 +410,9 @@ __global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams
           if (exact != tpix) atomicAdd(q.dbg + 2, 1ull);
         }
         if (exact >= 0 && fabsf(Z) < 0.984375f * rad) {  // how far the fast coordinates fall outside the canonical pixel
+          // (the fast row is a certified candidate, not a coordinate: it only counts when it was certified)
           const float cx = (float)(exact % q.W), cy = (float)(exact / q.W);
-          const float ex = fmaxf(fmaxf(cx - fx, fx - (cx + 1.0f)), 0.0f), ey = fmaxf(fmaxf(cy - fy, fy - (cy + 1.0f)), 0.0f);
+          const float ex = fmaxf(fmaxf(cx - fx, fx - (cx + 1.0f)), 0.0f), ey = certain ? fmaxf(fmaxf(cy - fy, fy - (cy + 1.0f)), 0.0f) : 0.0f;
           atomicMax(q.dbg + 3, ((unsigned long long)__float_as_uint(ex) << 32) | __float_as_uint(ey));
         }
         scf[k] = commit(exact, rad, pix0 + kLaneStride * k, dvalid, fvalid);

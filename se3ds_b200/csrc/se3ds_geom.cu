@@ -46,7 +46,8 @@ struct DevBuf {
 
 struct TableEntry {
   int h, w;
-  float* dev;
+  float margin;  // certification margin scale the row table was built for
+  float* dev;    // sin/cos of the row elevations (2 H), of the column headings (2 W), row certification table (2 H)
 };
 
 constexpr size_t kDefaultMaxBytes = (size_t)2 << 30;
@@ -88,7 +89,7 @@ size_t ws_total(const se3ds_ws* ws) {
   size_t t = ws->zbuf.cap + ws->zbuf32.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->bins.cap + ws->cbin.cap +
              ws->s_rgb.cap + ws->s_depth.cap + ws->s_src.cap + ws->s_tgt.cap + ws->s_img.cap +
              ws->s_dep.cap + ws->s_msk.cap + ws->s_win.cap;
-  for (const auto& e : ws->tables) t += (size_t)(2 * e.h + 2 * e.w) * sizeof(float);
+  for (const auto& e : ws->tables) t += (size_t)(4 * e.h + 2 * e.w) * sizeof(float);
   return t;
 }
 
@@ -173,10 +174,10 @@ void linspace_f32(float start, float stop, int n, float* out) {
 // Layout: sin_e[H], cos_e[H], sin_h[W], cos_h[W].  H + W values, computed once per shape.
 int get_tables(se3ds_ws* ws, int h, int w, cudaStream_t stream, const float** out) {
   for (const auto& e : ws->tables)
-    if (e.h == h && e.w == w) { *out = e.dev; return SE3DS_OK; }
+    if (e.h == h && e.w == w && e.margin == ws->margin_scale) { *out = e.dev; return SE3DS_OK; }
   const double pi = 3.141592653589793;
   const double hp = 0.5 * pi / (double)h;
-  std::vector<float> elev(h), head(w), host((size_t)2 * h + 2 * w);
+  std::vector<float> elev(h), head(w), host((size_t)4 * h + 2 * w);
   linspace_f32((float)hp, (float)(pi - hp), h, elev.data());
   linspace_f32((float)(1.5 * pi - hp), (float)(-0.5 * pi + hp), w, head.data());
   for (int r = 0; r < h; ++r) {
@@ -187,6 +188,15 @@ int get_tables(se3ds_ws* ws, int h, int w, cudaStream_t stream, const float** ou
     host[2 * h + c] = (float)std::sin((double)head[c]);
     host[2 * h + w + c] = (float)std::cos((double)head[c]);
   }
+  // row certification table of the fast projection (FastProj::rowb): q = z / rad certainly belongs to row r
+  // when it lies strictly between cos((r+1) pi/H) + m and cos(r pi/H) - m; m = the pixel margin dy = 2 H
+  // margin_scale as an angle, bounds rounded inwards by one float32 step
+  const double m = 2.0 * pi * (double)ws->margin_scale;
+  for (int r = 0; r < h; ++r) {
+    const float lo = (float)(std::cos((double)(r + 1) * pi / (double)h) + m), hi = (float)(std::cos((double)r * pi / (double)h) - m);
+    host[(size_t)2 * h + 2 * w + 2 * r] = std::nextafterf(lo, 2.0f);
+    host[(size_t)2 * h + 2 * w + 2 * r + 1] = std::nextafterf(hi, -2.0f);
+  }
   float* dev = nullptr;
   CU(cudaMalloc(&dev, host.size() * sizeof(float)));
   CU(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
@@ -195,7 +205,7 @@ int get_tables(se3ds_ws* ws, int h, int w, cudaStream_t stream, const float** ou
     cudaFree(ws->tables.front().dev);
     ws->tables.erase(ws->tables.begin());
   }
-  ws->tables.push_back({h, w, dev});
+  ws->tables.push_back({h, w, ws->margin_scale, dev});
   *out = dev;
   return SE3DS_OK;
 }
@@ -597,6 +607,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   q.fast.ky = (float)((double)h / 3.141592653589793);
   q.fast.dx = (float)w * ws->margin_scale;
   q.fast.dy = (float)h * 2.0f * ws->margin_scale;
+  q.fast.rowb = reinterpret_cast<const float2*>(tab + 2 * (size_t)h + 2 * (size_t)w);
   {
     volatile float one = 1.0f, ds = depth_scale;
     q.inv_depth_scale = one / ds;  // IEEE single division on the host: RN(1 / depth_scale)

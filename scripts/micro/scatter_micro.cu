@@ -75,7 +75,7 @@ int main() {
   for (int pat = 0; pat < 6; ++pat) {
     if (pat >= 4) {
       // target pixel of every source point of one 512x1024 pano as the oracle computes it (-1 = rejected),
-      // written by a script from oracle/ref_exact; replicated over the 8 jobs
+      // written by tests/tools/dump_scatter_indices.py; replicated over the 8 jobs
       FILE* f = fopen(pat == 4 ? "scripts/micro/bin/idx_room.i32" : "scripts/micro/bin/idx_rand.i32", "rb");
       if (!f) continue;
       std::vector<int32_t> one(HW);

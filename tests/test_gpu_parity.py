@@ -185,7 +185,7 @@ def test_fused_concurrent_lanes(mods, lanes):
 
 def test_fused_winner_at_owner_pixel(mods):
   """A rejected point nearer than every valid point of the reject bin's owner pixel takes that pixel's
-  depth: no valid point is its winner then (-1).  Found by scripts/gpu_fuzz.py (gan_manager voids, a
+  depth: no valid point is its winner then (-1).  Found by tests/tools/gpu_fuzz.py (gan_manager voids, a
   masked frame: many rejected points with small depths).  Single chunk, per-job bins, and the
   multi-chunk path where the owner pixel is patched after the last chunk."""
   g = mods['g']

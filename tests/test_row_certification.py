@@ -13,7 +13,7 @@ from se3ds_b200 import synth
 
 F32 = np.float32
 _spec = importlib.util.spec_from_file_location(
-    'row_cert_proto', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'scripts', 'proto', 'row_cert_proto.py'))
+    'row_cert_proto', os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tools', 'row_cert_proto.py'))
 proto = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(proto)
 

@@ -1,10 +1,10 @@
 """Randomised parity sweep on the GPU: random shapes / conventions / knobs against the bit-exact oracle.
-Usage: python scripts/gpu_fuzz.py [seconds] [seed]"""
+Usage: python tests/tools/gpu_fuzz.py [seconds] [seed]   (test tooling: it checks the CUDA path against oracle/)"""
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 

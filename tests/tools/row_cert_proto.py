@@ -6,7 +6,7 @@ row = floor(e * H / pi), and CERTIFY the row by comparing q with the tabulated c
 boundaries (cos is monotone) with a constant margin.  This script measures, against the bit-exact
 oracle, (a) that no certified row differs from the canonical row, (b) the deferral rate.
 
-Not product code; nothing here is imported by the package.  Run: python scripts/proto/row_cert_proto.py
+Not product code; nothing here is imported by the package.  Run: python tests/tools/row_cert_proto.py
 """
 import os
 import sys
@@ -86,7 +86,7 @@ if __name__ == '__main__' and len(sys.argv) == 1:
 # ------------------------------------------------------------------------------------------
 # Faithful float32 emulation of the kernel code (canon_math.cuh project_pixel_fast, row part) and of the
 # host table (se3ds_geom.cu get_tables), with the approximate reciprocal / square root perturbed by
-# +-2 ulp.  `python scripts/proto/row_cert_proto.py sweep` checks many shapes and seeds.
+# +-2 ulp.  `python tests/tools/row_cert_proto.py sweep` checks many shapes and seeds.
 KCOEF = np.array([float.fromhex(x) for x in ('0x1.921f16p+0', '-0x1.b67528p-3', '0x1.5a1b66p-4', '-0x1.22be94p-5', '0x1.171b8cp-7')], F32)
 
 

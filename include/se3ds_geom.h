@@ -80,13 +80,15 @@ int se3ds_ws_destroy(se3ds_ws* ws);
 int se3ds_ws_bytes(const se3ds_ws* ws, size_t* bytes);
 
 /* Projection mode of the fused path.  0: every point takes the canonical (IEEE-division)
- * projection; 1 (default): certified fast path -- MUFU approximations, accepted only when both
- * pixel coordinates are farther than the margin from an integer, canonical fallback otherwise, so
- * the results are the canonical ones bit for bit; 2: verify -- both are evaluated and compared
- * (slow; tests).  margin_scale > 0 overrides the margin (dx = W*scale, dy = 2*H*scale pixels).
- * se3ds_ws_verify_read returns {points, certified, certified-but-different} and the largest
- * distance by which a fast coordinate fell outside its canonical pixel (x, y; in pixels) since the
- * last read. */
+ * projection; 1 (default): certified fast path -- MUFU approximations, accepted only when the column
+ * coordinate is farther than the margin from an integer and z / rad lies inside the row's cosine
+ * interval shrunk by the margin, canonical fallback otherwise, so the results are the canonical ones
+ * bit for bit; 2: verify -- both are evaluated and compared (slow; tests).  margin_scale > 0 overrides
+ * the margin (dx = W*scale pixels, dy = 2*H*scale pixels = 2*pi*scale radians; default 1e-6 -- the
+ * measured deviation of the fast path is a tenth of that; smaller margins are for experiments in
+ * verify mode and void the bit-exactness of mode 1).  se3ds_ws_verify_read returns {points, certified,
+ * certified-but-different} and the largest distance by which a certified fast coordinate fell outside
+ * its canonical pixel (x, y; in pixels) since the last read. */
 int se3ds_ws_projection_mode(se3ds_ws* ws, int mode, float margin_scale);
 
 /* Programmatic dependent launch between the kernels of the fused path (default on): the next

@@ -177,14 +177,28 @@ int se3ds_reproject_se3(se3ds_ws* ws, const void* rgb, int rgb_dtype, const floa
                         float* proj_depth, float* proj_mask, int32_t* winner_out, float* bin_out,
                         void* stream);
 
+/* The memory of a trajectory as a frame RING (models/models.py:127-152,239-245 and the rollout loops
+ * trainers/gan_manager.py:462-463,550-551, utils/eval_metric.py:146-147,238-239 grow a concatenated
+ * cloud by tf.concat every frame: O(M) per step).  Same as se3ds_reproject_se3, but rgb / depth /
+ * src_pos are allocated for `s_capacity` frames per item -- (N,s_capacity,H,W,3), (N,s_capacity,H,W),
+ * (N,s_capacity,3) -- of which the first `s` are in use: a caller appends a frame by writing slot s in
+ * place and calling again with s + 1, nothing is copied or re-stacked. */
+int se3ds_reproject_ring(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
+                         const float* src_pos, const float* tgt_pos, const float* tgt_rot, int n, int s,
+                         int s_capacity, int p, int h, int w, float depth_scale, double mask_proportion,
+                         int mask_frames, int unproject_void, int project_void, unsigned flags,
+                         float* proj_image, float* proj_depth, float* proj_mask, int32_t* winner_out,
+                         float* bin_out, void* stream);
+
 /* Multi-GPU support for the global reject bin.  When se3ds_reproject is given bin_out (device,
  * 5 floats) the call's reject bin is NOT applied to job 0's pixel (0,0) but exported as
  * (min depth or +inf, max R, max G, max B, depth of that pixel's own winner or +inf); ranks reduce
  * the first four (min / max), the owner of global job 0 keeps its own fifth value and applies the
  * result with se3ds_apply_bin.  clip() and the divisions are monotone, so patching the finished
  * outputs is bit-identical to the single-call result; `winner` (job 0's winner plane, may be NULL)
- * gets -1 at the pixel when a rejected point is nearer than its own winner. */
-int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, float* proj_depth,
+ * gets -1 at the pixel when a rejected point is nearer than its own winner.  `flags`: pass
+ * SE3DS_FLAG_RAW_FEATURES when the outputs were produced with it (raw maxima, no x / 255). */
+int se3ds_apply_bin(const float* bin, float depth_scale, unsigned flags, float* proj_image, float* proj_depth,
                     float* proj_mask, int32_t* winner, void* stream);
 
 /* Same as se3ds_reproject with HOST buffers (pinned memory recommended): copies the inputs to the

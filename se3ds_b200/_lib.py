@@ -54,7 +54,9 @@ SIGNATURES = {
                         _vp, _vp, _vp],
     'se3ds_reproject_se3': [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp,
                             _vp, _vp, _vp, _vp],
-    'se3ds_apply_bin': [_vp, _f, _vp, _vp, _vp, _vp, _vp],
+    'se3ds_reproject_ring': [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp,
+                             _vp, _vp, _vp, _vp, _vp],
+    'se3ds_apply_bin': [_vp, _f, _u, _vp, _vp, _vp, _vp, _vp],
     'se3ds_reproject_host': [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp,
                              _vp, _vp],
     'se3ds_resize': [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
@@ -196,7 +198,7 @@ class Workspace:
       pass
 
 
-_default_ws: Dict[int, Workspace] = {}
+_default_ws: Dict[tuple, Workspace] = {}
 
 
 def plan_chunks(n: int, s: int, p: int, h: int, l2_chunk_bytes: int = 0, lanes: int = 2, min_points_per_lane: int = 0,
@@ -208,12 +210,20 @@ def plan_chunks(n: int, s: int, p: int, h: int, l2_chunk_bytes: int = 0, lanes: 
   return dict(lanes=out[0], items_per_chunk=out[1], poses_per_chunk=out[2], chunk_jobs=out[3], nchunks=out[4])
 
 
-def default_workspace(device) -> Workspace:
+def default_workspace(device, role: str = 'stream') -> Workspace:
+  """The process-wide default workspace for `device` AND the CUDA stream that is current on it.
+
+  The C ABI allows a workspace on one stream at a time (its z-buffer, feature buffer, scratch and bins
+  are reused by every call), so calls issued on different torch streams -- or through
+  se3ds_reproject_host, which runs on the workspace's own internal streams (role='host') -- must not
+  share one: the default is keyed by (device, stream handle / role).  Pass an explicit Workspace to
+  control placement yourself."""
   idx = torch.device(device).index
   if idx is None:
     idx = torch.cuda.current_device()
-  ws = _default_ws.get(idx)
+  key = (idx, 'host') if role == 'host' else (idx, int(torch.cuda.current_stream(idx).cuda_stream))
+  ws = _default_ws.get(key)
   if ws is None:
     chunk = int(os.environ.get('SE3DS_L2_CHUNK_MB', '0')) << 20
-    ws = _default_ws[idx] = Workspace(idx, 0, chunk)
+    ws = _default_ws[key] = Workspace(idx, 0, chunk)
   return ws

@@ -31,6 +31,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "canon_math.cuh"
 
 namespace se3ds {
@@ -81,6 +83,7 @@ struct FusedParams {
   float* out_mask;
   int* out_winner;
   int N, S, P, H, W, HW;
+  int SC;          // frame slots per item in rgb / depth / src_pos (>= S: a frame ring that is partly filled)
   int n0, p0, PC;  // chunk: items n0.., poses p0..p0+PC-1; blockIdx.z = (n-n0)*PC + (p-p0)
   int mh;          // int(H * mask_proportion)
   int mask_frames;
@@ -233,264 +236,301 @@ __device__ __forceinline__ SrcIdx src_index(const FusedParams& q) {
 // ------------------------------------------------------------------------------------------
 // K2: fused unproject + translate + project + depth splat
 // ------------------------------------------------------------------------------------------
+// Launch geometry: blockIdx.z = local job * S + frame, blockIdx.x = block of kThreads * 4 columns,
+// blockIdx.y = row group: a block walks the rows blockIdx.y + k * gridDim.y (k = 0 .. rows_per_block),
+// so the per-thread set-up (index math, poses, the column sines / cosines) is paid once per ~28 points
+// and the masked and unmasked rows of a pano are spread evenly over the blocks.  A thread owns 4
+// consecutive columns (VEC: one 128-bit depth load and two 128-bit scratch stores per row); the depth
+// of the next row is loaded while the current one is processed.  The host sizes rows_per_block so
+// that the grid is about one resident wave (8 blocks per SM).
+//
+// The kernel is bound by instruction issue, so the per-point path is kept to ~90 instructions:
+//  * rad: the two-fma refinement of MUFU.RSQ (fast_rad, = __fsqrt_rn for normal operands); its
+//    reciprocal square root doubles as 1 / rad for the elevation.
+//  * pixel: certified fast projection in pixel units (project_pixel_fast).
+//  * Points the fast path cannot certify (a few in a thousand), and points whose squared radius is
+//    zero / denormal / huge / not finite, are pushed on a warp-private stack in shared memory (one
+//    vote per point on the common path) and projected canonically 32 at a time by the whole warp
+//    (drain): no divergence in the slow path, no block barrier anywhere in the kernel.
 // FAST: uint8 RGB with project_void == -1 (every reference caller) and, if the compaction is on,
-// unproject_void == -1: a raw colour can then never equal a void class, so validity is decided by
-// the depth and the row mask alone and the per-channel compares disappear.
-// PROJ: 0 = canonical projection for every point, 1 = certified fast path; the few points it cannot
-// certify are queued in shared memory and projected canonically by a dense tail loop (so a single
-// uncertified lane does not drag its whole warp through the slow path), 2 = verify (both
-// projections for every point, disagreements counted into q.dbg; results are the canonical ones).
+// unproject_void == -1: a raw colour can then never equal a void class, so the fate of a point
+// (0 dropped / 1 rejected: only its depth feeds the reject bin / 2 projected) follows from its depth
+// validity and the row mask alone; otherwise the colours are read and compared.
+// PROJ: 0 = every point takes the canonical path (through the stack), 1 = certified fast path,
+// 2 = verify (both projections for every point, disagreements counted into q.dbg).
 // KEY64: the z-buffer holds the 64-bit packed (depth | point index) key -- the deterministic winner
 // (nearest depth, lowest index).  When the caller does not ask for winner indices the same minimum
 // depth comes from a 32-bit key (depth bits only): half the z-buffer traffic, identical guidance.
-template <typename RGB_T, int PPT, bool FAST, int PROJ, bool KEY64, bool ROT>
-__global__ void __launch_bounds__(kThreads) splat_depth_kernel(const FusedParams q) {
+constexpr int kStackCap = 160;  // < 32 entries survive a row, a row pushes at most 128 per warp
+
+template <typename RGB_T, bool VEC, bool FAST, int PROJ, bool KEY64, bool ROT>
+__global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedParams q) {
   // K2 only reads caller inputs until it touches the z-buffer / scratch / bins.  If the caller
   // guarantees that those inputs were not produced by the kernel launched just before this call
   // (SE3DS_FLAG_INPUTS_READY), the wait for the previous grid -- normally the resolve that re-arms
-  // the z-buffer -- is postponed until after the projection math; otherwise it comes first.
+  // the z-buffer -- is postponed until after the first row's projection math; otherwise it comes first.
   pdl_launch_dependents();
-  const bool late_wait = q.flags & SE3DS_FLAG_INPUTS_READY;
-  if (!late_wait) pdl_wait();
-  constexpr int kLaneStride = 1;
-  const SrcIdx ix = src_index<PPT, kLaneStride>(q);
-  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
-  uint32_t bin_z = 0u;  // ~ordered(min depth) of this thread's rejected points, 0 = none
-  // deferred points: every warp appends to its own segment (no shared counter, no init barrier)
-  constexpr int kWarps = kThreads / 32, kSeg = 32 * PPT;
-  __shared__ float4 sq_pt[PROJ == 1 ? kThreads * PPT : 1];     // X, Y, Z, rad
-  __shared__ uint32_t sq_meta[PROJ == 1 ? kThreads * PPT : 1];  // pixel | feature-valid << 30 | depth-valid << 31
-  __shared__ int sq_cnt[kWarps];
-  __shared__ uint32_t sm_z[kWarps];
-  int wq = 0;  // entries this warp has queued (warp-uniform)
+  bool waited = !(q.flags & SE3DS_FLAG_INPUTS_READY);
+  if (waited) pdl_wait();
+  constexpr int kWarps = kThreads / 32;
+  __shared__ float4 sq[kWarps][kStackCap];  // X, Y, Z, bits: source pixel | projected << 30 | depth-valid << 31
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned long long* zb = q.zbuf + (size_t)ix.lj * q.HW;
-  uint32_t* zb32 = q.zbuf32 + (size_t)ix.lj * q.HW;
-  const size_t sc_frame = ((size_t)ix.lj * q.S + ix.s) * q.HW;
-  const uint32_t idx_frame = (uint32_t)(ix.s * q.HW);
 
-  // classify one projected point: returns its scratch word (target pixel or rejected); the splat
-  // itself (below) is deferred until after pdl_wait()
-  auto commit = [&](int tpix, float rad, int pix, bool dvalid, bool fvalid) -> uint32_t {
-    const uint32_t dflag = dvalid ? 0u : kScDepthInv;
-    if (fvalid && tpix >= 0) return (uint32_t)tpix | dflag;
-    bin_z = max(bin_z, ~f32_ordered(rad));
-    return kScInvalid | dflag;
-  };
-  // With several source frames most points arrive at a pixel that already holds something nearer:
-  // a plain read (the entry only decreases, so a stale value is a safe filter) saves the REDG.
-  const bool prefilter = q.prefilter_z != 0;
-  auto splat = [&](uint32_t word, float rad, int pix) {
-    if (word & (kScInvalid | kScDropped)) return;
-    if constexpr (KEY64) {
-      const unsigned long long key = ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | ((word & kScDepthInv) ? 1u : 0u);
-      if (!prefilter || key < __ldcg(zb + (word & kScPixMask))) atomicMin(zb + (word & kScPixMask), key);
-    } else {
-      const uint32_t key = __float_as_uint(rad);
-      if (!prefilter || key < __ldcg(zb32 + (word & kScPixMask))) atomicMin(zb32 + (word & kScPixMask), key);
-    }
-  };
-
-  // Points past the end of a row run the loop as dropped points, so that the warp-wide ballots
-  // below always see all 32 lanes.
-  const int pix0 = ix.row * q.W + ix.col0;  // point k: pixel pix0 + kLaneStride * k
-  const size_t frame = (size_t)(ix.n * q.S + ix.s) * q.HW;
-  float d[PPT] = {}, sh[PPT] = {}, ch[PPT] = {};
-  RawRGB<RGB_T> raw[PPT];
-  bool act[PPT];
-  const float *sin_e = q.tab, *cos_e = q.tab + q.H, *sin_h = q.tab + 2 * q.H, *cos_h = sin_h + q.W;
-  const uint64_t stream_pol = l2_policy_evict_first();
+  const int zz = blockIdx.z;
+  int lj, s;
+  if (q.S == 1) { lj = zz; s = 0; } else { lj = zz / q.S; s = zz - lj * q.S; }
+  int n, p;
+  if (q.PC == 1) { n = q.n0 + lj; p = q.p0; } else { const int a = lj / q.PC; n = q.n0 + a; p = q.p0 + (lj - a * q.PC); }
+  const int job = n * q.P + p;
+  const int col0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
+  const int W = q.W, H = q.H;
+  bool act[4];
 #pragma unroll
-  for (int k = 0; k < PPT; ++k) act[k] = ix.col0 + kLaneStride * (PPT == 4 && kLaneStride == 1 ? 0 : k) < q.W;  // W % 4 == 0 on the PPT = 4 path
-  if constexpr (PPT == 4 && kLaneStride == 1) {  // W % 4 == 0: the four points are active together
+  for (int k = 0; k < 4; ++k) act[k] = col0 + (VEC ? 0 : k) < W;  // VEC: W % 4 == 0, the four points are active together
+
+  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? job : 0);
+  unsigned long long* zb = q.zbuf + (size_t)lj * q.HW;
+  uint32_t* zb32 = q.zbuf32 + (size_t)lj * q.HW;
+  const size_t sc_frame = ((size_t)lj * q.S + s) * q.HW;
+  const uint32_t idx_frame = (uint32_t)(s * q.HW);
+  const size_t frame = (size_t)(n * q.SC + s) * q.HW;
+  const float* dframe = q.depth + frame;
+  const float *sin_e = q.tab, *cos_e = q.tab + H, *sin_h = q.tab + 2 * H, *cos_h = sin_h + W;
+  const uint64_t stream_pol = l2_policy_evict_first();
+
+  float sh[4] = {}, ch[4] = {};
+  if constexpr (VEC) {
     if (act[0]) {
-      const uint4 dv = ldg_u128_stream(q.depth + frame + pix0, stream_pol);
-      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sin_h + ix.col0));
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cos_h + ix.col0));
-      d[0] = __uint_as_float(dv.x); d[1] = __uint_as_float(dv.y); d[2] = __uint_as_float(dv.z); d[3] = __uint_as_float(dv.w);
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sin_h + col0));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cos_h + col0));
       sh[0] = s4.x; sh[1] = s4.y; sh[2] = s4.z; sh[3] = s4.w;
       ch[0] = c4.x; ch[1] = c4.y; ch[2] = c4.z; ch[3] = c4.w;
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < PPT; ++k)
-      if (act[k]) {
-        const int col = ix.col0 + kLaneStride * k;
-        d[k] = __uint_as_float(ldg_u32_stream(q.depth + frame + pix0 + kLaneStride * k, stream_pol));
-        sh[k] = __ldg(sin_h + col); ch[k] = __ldg(cos_h + col);
-      }
+    for (int k = 0; k < 4; ++k)
+      if (act[k]) { sh[k] = __ldg(sin_h + col0 + k); ch[k] = __ldg(cos_h + col0 + k); }
   }
-  if constexpr (!FAST) {
-#pragma unroll
-    for (int k = 0; k < PPT; ++k)
-      if (act[k]) raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k, stream_pol);
-  }
-  const float se = __ldg(sin_e + ix.row), ce = __ldg(cos_e + ix.row);
-  const float* sp = q.src_pos + (size_t)(ix.n * q.S + ix.s) * 3;
-  const float* tp = q.tgt_pos + (size_t)ix.job * 3;
+  const float* sp = q.src_pos + (size_t)(n * q.SC + s) * 3;
+  const float* tp = q.tgt_pos + (size_t)job * 3;
   const float sx = __ldg(sp), sy = __ldg(sp + 1), sz = __ldg(sp + 2);
   const float tx = __ldg(tp), ty = __ldg(tp + 1), tz = __ldg(tp + 2);
   float rot[ROT ? 9 : 1];  // ROT: full SE(3) target pose (q.tgt_rot != nullptr), a separate instantiation
   if constexpr (ROT) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) rot[i] = __ldg(q.tgt_rot + (size_t)ix.job * 9 + i);
+    for (int i = 0; i < 9; ++i) rot[i] = __ldg(q.tgt_rot + (size_t)job * 9 + i);
   }
-  const bool masked = row_masked(q, ix.s, ix.row);
-  // FAST: the feature of a point is (uv,uv,uv) for an invalid depth, (-1,-1,-1) on a masked row, else a
-  // raw colour that equals no void class -- its fate follows from the depth validity and the row alone
-  int a_void = 2, a_row = 2;
-  if constexpr (FAST) {
-    const bool filt = q.flags & SE3DS_FLAG_FILTER_VOID;
-    a_void = filt ? 0 : (q.uv != -1 ? 2 : 1);
-    a_row = masked ? (filt ? 0 : 1) : 2;
-    if (PPT == 4 && kLaneStride == 1 && !act[0]) a_void = a_row = 0;  // the thread's four points lie past the row end together
-  }
-  uint32_t scf[PPT];
-  float scr[PPT];
-#pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    // pano_utils.py:220-236
-    const bool dvalid = d[k] > 0.0f && d[k] < 1.0f;
-    const float rad0 = __fmul_rn(__fmul_rn(d[k], q.depth_scale), dvalid ? 1.0f : 0.0f);
-    const float t = __fmul_rn(rad0, se);
-    const float x = __fmul_rn(t, ch[k]);
-    const float y = __fmul_rn(t, sh[k]);
-    const float z = __fmul_rn(rad0, ce);
-    // models.py:225-226 then :273-275 -- two roundings
-    float X = __fsub_rn(__fadd_rn(x, sx), tx);
-    float Y = __fsub_rn(__fadd_rn(y, sy), ty);
-    float Z = __fsub_rn(__fadd_rn(z, sz), tz);
-    if constexpr (ROT) {  // into the target camera frame: row-wise fma(r2, z, fma(r1, y, r0 * x))
-      const float a = X, b = Y, c = Z;
-      X = __fmaf_rn(rot[2], c, __fmaf_rn(rot[1], b, __fmul_rn(rot[0], a)));
-      Y = __fmaf_rn(rot[5], c, __fmaf_rn(rot[4], b, __fmul_rn(rot[3], a)));
-      Z = __fmaf_rn(rot[8], c, __fmaf_rn(rot[7], b, __fmul_rn(rot[6], a)));
-    }
-    // what happens to the point: 0 dropped (compaction, or past the end of the row), 1 rejected (void
-    // feature: only its depth feeds the reject bin, point_cloud_utils.py:146-149, no projection),
-    // 2 projected
-    int action;
-    if constexpr (FAST) {
-      action = (PPT == 4 && kLaneStride == 1) ? (dvalid ? a_row : a_void) : (act[k] ? (dvalid ? a_row : a_void) : 0);
-    } else {
-      const int3 f = point_feat(q, !dvalid, masked, raw[k].get());
-      const bool dropped = (q.flags & SE3DS_FLAG_FILTER_VOID) && f.x == q.uv && f.y == q.uv && f.z == q.uv;
-      const bool fv = f.x != q.pv && f.y != q.pv && f.z != q.pv;
-      action = (dropped || !act[k]) ? 0 : (fv ? 2 : 1);
-    }
-    const bool skip = action != 2;
-    constexpr bool fvalid = true;  // wherever it is still consulted below, the point is being projected
-    const float rad = canon_rad(X, Y, Z);
-    scr[k] = rad;
-    scf[k] = kScDropped;
-    if (action == 1) scf[k] = commit(-1, rad, pix0 + kLaneStride * k, dvalid, false);  // masked rows: branch-uniform
-    if constexpr (PROJ == 0) {
-      if (!skip) scf[k] = commit(project_pixel_rad(X, Y, Z, q.H, q.W, rad), rad, pix0 + kLaneStride * k, dvalid, fvalid);
-    } else {
-      int tpix = -1;
-      float fx = 0.f, fy = 0.f;
-      bool certain = true;
-      if (!skip) certain = project_pixel_fast(X, Y, Z, rad, q.H, q.W, q.fast, tpix, fx, fy);
-      if constexpr (PROJ == 1) {
-        const bool defer = !skip && !certain;
-        if (!skip && certain) scf[k] = (uint32_t)tpix | (dvalid ? 0u : kScDepthInv);  // fvalid holds here, tpix is inside the image
-        // uncertified points go to the warp's queue segment; the tail loop projects them canonically
-        const unsigned dmask = __ballot_sync(0xffffffffu, defer);
-        if (defer) {
-          const int slot = wid * kSeg + wq + __popc(dmask & ((1u << lane) - 1u));
-          sq_pt[slot] = make_float4(X, Y, Z, rad);
-          sq_meta[slot] = (uint32_t)(pix0 + kLaneStride * k) | (fvalid ? 1u << 30 : 0u) | (dvalid ? 1u << 31 : 0u);
+  const bool filt = q.flags & SE3DS_FLAG_FILTER_VOID;
+  const bool prefilter = q.prefilter_z != 0;
+  // FAST: fate of a depth-invalid point (feature = unproject_void everywhere, pano_utils.py:225)
+  const int a_void = filt ? 0 : (q.uv != -1 ? 2 : 1);
+
+  uint32_t minb = 0x7fffffffu;  // smallest depth bits among this thread's rejected points (depths are > 0 here)
+  int wq = 0;                   // entries on the warp's stack (warp-uniform)
+
+  // canonical projection of up to 32 stacked points by the whole warp
+  auto drain = [&]() {
+    __syncwarp();
+    const int m = min(wq, 32);
+    if (lane < m) {
+      const float4 e = sq[wid][wq - 1 - lane];
+      const uint32_t meta = __float_as_uint(e.w);
+      const int pix = (int)(meta & kScPixMask);
+      const bool dvalid = meta >> 31, isproj = (meta >> 30) & 1u;
+      const float rad = canon_rad(e.x, e.y, e.z);
+      const int tpix = isproj ? project_pixel_rad(e.x, e.y, e.z, H, W, rad) : -1;
+      const uint32_t dflag = dvalid ? 0u : kScDepthInv;
+      uint32_t word;
+      if (tpix >= 0) {
+        word = (uint32_t)tpix | dflag;
+        if constexpr (KEY64) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | (dvalid ? 0u : 1u);
+          if (!prefilter || key < __ldcg(zb + tpix)) atomicMin(zb + tpix, key);
+        } else {
+          const uint32_t key = __float_as_uint(rad);
+          if (!prefilter || key < __ldcg(zb32 + tpix)) atomicMin(zb32 + tpix, key);
         }
-        wq += __popc(dmask);
-      } else if (!skip) {
-        const int exact = project_pixel_rad(X, Y, Z, q.H, q.W, rad);
-        atomicAdd(q.dbg, 1ull);
-        if (certain) {
-          atomicAdd(q.dbg + 1, 1ull);
-          if (exact != tpix) atomicAdd(q.dbg + 2, 1ull);
-        }
-        if (exact >= 0 && fabsf(Z) < 0.984375f * rad) {  // how far the fast coordinates fall outside the canonical pixel
-          // (the fast row is a certified candidate, not a coordinate: it only counts when it was certified)
-          const float cx = (float)(exact % q.W), cy = (float)(exact / q.W);
-          const float ex = fmaxf(fmaxf(cx - fx, fx - (cx + 1.0f)), 0.0f), ey = certain ? fmaxf(fmaxf(cy - fy, fy - (cy + 1.0f)), 0.0f) : 0.0f;
-          atomicMax(q.dbg + 3, ((unsigned long long)__float_as_uint(ex) << 32) | __float_as_uint(ey));
-        }
-        scf[k] = commit(exact, rad, pix0 + kLaneStride * k, dvalid, fvalid);
+      } else {  // rejected: only its depth feeds the reject bin (point_cloud_utils.py:146-159)
+        word = kScInvalid | dflag;
+        const uint32_t zneg = ~f32_ordered(rad);
+        if (zneg) bin_update_z(bin, zneg);
       }
+      __stcg(q.sc_flat + sc_frame + pix, word);
+      __stcg(q.sc_rad + sc_frame + pix, rad);
     }
-  }
-  if (late_wait) pdl_wait();  // from here on: z-buffer, scratch and bins of this workspace
-  if (prefilter) {
-    // multi-frame jobs: issue the PPT filter reads together, then the reductions that can still win
-    unsigned long long cur[PPT];
+    wq -= m;
+    __syncwarp();
+  };
+
+  const int row_step = gridDim.y;
+  int row = blockIdx.y;
+  // depth of the first row
+  float dn[4] = {};
+  auto load_depth = [&](int r) {
+    if constexpr (VEC) {
+      if (act[0]) {
+        const uint4 dv = ldg_u128_stream(dframe + (size_t)r * W + col0, stream_pol);
+        dn[0] = __uint_as_float(dv.x); dn[1] = __uint_as_float(dv.y); dn[2] = __uint_as_float(dv.z); dn[3] = __uint_as_float(dv.w);
+      }
+    } else {
 #pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-      const bool ok = !(scf[k] & (kScInvalid | kScDropped));
-      if constexpr (KEY64) cur[k] = ok ? __ldcg(zb + (scf[k] & kScPixMask)) : 0ull;
-      else cur[k] = ok ? (unsigned long long)__ldcg(zb32 + (scf[k] & kScPixMask)) : 0ull;
+      for (int k = 0; k < 4; ++k)
+        if (act[k]) dn[k] = __uint_as_float(ldg_u32_stream(dframe + (size_t)r * W + col0 + k, stream_pol));
     }
+  };
+  if (row < H) load_depth(row);
+  for (; row < H; row += row_step) {
+    float d[4];
 #pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-      if (scf[k] & (kScInvalid | kScDropped)) continue;
-      if constexpr (KEY64) {
-        const unsigned long long key = ((unsigned long long)__float_as_uint(scr[k]) << 32) | ((idx_frame + (uint32_t)(pix0 + kLaneStride * k)) << 1) | ((scf[k] & kScDepthInv) ? 1u : 0u);
-        if (key < cur[k]) atomicMin(zb + (scf[k] & kScPixMask), key);
+    for (int k = 0; k < 4; ++k) d[k] = dn[k];
+    if (row + row_step < H) load_depth(row + row_step);
+    const float se = __ldg(sin_e + row), ce = __ldg(cos_e + row);
+    const bool masked = row_masked(q, s, row);
+    const int pix0 = row * W + col0;
+    // FAST: fate of a depth-valid point of this row (masked rows hold -1 features, pano_utils.py:262-265)
+    const int a_row = masked ? (filt ? 0 : 1) : 2;
+    RawRGB<RGB_T> raw[4];
+    if constexpr (!FAST) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (act[k]) raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + k, stream_pol);
+    }
+    uint32_t scf[4];
+    float scr[4];
+    bool hit[4];  // certified and projected: splat below
+    // LEAN rows (FAST only): no point of the row is projected (a masked row whose depth-invalid points
+    // are not projected either) -- only the depths of the rejected points are needed, for the reject bin.
+    auto points = [&](auto lean_tag) {
+      constexpr bool LEAN = decltype(lean_tag)::value;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // pano_utils.py:220-236
+      const bool dvalid = d[k] > 0.0f && d[k] < 1.0f;
+      const float rad0 = __fmul_rn(__fmul_rn(d[k], q.depth_scale), dvalid ? 1.0f : 0.0f);
+      const float t = __fmul_rn(rad0, se);
+      // models.py:225-226 then :273-275 -- two roundings
+      float X = __fsub_rn(__fadd_rn(__fmul_rn(t, ch[k]), sx), tx);
+      float Y = __fsub_rn(__fadd_rn(__fmul_rn(t, sh[k]), sy), ty);
+      float Z = __fsub_rn(__fadd_rn(__fmul_rn(rad0, ce), sz), tz);
+      if constexpr (ROT) {  // into the target camera frame: row-wise fma(r2, z, fma(r1, y, r0 * x))
+        const float a = X, b = Y, c = Z;
+        X = __fmaf_rn(rot[2], c, __fmaf_rn(rot[1], b, __fmul_rn(rot[0], a)));
+        Y = __fmaf_rn(rot[5], c, __fmaf_rn(rot[4], b, __fmul_rn(rot[3], a)));
+        Z = __fmaf_rn(rot[8], c, __fmaf_rn(rot[7], b, __fmul_rn(rot[6], a)));
+      }
+      int action;  // 0 dropped (compaction, or past the end of the row), 1 rejected (void feature), 2 projected
+      if constexpr (FAST) {
+        action = dvalid ? a_row : a_void;
+        if (!act[k]) action = 0;
       } else {
-        const uint32_t key = __float_as_uint(scr[k]);
-        if (key < (uint32_t)cur[k]) atomicMin(zb32 + (scf[k] & kScPixMask), key);
+        const int3 f = point_feat(q, !dvalid, masked, raw[k].get());
+        const bool dropped = filt && f.x == q.uv && f.y == q.uv && f.z == q.uv;
+        const bool fv = f.x != q.pv && f.y != q.pv && f.z != q.pv;
+        action = (dropped || !act[k]) ? 0 : (fv ? 2 : 1);
+      }
+      const bool proj = !LEAN && action == 2, rej = action == 1;
+      const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(X, X), __fmul_rn(Y, Y)), __fmul_rn(Z, Z));
+      float rs;
+      bool sq_ok;
+      const float rad = fast_rad(r2, rs, sq_ok);
+      int tpix = 0, frow = 0;
+      float fx = 0.f;
+      bool certain = false;
+      if constexpr (!LEAN && PROJ != 0) certain = project_pixel_fast(X, Y, Z, rs, H, W, q.fast, tpix, fx, frow) && sq_ok;
+      if constexpr (PROJ == 2 && !LEAN) {
+        if (proj) {
+          const float radx = canon_rad(X, Y, Z);
+          const int exact = project_pixel_rad(X, Y, Z, H, W, radx);
+          atomicAdd(q.dbg, 1ull);
+          if (certain) {
+            atomicAdd(q.dbg + 1, 1ull);
+            if (exact != tpix || __float_as_uint(radx) != __float_as_uint(rad)) atomicAdd(q.dbg + 2, 1ull);
+          }
+          if (exact >= 0 && fabsf(Z) < 0.984375f * radx) {  // how far the fast column falls outside the canonical pixel
+            // (the fast row is a certified candidate, not a coordinate: it only counts when it was certified)
+            const float cx = (float)(exact % W);
+            const float ex = fmaxf(fmaxf(cx - fx, fx - (cx + 1.0f)), 0.0f);
+            const float ey = (certain && frow != exact / W) ? 1.0f : 0.0f;
+            atomicMax(q.dbg + 3, ((unsigned long long)__float_as_uint(ex) << 32) | __float_as_uint(ey));
+          }
+          certain = false;  // the results are the canonical ones
+        }
+      }
+      const uint32_t dflag = dvalid ? 0u : kScDepthInv;
+      hit[k] = proj && certain;
+      scr[k] = rad;
+      scf[k] = (proj ? (uint32_t)tpix : (rej ? kScInvalid : kScDropped)) | dflag;
+      minb = min(minb, (rej && sq_ok) ? __float_as_uint(rad) : 0x7fffffffu);
+      // the rest goes to the warp's stack: projected but uncertified, or a radius the fast square root
+      // does not cover; drain() finishes those points (pixel, splat, scratch, reject bin)
+      const bool defer = (proj && !certain) || (rej && !sq_ok);
+      if (__any_sync(0xffffffffu, defer)) {
+        const unsigned dmask = __ballot_sync(0xffffffffu, defer);
+        if (defer)
+          sq[wid][wq + __popc(dmask & ((1u << lane) - 1u))] =
+              make_float4(X, Y, Z, __uint_as_float((uint32_t)(pix0 + k) | (proj ? 1u << 30 : 0u) | (dvalid ? 1u << 31 : 0u)));
+        wq += __popc(dmask);
       }
     }
-  } else {
+    };
+    if (FAST && a_row != 2 && a_void != 2) points(std::true_type{});
+    else points(std::false_type{});
+    if (!waited) { pdl_wait(); waited = true; }  // from here on: z-buffer, scratch and bins of this workspace
+    if (prefilter) {
+      // multi-frame jobs: most points arrive at a pixel that already holds something nearer; a plain read
+      // (the entry only decreases, so a stale value is a safe filter) saves the reduction.  The four
+      // filter reads are issued together.
+      unsigned long long cur[4];
 #pragma unroll
-    for (int k = 0; k < PPT; ++k) splat(scf[k], scr[k], pix0 + kLaneStride * k);
-  }
-  if constexpr (PPT == 4 && kLaneStride == 1) {
-    if (act[0]) {
-      __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc_frame + pix0), make_uint4(scf[0], scf[1], scf[2], scf[3]));
-      __stcg(reinterpret_cast<float4*>(q.sc_rad + sc_frame + pix0), make_float4(scr[0], scr[1], scr[2], scr[3]));
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < PPT; ++k)
-      if (act[k]) {
-        __stcg(q.sc_flat + sc_frame + pix0 + kLaneStride * k, scf[k]);
-        __stcg(q.sc_rad + sc_frame + pix0 + kLaneStride * k, scr[k]);
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (KEY64) cur[k] = hit[k] ? __ldcg(zb + (scf[k] & kScPixMask)) : 0ull;
+        else cur[k] = hit[k] ? (unsigned long long)__ldcg(zb32 + (scf[k] & kScPixMask)) : 0ull;
       }
-  }
-  // one barrier: publishes the per-warp reject minima and queue lengths (and orders the scratch
-  // stores above before the tail loop's fix-ups)
-  const uint32_t wz = __reduce_max_sync(0xffffffffu, bin_z);
-  if (lane == 0) { sm_z[wid] = wz; sq_cnt[wid] = wq; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t m = sm_z[0];
 #pragma unroll
-    for (int i = 1; i < kWarps; ++i) m = max(m, sm_z[i]);
-    if (m) bin_update_z(bin, m);
-  }
-  if constexpr (PROJ == 1) {
-    int total = 0;
-#pragma unroll
-    for (int j = 0; j < kWarps; ++j) total += sq_cnt[j];
-    for (int i = threadIdx.x; i < total; i += kThreads) {
-      int w = 0, base = 0, acc = 0;  // segment that holds the i-th deferred point
-#pragma unroll
-      for (int j = 0; j < kWarps - 1; ++j) {
-        acc += sq_cnt[j];
-        if (i >= acc) { w = j + 1; base = acc; }
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (KEY64) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(scr[k]) << 32) | ((idx_frame + (uint32_t)(pix0 + k)) << 1) | ((scf[k] & kScDepthInv) ? 1u : 0u);
+          if (hit[k] && key < cur[k]) atomicMin(zb + (scf[k] & kScPixMask), key);
+        } else {
+          const uint32_t key = __float_as_uint(scr[k]);
+          if (hit[k] && key < (uint32_t)cur[k]) atomicMin(zb32 + (scf[k] & kScPixMask), key);
+        }
       }
-      const int slot = w * kSeg + (i - base);
-      const float4 pt = sq_pt[slot];
-      const uint32_t m = sq_meta[slot];
-      const int pix = (int)(m & 0x3FFFFFFFu);
-      const int tpix = project_pixel_rad(pt.x, pt.y, pt.z, q.H, q.W, pt.w);
-      bin_z = 0u;
-      const uint32_t word = commit(tpix, pt.w, pix, m >> 31, (m >> 30) & 1u);
-      splat(word, pt.w, pix);
-      q.sc_flat[sc_frame + pix] = word;
-      if (bin_z) bin_update_z(bin, bin_z);  // a deferred point that turned out to be rejected (rare)
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!hit[k]) continue;
+        if constexpr (KEY64) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(scr[k]) << 32) | ((idx_frame + (uint32_t)(pix0 + k)) << 1) | ((scf[k] & kScDepthInv) ? 1u : 0u);
+          atomicMin(zb + (scf[k] & kScPixMask), key);
+        } else {
+          atomicMin(zb32 + (scf[k] & kScPixMask), __float_as_uint(scr[k]));
+        }
+      }
     }
+    // K3 skips the masked rows altogether when their features (-1 / unproject_void) cannot raise a maximum
+    if (!(masked && q.uv <= 0)) {
+      if constexpr (VEC) {
+        if (act[0]) {
+          __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc_frame + pix0), make_uint4(scf[0], scf[1], scf[2], scf[3]));
+          __stcg(reinterpret_cast<float4*>(q.sc_rad + sc_frame + pix0), make_float4(scr[0], scr[1], scr[2], scr[3]));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (act[k]) {
+            __stcg(q.sc_flat + sc_frame + pix0 + k, scf[k]);
+            __stcg(q.sc_rad + sc_frame + pix0 + k, scr[k]);
+          }
+      }
+    }
+    while (wq >= 32) drain();
   }
+  if (!waited) pdl_wait();
+  while (wq > 0) drain();
+  // reject bin: smallest depth of this warp's rejected points (drain() adds its own)
+  const uint32_t wmin = __reduce_min_sync(0xffffffffu, minb);
+  if (lane == 0 && wmin != 0x7fffffffu) bin_update_z(bin, 0x7fffffffu - wmin);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -510,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 16) splat_feat_kernel(const FusedPar
   int3 bin_f = make_int3(0, 0, 0);
   if (ix.col0 < q.W) {
     const int pix0 = ix.row * q.W + ix.col0;  // point k: pixel pix0 + kLaneStride * k
-    const size_t frame = (size_t)(ix.n * q.S + ix.s) * q.HW;
+    const size_t frame = (size_t)(ix.n * q.SC + ix.s) * q.HW;
     const size_t sc0 = ((size_t)ix.lj * q.S + ix.s) * q.HW + pix0;
     uint32_t scf[PPT];
     float scr[PPT];
@@ -767,14 +807,15 @@ __global__ void export_bin_kernel(const FusedParams q) {
 }
 
 // Applies a (reduced) bin to pixel (0,0) of the first job of finished guidance tensors.
-__global__ void apply_bin_kernel(const float* bin, float depth_scale, float* image, float* depth, float* mask, int32_t* winner) {
+__global__ void apply_bin_kernel(const float* bin, float depth_scale, bool raw, float* image, float* depth, float* mask, int32_t* winner) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (winner && bin[0] < bin[4]) winner[0] = -1;  // a rejected point is nearer than the pixel's own winner
   const float d = fminf(depth[0], __fdiv_rn(fminf(fmaxf(bin[0], 0.0f), depth_scale), depth_scale));
   depth[0] = d;
   float f[3];
-  for (int c = 0; c < 3; ++c) { f[c] = fmaxf(image[c], clip01_div255(bin[1 + c])); image[c] = f[c]; }
-  mask[0] = (d > 0.0f && d < 1.0f) ? 1.0f : 0.0f;
+  // raw: the outputs hold raw per-channel maxima (SE3DS_FLAG_RAW_FEATURES), else clip(x / 255, 0, 1)
+  for (int c = 0; c < 3; ++c) { f[c] = fmaxf(image[c], raw ? bin[1 + c] : clip01_div255(bin[1 + c])); image[c] = f[c]; }
+  mask[0] = (d > 0.0f && d < 1.0f && f[0] != -1.0f && f[1] != -1.0f && f[2] != -1.0f) ? 1.0f : 0.0f;
 }
 
 // ------------------------------------------------------------------------------------------

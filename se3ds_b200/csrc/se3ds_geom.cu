@@ -31,6 +31,10 @@ int fail(int status, const char* fmt, ...) {
   return status;
 }
 
+#define GUARD(device)        \
+  DeviceGuard guard_(device); \
+  CU(guard_.err)
+
 #define CU(call)                                                                          \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \
@@ -43,6 +47,34 @@ struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
 };
+
+// Every entry point runs on the device of its workspace (or of its tensors) and leaves the caller's
+// current device as it found it -- a process that drives several GPUs (or PyTorch's own device
+// bookkeeping) must not see it change behind its back.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && device >= 0 && device != prev) err = cudaSetDevice(device);
+    else if (device < 0 || device == prev) prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// device that owns a device pointer (-1: not a device pointer / unknown: stay on the current device)
+int device_of(const void* p) {
+  cudaPointerAttributes a;
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
 
 struct TableEntry {
   int h, w;
@@ -234,11 +266,24 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// K2 grid: a block walks several rows (kernels.cuh); rows_per_block is sized so that the grid is about
+// one resident wave of kK2BlocksPerSM blocks per SM, capped so that short panos still spread over the SMs.
+constexpr int kK2BlocksPerSM = 8;
+int k2_row_groups(const se3ds_ws* ws, int gx, int h, int job_frames) {
+  const long long row_blocks = (long long)gx * h * job_frames;
+  const long long resident = (long long)ws->sm_count * kK2BlocksPerSM;
+  long long rpb = (row_blocks + resident - 1) / resident;
+  rpb = std::max<long long>(1, std::min<long long>(rpb, 32));
+  return (int)((h + rpb - 1) / rpb);
+}
+
 template <typename RGB_T, int PPT, bool KEY64>
 int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st) {
   const int gx = (q.W + kThreads * PPT - 1) / (kThreads * PPT);
   const int jobs = nitems * q.PC;
   const dim3 grid(gx, q.H, jobs * q.S), block(kThreads);
+  const int gx2 = (q.W + kThreads * 4 - 1) / (kThreads * 4);
+  const dim3 grid2(gx2, k2_row_groups(ws, gx2, q.H, jobs * q.S), jobs * q.S);
   cudaEvent_t* ev = nullptr;
   if (ws->profile) {
     if (ws->ev_used + 4 > ws->ev_pool.size())
@@ -256,10 +301,11 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
                     (!(q.flags & SE3DS_FLAG_FILTER_VOID) || q.uv == -1);
   const int proj = ws->proj_mode;
   const bool pdl = ws->pdl && !ws->profile;
-#define LAUNCH_K2(F, P)                                                                                        \
-  do {                                                                                                        \
-    if (q.tgt_rot) CU(launch_pdl(splat_depth_kernel<RGB_T, PPT, F, P, KEY64, true>, grid, block, st, pdl, q)); \
-    else CU(launch_pdl(splat_depth_kernel<RGB_T, PPT, F, P, KEY64, false>, grid, block, st, pdl, q));          \
+  constexpr bool VEC = PPT == 4;
+#define LAUNCH_K2(F, P)                                                                                         \
+  do {                                                                                                         \
+    if (q.tgt_rot) CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, true>, grid2, block, st, pdl, q)); \
+    else CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, false>, grid2, block, st, pdl, q));          \
   } while (0)
   if (fast) { if (proj == 0) LAUNCH_K2(true, 0); else if (proj == 1) LAUNCH_K2(true, 1); else LAUNCH_K2(true, 2); }
   else { if (proj == 0) LAUNCH_K2(false, 0); else if (proj == 1) LAUNCH_K2(false, 1); else LAUNCH_K2(false, 2); }
@@ -304,7 +350,7 @@ int se3ds_ws_create(int device, size_t max_bytes, size_t l2_chunk_bytes, se3ds_w
   int count = 0;
   CU(cudaGetDeviceCount(&count));
   if (device < 0 || device >= count) return fail(SE3DS_ERR_BAD_ARG, "device %d of %d", device, count);
-  CU(cudaSetDevice(device));
+  GUARD(device);
   se3ds_ws* ws = new se3ds_ws();
   ws->device = device;
   cudaDeviceGetAttribute(&ws->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -322,7 +368,7 @@ int se3ds_ws_create(int device, size_t max_bytes, size_t l2_chunk_bytes, se3ds_w
 
 int se3ds_ws_destroy(se3ds_ws* ws) {
   if (!ws) return SE3DS_OK;
-  cudaSetDevice(ws->device);
+  DeviceGuard guard_(ws->device);
   cudaDeviceSynchronize();
   for (DevBuf* b : {&ws->zbuf, &ws->zbuf32, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->dbg, &ws->s_rgb, &ws->s_depth,
                     &ws->s_src, &ws->s_tgt, &ws->s_img, &ws->s_dep, &ws->s_msk, &ws->s_win})
@@ -385,7 +431,7 @@ int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_d
   counts[0] = counts[1] = counts[2] = 0;
   max_dev[0] = max_dev[1] = 0.f;
   if (!ws->dbg.p) return SE3DS_OK;
-  CU(cudaSetDevice(ws->device));
+  GUARD(ws->device);
   CU(cudaDeviceSynchronize());
   unsigned long long h[4];
   CU(cudaMemcpy(h, ws->dbg.p, sizeof(h), cudaMemcpyDeviceToHost));
@@ -406,7 +452,7 @@ int se3ds_ws_profile(se3ds_ws* ws, int enable) {
 
 int se3ds_ws_profile_read(se3ds_ws* ws, float ms[3], unsigned long long* launches) {
   if (!ws || !ms) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
-  CU(cudaSetDevice(ws->device));
+  GUARD(ws->device);
   ms[0] = ms[1] = ms[2] = 0.f;
   for (size_t i = 0; i + 4 <= ws->ev_used; i += 4) {
     CU(cudaEventSynchronize(ws->ev_pool[i + 3]));
@@ -424,6 +470,7 @@ int se3ds_ws_profile_read(se3ds_ws* ws, float ms[3], unsigned long long* launche
 int se3ds_mask_pano(const void* pano, int dtype, int n, int h, int w, int c, double proportion,
                     double masked_region_value, void* out, void* stream) {
   if (!pano || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL tensor");
+  GUARD(device_of(out));
   if (n < 0 || h <= 0 || w <= 0 || c <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "pano must be (N,H,W,C)");
   const long long total = (long long)n * h * w * c;
   if (total == 0) return SE3DS_OK;
@@ -458,7 +505,7 @@ int se3ds_unproject_equirect(se3ds_ws* ws, const void* feats, int in_dtype, cons
   if (out_dtype != in_dtype && out_dtype != SE3DS_F32) return fail(SE3DS_ERR_BAD_DTYPE, "out dtype must be the input dtype or f32");
   if (n == 0) return SE3DS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  CU(cudaSetDevice(ws->device));
+  GUARD(ws->device);
   const float* tab = nullptr;
   if (int rc = get_tables(ws, h, w, st, &tab)) return rc;
   const long long total = (long long)n * h * w;
@@ -488,7 +535,7 @@ int se3ds_project_cloud(se3ds_ws* ws, const float* coords, const void* feats, in
   if (feat_dtype < SE3DS_U8 || feat_dtype > SE3DS_F32) return fail(SE3DS_ERR_BAD_DTYPE, "dtype %d", feat_dtype);
   if (n == 0) return SE3DS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  CU(cudaSetDevice(ws->device));
+  GUARD(ws->device);
   const long long npix = (long long)n * h * w;
   if (ws->dirty)
     if (int rc = rearm(ws, st)) return rc;
@@ -544,23 +591,26 @@ struct HostPipe {
 };
 
 int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
-                   const float* src_pos, const float* tgt_pos, const float* tgt_rot, int n, int s, int p, int h, int w,
+                   const float* src_pos, const float* tgt_pos, const float* tgt_rot, int n, int s, int s_capacity, int p, int h, int w,
                    float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
                    int project_void, unsigned flags, float* proj_image, float* proj_depth,
                    float* proj_mask, int32_t* winner_out, float* bin_out, void* stream, const HostPipe* pipe) {
   if (!ws || !rgb || !depth || !src_pos || !tgt_pos || !proj_image || !proj_depth || !proj_mask)
     return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
   if (n < 0 || s <= 0 || p <= 0 || h <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "rgb must be (N,S,H,W,3), tgt_pos (N,P,3)");
+  if (s_capacity == 0) s_capacity = s;
+  if (s_capacity < s) return fail(SE3DS_ERR_BAD_SHAPE, "frame capacity %d < frames %d", s_capacity, s);
   if (w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "Expected equirectangular input images");
   if (rgb_dtype != SE3DS_U8 && rgb_dtype != SE3DS_I32) return fail(SE3DS_ERR_BAD_DTYPE, "rgb must be uint8 or int32");
   if (unproject_void < -1 || unproject_void > 255 || project_void < -1 || project_void > 255)
     return fail(SE3DS_ERR_BAD_ARG, "void classes must be in [-1, 255]");
   const long long hw = (long long)h * w;
   if (hw > (long long)kScPixMask || (long long)s * hw >= (1ll << 31)) return fail(SE3DS_ERR_BAD_SHAPE, "S*H*W too large");
+  if ((long long)n * (s_capacity ? s_capacity : s) >= (1ll << 31) / 3) return fail(SE3DS_ERR_BAD_SHAPE, "N*S too large");
   if (s > 65535 || h > 65535) return fail(SE3DS_ERR_BAD_SHAPE, "S or H too large");
   if (n == 0) return SE3DS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  CU(cudaSetDevice(ws->device));
+  GUARD(ws->device);
 
   // job chunking and lanes (plan_chunks below)
   const long long J = (long long)n * p;
@@ -591,7 +641,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   q.zbuf = (unsigned long long*)ws->zbuf.p; q.zbuf32 = (uint32_t*)ws->zbuf32.p; q.fbuf = (uint2*)ws->fbuf.p;
   q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.bins = (Bin*)ws->bins.p;
   q.out_image = proj_image; q.out_depth = proj_depth; q.out_mask = proj_mask; q.out_winner = winner_out;
-  q.N = n; q.S = s; q.P = p; q.H = h; q.W = w; q.HW = (int)hw;
+  q.N = n; q.S = s; q.SC = s_capacity; q.P = p; q.H = h; q.W = w; q.HW = (int)hw;
   q.mh = (int)(h * mask_proportion);
   q.mask_frames = mask_frames;
   q.uv = unproject_void; q.pv = project_void; q.flags = flags; q.depth_scale = depth_scale;
@@ -603,16 +653,24 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   q.prefilter_f = (s > 1 && lanes * lane_px * 8 <= ((size_t)48 << 20)) ? 1 : 0;
   if (int rc = grow(ws->dbg, 4 * sizeof(unsigned long long), 0, st)) return rc;
   q.dbg = (unsigned long long*)ws->dbg.p;
-  q.fast.kx = (float)((double)w / (2.0 * 3.141592653589793));
-  q.fast.ky = (float)((double)h / 3.141592653589793);
-  q.fast.dx = (float)w * ws->margin_scale;
-  q.fast.dy = (float)h * 2.0f * ws->margin_scale;
+  {  // certified fast projection: polynomials in pixel units (canon_math.cuh)
+    const double kx = (double)w / (2.0 * 3.141592653589793), ky = (double)h / 3.141592653589793;
+    const double atan_c[9] = CANON_ATAN_COEFFS, acos_c[5] = FAST_ACOS_COEFFS;
+    for (int i = 0; i < 9; ++i) q.fast.ca[i] = (float)(kx * atan_c[i]);
+    for (int i = 0; i < 5; ++i) q.fast.ce[i] = (float)(ky * acos_c[i]);
+    q.fast.kx = (float)kx;
+    q.fast.w4 = (float)(0.25 * w); q.fast.w34 = (float)(0.75 * w); q.fast.hf = (float)h;
+    q.fast.dx = (float)w * ws->margin_scale;
+  }
   q.fast.rowb = reinterpret_cast<const float2*>(tab + 2 * (size_t)h + 2 * (size_t)w);
   {
     volatile float one = 1.0f, ds = depth_scale;
     q.inv_depth_scale = one / ds;  // IEEE single division on the host: RN(1 / depth_scale)
   }
-  const bool vec = (w % 4 == 0) && aligned(depth, 16) && aligned(rgb, rgb_dtype == SE3DS_U8 ? 4 : 16);
+  // the 4-pixels-per-thread kernels use 128 / 256-bit accesses on the inputs AND on every output plane
+  const bool vec = (w % 4 == 0) && aligned(depth, 16) && aligned(rgb, rgb_dtype == SE3DS_U8 ? 4 : 16) &&
+                   aligned(proj_image, 16) && aligned(proj_depth, 16) && aligned(proj_mask, 16) &&
+                   (!winner_out || aligned(winner_out, 16));
 
   ws->dirty = true;
   // fork: everything enqueued so far on the caller's stream (its inputs, re-arming, tables) comes first
@@ -686,7 +744,7 @@ int se3ds_reproject(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* d
                     float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
                     int project_void, unsigned flags, float* proj_image, float* proj_depth,
                     float* proj_mask, int32_t* winner_out, float* bin_out, void* stream) {
-  return reproject_core(ws, rgb, rgb_dtype, depth, src_pos, tgt_pos, nullptr, n, s, p, h, w, depth_scale,
+  return reproject_core(ws, rgb, rgb_dtype, depth, src_pos, tgt_pos, nullptr, n, s, s, p, h, w, depth_scale,
                         mask_proportion, mask_frames, unproject_void, project_void, flags, proj_image, proj_depth,
                         proj_mask, winner_out, bin_out, stream, nullptr);
 }
@@ -697,7 +755,18 @@ int se3ds_reproject_se3(se3ds_ws* ws, const void* rgb, int rgb_dtype, const floa
                         int unproject_void, int project_void, unsigned flags, float* proj_image,
                         float* proj_depth, float* proj_mask, int32_t* winner_out, float* bin_out,
                         void* stream) {
-  return reproject_core(ws, rgb, rgb_dtype, depth, src_pos, tgt_pos, tgt_rot, n, s, p, h, w, depth_scale,
+  return reproject_core(ws, rgb, rgb_dtype, depth, src_pos, tgt_pos, tgt_rot, n, s, s, p, h, w, depth_scale,
+                        mask_proportion, mask_frames, unproject_void, project_void, flags, proj_image, proj_depth,
+                        proj_mask, winner_out, bin_out, stream, nullptr);
+}
+
+int se3ds_reproject_ring(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* depth,
+                         const float* src_pos, const float* tgt_pos, const float* tgt_rot, int n, int s,
+                         int s_capacity, int p, int h, int w, float depth_scale, double mask_proportion,
+                         int mask_frames, int unproject_void, int project_void, unsigned flags,
+                         float* proj_image, float* proj_depth, float* proj_mask, int32_t* winner_out,
+                         float* bin_out, void* stream) {
+  return reproject_core(ws, rgb, rgb_dtype, depth, src_pos, tgt_pos, tgt_rot, n, s, s_capacity, p, h, w, depth_scale,
                         mask_proportion, mask_frames, unproject_void, project_void, flags, proj_image, proj_depth,
                         proj_mask, winner_out, bin_out, stream, nullptr);
 }
@@ -713,7 +782,7 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
     return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
   if (n <= 0 || s <= 0 || p <= 0 || h <= 0 || w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "bad shape");
   if (rgb_dtype != SE3DS_U8 && rgb_dtype != SE3DS_I32) return fail(SE3DS_ERR_BAD_DTYPE, "rgb must be uint8 or int32");
-  CU(cudaSetDevice(ws->device));
+  GUARD(ws->device);
   for (cudaStream_t* sp : {&ws->hstream, &ws->h2d_stream, &ws->d2h_stream})
     if (!*sp) CU(cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking));
   while (ws->pipe_ev.size() < (size_t)2 * n) {
@@ -748,7 +817,7 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
   HostPipe pipe{ws->d2h_stream, ws->pipe_ev.data(), ws->pipe_ev.data() + n, proj_image_host, proj_depth_host,
                 proj_mask_host, winner_out_host};
   if (int rc = reproject_core(ws, ws->s_rgb.p, rgb_dtype, (const float*)ws->s_depth.p, (const float*)ws->s_src.p,
-                              (const float*)ws->s_tgt.p, nullptr, n, s, p, h, w, depth_scale, mask_proportion, mask_frames,
+                              (const float*)ws->s_tgt.p, nullptr, n, s, s, p, h, w, depth_scale, mask_proportion, mask_frames,
                               unproject_void, project_void, flags, (float*)ws->s_img.p, (float*)ws->s_dep.p,
                               (float*)ws->s_msk.p, winner_out_host ? (int32_t*)ws->s_win.p : nullptr, nullptr, st, &pipe))
     return rc;
@@ -757,10 +826,11 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
   return SE3DS_OK;
 }
 
-int se3ds_apply_bin(const float* bin, float depth_scale, float* proj_image, float* proj_depth,
+int se3ds_apply_bin(const float* bin, float depth_scale, unsigned flags, float* proj_image, float* proj_depth,
                     float* proj_mask, int32_t* winner, void* stream) {
   if (!bin || !proj_image || !proj_depth || !proj_mask) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
-  apply_bin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bin, depth_scale, proj_image, proj_depth, proj_mask, winner);
+  GUARD(device_of(proj_image));
+  apply_bin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bin, depth_scale, (flags & SE3DS_FLAG_RAW_FEATURES) != 0, proj_image, proj_depth, proj_mask, winner);
   return launch_check("apply_bin_kernel");
 }
 
@@ -768,6 +838,7 @@ int se3ds_filtered_coords_and_feats(const void* feats, int dtype, const float* d
                                     float depth_scale, float kinv_x, float kinv_y, float* xyz_out, float* feats_out,
                                     void* stream) {
   if (!feats || !depth || !xyz_out || !feats_out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  GUARD(device_of(xyz_out));
   if (n < 0 || h <= 0 || w <= 0 || c <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "feats should have shape (N, H, W) or (N, H, W, C)");
   const long long total = (long long)n * h * w;
   if (total == 0) return SE3DS_OK;
@@ -782,6 +853,7 @@ int se3ds_filtered_coords_and_feats(const void* feats, int dtype, const float* d
 
 int se3ds_pixel_rays(int output_height, float* out, void* stream) {
   if (!out || output_height <= 0) return fail(SE3DS_ERR_BAD_ARG, "bad argument");
+  GUARD(device_of(out));
   const long long total = 2ll * output_height * output_height;
   pixel_rays_kernel<<<(int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32), kThreads, 0, (cudaStream_t)stream>>>(output_height, out);
   return launch_check("pixel_rays_kernel");
@@ -790,6 +862,7 @@ int se3ds_pixel_rays(int output_height, float* out, void* stream) {
 int se3ds_rotate_pano(const float* pano, const float* matrix, int n, int h, int w, int c, int output_height,
                       float* out, void* stream) {
   if (!pano || !matrix || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  GUARD(device_of(out));
   if (n < 0 || h < 2 || c <= 0 || output_height <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "pano must be (N,H,W,C)");
   if (w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "Pano width must be twice height.");
   const long long total = (long long)n * output_height * 2 * output_height;
@@ -803,6 +876,7 @@ int se3ds_project_perspective_image(const float* image, int h, int w, int c, con
                                     int output_height, int pad, float pad_value, int round_to_nearest, float* out,
                                     void* stream) {
   if (!image || !world_to_image || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  GUARD(device_of(out));
   if (h < 1 || w < 1 || c <= 0 || output_height <= 0 || (!pad && (h < 2 || w < 2))) return fail(SE3DS_ERR_BAD_SHAPE, "image must be (H,W,C)");
   Mat3 m;
   memcpy(m.m, world_to_image, sizeof(m.m));
@@ -815,6 +889,7 @@ int se3ds_project_perspective_image(const float* image, int h, int w, int c, con
 int se3ds_perspective_from_equirect(const float* image, int eq_h, int eq_w, int c, const float kinv_t[9],
                                     const float rotation[9], int height, int width, float* out, void* stream) {
   if (!image || !kinv_t || !rotation || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  GUARD(device_of(out));
   if (eq_h < 2 || eq_w < 2 || c <= 0 || height <= 0 || width <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "image must be (H,W,C)");
   Mat3 a, r;
   memcpy(a.m, kinv_t, sizeof(a.m));
@@ -828,6 +903,7 @@ int se3ds_perspective_from_equirect(const float* image, int eq_h, int eq_w, int 
 int se3ds_resize(const void* in, int dtype, int n, int h, int w, int c, int out_h, int out_w, int bilinear,
                  void* out, void* stream) {
   if (!in || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  GUARD(device_of(out));
   if (n < 0 || h <= 0 || w <= 0 || c <= 0 || out_h <= 0 || out_w <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "images must be (N,H,W,C)");
   const long long total = (long long)n * out_h * out_w;
   if (total == 0) return SE3DS_OK;
@@ -852,6 +928,7 @@ int se3ds_resize(const void* in, int dtype, int n, int h, int w, int c, int out_
 int se3ds_interpolate_bilinear(const float* grid, const float* query_points, int b, int h, int w, int c,
                                long long num_queries, int indexing_xy, float* out, void* stream) {
   if (!grid || !query_points || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  GUARD(device_of(out));
   if (b < 0 || h < 2 || w < 2 || c <= 0 || num_queries < 0) return fail(SE3DS_ERR_BAD_SHAPE, "Grid must be at least 2x2 with shape (B,H,W,C)");
   const long long total = (long long)b * num_queries;
   if (total == 0) return SE3DS_OK;
@@ -864,6 +941,7 @@ int se3ds_interpolate_bilinear(const float* grid, const float* query_points, int
 int se3ds_proportion_invalid(const float* offsets, int p, const float* depth, int h, int w,
                              float distance_padding, float depth_scale, float* out, void* stream) {
   if (!offsets || !depth || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  GUARD(device_of(out));
   if (p < 0 || h <= 0 || w <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "depth_image must be (H, W)");
   if (p == 0) return SE3DS_OK;
   proportion_invalid_kernel<<<p, kThreads, 0, (cudaStream_t)stream>>>(offsets, depth, h, w, distance_padding, depth_scale, out);

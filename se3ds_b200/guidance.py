@@ -78,8 +78,9 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
     raw_features: proj_image holds the raw per-channel maxima instead of clip(x/255, 0, 1).
     tgt_rot: optional (N,P,3,3) rotations into the target camera frames (full SE(3) poses; the
       reference only translates, models/models.py:120-125): q = R (local + src - tgt).
-  Returns dict with proj_image (J,H,W,3), proj_depth (J,H,W,1), proj_mask (J,H,W,1),
-  blurred_mask (zeros, shares no memory), and optionally winner (J,H,W) int32, bin (4,).
+  Returns dict with proj_image (J,H,W,3), proj_depth (J,H,W,1), proj_mask (J,H,W,1), and optionally
+  winner (J,H,W) int32 and bin (5,) = (min depth, max R, G, B of the call's reject bin, depth of the
+  owner pixel's own winner) with export_bin (see se3ds_apply_bin).
   """
   rgb, depth, src_pos, tgt_pos = _prep(rgb, depth, src_pos, tgt_pos, True)
   n, s, h, w, _ = rgb.shape
@@ -90,7 +91,8 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
     out = {}
   def buf(name, shape, dtype=torch.float32):
     t = out.get(name)
-    if t is None or tuple(t.shape) != shape or t.dtype != dtype or t.device != dev:
+    # a caller's buffer is written through its data pointer as a dense tensor: it must be one
+    if t is None or tuple(t.shape) != shape or t.dtype != dtype or t.device != dev or not t.is_contiguous():
       t = out[name] = torch.empty(shape, dtype=dtype, device=dev)
     return t
   image = buf('proj_image', (j, h, w, 3))
@@ -156,14 +158,17 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
   return PreparedReprojection((rgb, depth, src_pos, tgt_pos), out, args, ws)
 
 
-def apply_bin(bin_values: torch.Tensor, out: Dict[str, torch.Tensor], depth_scale: float = constants.DEPTH_SCALE):
+def apply_bin(bin_values: torch.Tensor, out: Dict[str, torch.Tensor], depth_scale: float = constants.DEPTH_SCALE,
+              raw_features: bool = False):
   """Applies a reduced reject bin to pixel (0,0) of job 0 of `out` (see se3ds_apply_bin).
 
   bin_values: (5,) = reduced (min depth, max R, G, B) followed by the owner call's own fifth value
-  (depth of that pixel's own winner, as exported)."""
+  (depth of that pixel's own winner, as exported).  raw_features: `out` was produced with
+  raw_features=True (raw per-channel maxima instead of clip(x / 255, 0, 1))."""
   dev = out['proj_image'].device
   assert bin_values.numel() == 5, 'bin is (min depth, max R, max G, max B, own winner depth)'
   _lib.check(_lib.load().se3ds_apply_bin(_lib.ptr(bin_values.contiguous()), float(depth_scale),
+                                         _lib.FLAG_RAW_FEATURES if raw_features else 0,
                                          _lib.ptr(out['proj_image']), _lib.ptr(out['proj_depth']),
                                          _lib.ptr(out['proj_mask']), _lib.ptr(out.get('winner')),
                                          _lib.stream_handle(dev)))
@@ -191,7 +196,7 @@ def reproject_host(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.
   pin = torch.cuda.is_available()
   def buf(name, shape, dtype=torch.float32):
     t = out.get(name)
-    if t is None or tuple(t.shape) != shape or t.dtype != dtype or t.is_cuda:
+    if t is None or tuple(t.shape) != shape or t.dtype != dtype or t.is_cuda or not t.is_contiguous():
       t = out[name] = torch.empty(shape, dtype=dtype, pin_memory=pin)
     return t
   image = buf('proj_image', (j, h, w, 3))
@@ -199,7 +204,7 @@ def reproject_host(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.
   mask = buf('proj_mask', (j, h, w, 1))
   winner = buf('winner', (j, h, w), torch.int32) if return_winner else None
   flags = (_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0)
-  ws = workspace or _lib.default_workspace(torch.device('cuda', device))
+  ws = workspace or _lib.default_workspace(torch.device('cuda', device), role='host')
   _lib.check(_lib.load().se3ds_reproject_host(
       ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
       n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),

@@ -119,7 +119,10 @@ def reproject_sharded(rgb, depth, src_pos, tgt_pos, *, group=None, bin_mode: str
     if owner:
       # fifth value: depth of the owner pixel's own winner, from the call that rendered this rank's first job
       red = torch.cat([-red[:1], red[1:], bins[0][4:5].to(red.device)])
-      apply_bin_fn(red, local, depth_scale)
+      if kwargs.get('raw_features'):
+        apply_bin_fn(red, local, depth_scale, raw_features=True)
+      else:
+        apply_bin_fn(red, local, depth_scale)
 
   result = dict(local)
   result['job_range'] = (lo, hi)

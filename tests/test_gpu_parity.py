@@ -292,6 +292,44 @@ def test_certified_fast_projection(mods, h, dist):
       assert torch.equal(outs[0][k], outs[mode][k]), (mode, k)
 
 
+@pytest.mark.parametrize('h', [500, 512, 2048])
+def test_planted_column_borders(mods, h):
+  """Adversarial input for the column certificate: source and target position coincide
+  and the target frame is rotated about the vertical axis by (0.5 +- dx (1 + eps)) columns, so EVERY point
+  sits at a column border +- dx (1 + eps) -- right at the certification margin, for all depths.  Verify
+  mode: no certified point may differ from the canonical pixel; and the fast, canonical-only and verify
+  results are identical."""
+  g, lib = mods['g'], mods['lib']
+  w = 2 * h
+  inp = mods['synth'].make_inputs(1, 1, 1, h, seed=h + 3, dist='rand')
+  inp['tgt_pos'] = inp['src_pos'][:, 0].copy()
+  t = _cuda(inp)
+  ws = lib.Workspace(0)
+  dx = w * 1e-6
+  for eps in (-0.3, -0.02, 0.02, 0.3):
+    for sgn in (-1.0, 1.0):
+      alpha = 2.0 * np.pi * (0.5 + sgn * dx * (1.0 + eps)) / w
+      c, s_ = np.cos(alpha), np.sin(alpha)
+      rot = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]], np.float64).astype(F32)[None, None]
+      outs = {}
+      for mode in (0, 1, 2):
+        ws.projection_mode(mode)
+        o = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], return_winner=True, workspace=ws, tgt_rot=rot)
+        outs[mode] = {k: v.clone() for k, v in o.items()}
+      v = ws.verify_read()
+      assert v['wrong'] == 0, (eps, sgn, v)
+      assert v['max_dev_x'] < 0.53 * dx, (eps, sgn, v)
+      # the points really sit where they were planted: outside the margin they are certified, inside not
+      if eps >= 0.3:
+        assert v['certified'] > 0.9 * v['points'], (eps, sgn, v)
+      if eps <= -0.3:
+        assert v['certified'] < 0.1 * v['points'], (eps, sgn, v)
+      for mode in (1, 2):
+        for k in outs[0]:
+          assert torch.equal(outs[0][k], outs[mode][k]), (mode, k, eps, sgn)
+  ws.close()
+
+
 def test_non_finite_inputs_do_not_corrupt_memory(mods):
   """NaN / Inf depth and positions are outside the contract (the reference propagates NaN through
   `(depth * scale) * mask`), but they must never index out of bounds or poison other items."""

@@ -99,20 +99,24 @@ def host_table(h, margin_scale=1e-6):
 
 
 def kernel_rows(z, rad, h, sr, ss):
+  """canon_math.cuh project_pixel_fast, row part: q = z * rsqrt(r2) (the approximate reciprocal square root
+  of the squared radius doubles as 1 / rad; emulated as 1 / rad off by sr * 2 ulp), candidate row from the
+  polynomial in row units (coefficients times H / pi, as se3ds_geom.cu scales them), certified against the
+  cosine table."""
   rinv = ((F32(1) / rad).astype(F32) * F32(1 + sr * 2.0 ** -22)).astype(F32)
   q = (z * rinv).astype(F32)
   a = np.abs(q)
-  p = np.full_like(a, KCOEF[4])
-  for c in KCOEF[3::-1]:
+  ce = (KCOEF.astype(np.float64) * (h / np.pi)).astype(F32)  # lowest degree first here
+  p = np.full_like(a, ce[4])
+  for c in ce[3::-1]:
     p = (p * a + c).astype(F32)          # fma in the kernel: one rounding less, irrelevant at 1e-5
   with np.errstate(invalid='ignore'):
     sq = (np.sqrt((F32(1) - a).astype(F32)) * F32(1 + ss * 2.0 ** -22)).astype(F32)
-  r0 = (sq * p).astype(F32)
-  e = np.where(q < 0, (F32(np.pi) - r0).astype(F32), r0)
-  fy = (e * F32(h / np.pi)).astype(F32)
+  fy = (sq * p).astype(F32)
+  fy = np.where(q < 0, (F32(h) - fy).astype(F32), fy)
   with np.errstate(invalid='ignore'):
     row = np.where(np.isfinite(fy), np.floor(fy), 0).astype(np.int64)
-  row = np.clip(row, 0, h - 1)
+  row = np.where(row < 0, h - 1, np.minimum(row, h - 1))  # min((unsigned)floor, H - 1)
   lo, hi = host_table(h)
   certain = (q > lo[row]) & (q < hi[row])
   return row, certain

@@ -190,6 +190,13 @@ int se3ds_reproject_ring(se3ds_ws* ws, const void* rgb, int rgb_dtype, const flo
                          float* proj_image, float* proj_depth, float* proj_mask, int32_t* winner_out,
                          float* bin_out, void* stream);
 
+/* Feedback of a generated frame into the memory (trainers/gan_manager.py:539-542,
+ * utils/eval_metric.py:227-230): out = clip_by_value(cast(image * 255, int32), -1, 255), cast truncating
+ * toward zero.  image: n dense items of elems_per_item float32 (= H*W*3); item i is written to
+ * out + i * out_item_stride (int32 elements), e.g. frame slot s of an (N,S_cap,H,W,3) ring. */
+int se3ds_quantize_rgb(const float* image, int n, long long elems_per_item, int32_t* out, long long out_item_stride,
+                       void* stream);
+
 /* Multi-GPU support for the global reject bin.  When se3ds_reproject is given bin_out (device,
  * 5 floats) the call's reject bin is NOT applied to job 0's pixel (0,0) but exported as
  * (min depth or +inf, max R, max G, max B, depth of that pixel's own winner or +inf); ranks reduce

@@ -56,6 +56,7 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp],
     'se3ds_reproject_ring': [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp,
                              _vp, _vp, _vp, _vp, _vp],
+    'se3ds_quantize_rgb': [_vp, _i, _ll, _vp, _ll, _vp],
     'se3ds_apply_bin': [_vp, _f, _u, _vp, _vp, _vp, _vp, _vp],
     'se3ds_reproject_host': [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp,
                              _vp, _vp],

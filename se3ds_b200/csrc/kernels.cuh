@@ -1173,6 +1173,19 @@ __global__ void __launch_bounds__(kThreads) filtered_coords_kernel(const T* __re
   }
 }
 
+// Feedback of a generated frame into the memory (trainers/gan_manager.py:539-542,
+// utils/eval_metric.py:227-230): clip_by_value(cast(image * 255, int32), -1, 255); the cast truncates
+// toward zero (NaN / out of range -> INT_MIN as on x86, then clipped to -1).  The destination is a frame
+// slot of a ring: item n of the dense input goes to out + n * out_item_stride.
+__global__ void __launch_bounds__(kThreads) quantize_rgb_kernel(const float* __restrict__ image, long long per_item, int n,
+                                                               int* __restrict__ out, long long out_item_stride) {
+  const long long total = per_item * n;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const long long b = i / per_item, e = i - b * per_item;
+    out[b * out_item_stride + e] = min(max(cast_i32(__fmul_rn(image[i], 255.0f)), -1), 255);
+  }
+}
+
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -938,6 +938,18 @@ int se3ds_interpolate_bilinear(const float* grid, const float* query_points, int
   return launch_check("interpolate_bilinear_kernel");
 }
 
+int se3ds_quantize_rgb(const float* image, int n, long long elems_per_item, int32_t* out, long long out_item_stride,
+                       void* stream) {
+  if (!image || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (n < 0 || elems_per_item < 0 || out_item_stride < elems_per_item) return fail(SE3DS_ERR_BAD_SHAPE, "bad shape");
+  const long long total = (long long)n * elems_per_item;
+  if (total == 0) return SE3DS_OK;
+  GUARD(device_of(out));
+  quantize_rgb_kernel<<<(int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32), kThreads, 0, (cudaStream_t)stream>>>(
+      image, elems_per_item, n, out, out_item_stride);
+  return launch_check("quantize_rgb_kernel");
+}
+
 int se3ds_proportion_invalid(const float* offsets, int p, const float* depth, int h, int w,
                              float distance_padding, float depth_scale, float* out, void* stream) {
   if (!offsets || !depth || !out) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");

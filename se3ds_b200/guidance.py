@@ -12,7 +12,7 @@ keeping the S source frames (7 B per point) instead of a concatenated cloud (28 
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, List, NamedTuple, Optional
+from typing import Callable, Dict, List, NamedTuple, Optional
 
 import numpy as np
 import torch
@@ -65,7 +65,7 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
               filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
               export_bin: bool = False, out: Optional[Dict[str, torch.Tensor]] = None,
               workspace: Optional[_lib.Workspace] = None, tgt_rot=None, key64: bool = False,
-              raw_features: bool = False) -> Dict[str, torch.Tensor]:
+              raw_features: bool = False, frames: Optional[int] = None) -> Dict[str, torch.Tensor]:
   """Re-projects S source RGB-D panos per item onto P target poses per item.
 
   Args:
@@ -78,12 +78,17 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
     raw_features: proj_image holds the raw per-channel maxima instead of clip(x/255, 0, 1).
     tgt_rot: optional (N,P,3,3) rotations into the target camera frames (full SE(3) poses; the
       reference only translates, models/models.py:120-125): q = R (local + src - tgt).
+    frames: only the first `frames` of the S frame slots are in use (a partly filled frame ring, see
+      `FrameRing`); the tensors are read in place, nothing is sliced or copied.
   Returns dict with proj_image (J,H,W,3), proj_depth (J,H,W,1), proj_mask (J,H,W,1), and optionally
   winner (J,H,W) int32 and bin (5,) = (min depth, max R, G, B of the call's reject bin, depth of the
   owner pixel's own winner) with export_bin (see se3ds_apply_bin).
   """
   rgb, depth, src_pos, tgt_pos = _prep(rgb, depth, src_pos, tgt_pos, True)
-  n, s, h, w, _ = rgb.shape
+  n, s_cap, h, w, _ = rgb.shape
+  s = s_cap if frames is None else int(frames)
+  if not 0 < s <= s_cap:
+    raise ValueError(f'frames must be in [1, {s_cap}], got {frames}')
   p = tgt_pos.shape[1]
   j = n * p
   dev = rgb.device
@@ -106,9 +111,9 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
   if tgt_rot is not None:
     tgt_rot = _lib.require_cuda(torch.as_tensor(tgt_rot), 'tgt_rot').to(device=dev, dtype=torch.float32)
     tgt_rot = tgt_rot.reshape(n, p, 3, 3).contiguous()
-  _lib.check(_lib.load().se3ds_reproject_se3(
+  _lib.check(_lib.load().se3ds_reproject_ring(
       ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
-      _lib.ptr(tgt_rot), n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames),
+      _lib.ptr(tgt_rot), n, s, s_cap, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames),
       int(unproject_void), int(project_void), flags, _lib.ptr(image), _lib.ptr(pdepth), _lib.ptr(mask),
       _lib.ptr(winner), _lib.ptr(binb), _lib.stream_handle(dev)))
   return out
@@ -212,22 +217,184 @@ def reproject_host(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.
   return out
 
 
+class FrameRing(object):
+  """The memory of a trajectory as the frames that were observed: rgb (N,cap,H,W,3) uint8 / int32,
+  depth (N,cap,H,W) float32, position (N,cap,3) float32, `count` slots in use.
+
+  The reference keeps the concatenated cloud and re-concatenates it for every new frame
+  (models/models.py:239-245, trainers/gan_manager.py:550-551, utils/eval_metric.py:238-239: O(M) per
+  step, 28 B per point); here a frame is appended by writing its slot in place (7 - 16 B per point) and
+  `reproject(..., frames=count)` reads the ring where it lies.  The capacity doubles when it runs out.
+  Frames whose blurred rows are to be masked (`mask_pano`) are kept in front: `masked` is the prefix
+  count `reproject(mask_frames=...)` expects (the order of the frames changes no output)."""
+
+  def __init__(self, batch_size: int, height: int, device, dtype=torch.uint8, capacity: int = 4):
+    self.n, self.h, self.w = batch_size, height, 2 * height
+    self.device = torch.device(device)
+    self.count = 0
+    self.masked = 0
+    self._alloc(max(1, capacity), dtype)
+
+  def _alloc(self, capacity, dtype):
+    old = (self.rgb, self.depth, self.position) if self.count else None
+    self.rgb = torch.zeros((self.n, capacity, self.h, self.w, 3), dtype=dtype, device=self.device)
+    self.depth = torch.zeros((self.n, capacity, self.h, self.w), dtype=torch.float32, device=self.device)
+    self.position = torch.zeros((self.n, capacity, 3), dtype=torch.float32, device=self.device)
+    if old is not None:
+      c = self.count
+      self.rgb[:, :c] = old[0][:, :c].to(dtype)
+      self.depth[:, :c] = old[1][:, :c]
+      self.position[:, :c] = old[2][:, :c]
+
+  @property
+  def capacity(self):
+    return self.rgb.shape[1]
+
+  def _slot(self, masked: bool, dtype) -> int:
+    """Makes room for one more frame and returns the slot it goes to."""
+    want = torch.int32 if torch.int32 in (dtype, self.rgb.dtype) else torch.uint8
+    if self.count == self.capacity or want != self.rgb.dtype:
+      self._alloc(self.capacity * 2 if self.count == self.capacity else self.capacity, want)
+    slot = self.count
+    if masked and self.masked < self.count:  # keep the masked frames in front: move the first unmasked frame to the end
+      m = self.masked
+      self.rgb[:, slot] = self.rgb[:, m]
+      self.depth[:, slot] = self.depth[:, m]
+      self.position[:, slot] = self.position[:, m]
+      slot = m
+    self.count += 1
+    self.masked += int(masked)
+    return slot
+
+  def append(self, rgb: torch.Tensor, depth: torch.Tensor, position: torch.Tensor, masked: bool = False) -> int:
+    """rgb (N,H,W,3) uint8 / int32, depth (N,H,W[,1]) float32, position (N,3)."""
+    slot = self._slot(masked, rgb.dtype)
+    self.rgb[:, slot] = rgb.reshape(self.n, self.h, self.w, 3).to(self.rgb.dtype)
+    self.depth[:, slot] = depth.reshape(self.n, self.h, self.w)
+    self.position[:, slot] = position.reshape(self.n, 3)
+    return slot
+
+  def append_image(self, image: torch.Tensor, depth: torch.Tensor, position: torch.Tensor, masked: bool = False) -> int:
+    """image (N,H,W,3) float32 in [0,1] (a ground-truth or generated frame): stored as
+    clip(int32(image * 255), -1, 255) like the rollout loops do (trainers/gan_manager.py:539-542)."""
+    slot = self._slot(masked, torch.int32)
+    image = _lib.require_cuda(image, 'image').to(torch.float32)
+    per_item = self.h * self.w * 3
+    _lib.check(_lib.load().se3ds_quantize_rgb(_lib.ptr(image), self.n, per_item, _lib.ptr(self.rgb[:, slot]),
+                                              self.capacity * per_item, _lib.stream_handle(self.device)))
+    self.depth[:, slot] = depth.reshape(self.n, self.h, self.w)
+    self.position[:, slot] = position.reshape(self.n, 3)
+    return slot
+
+  def reproject(self, tgt_pos, **kwargs) -> Dict[str, torch.Tensor]:
+    if self.count == 0:
+      raise ValueError('the frame ring is empty')
+    return reproject(self.rgb, self.depth, self.position, tgt_pos, mask_frames=self.masked, frames=self.count, **kwargs)
+
+
+def empty_memory_guidance(n: int, height: int, device) -> Dict[str, torch.Tensor]:
+  """What the projection of an EMPTY memory yields (frame 0 of the rollout loops: tf.zeros((N,4,0))
+  clouds, trainers/gan_manager.py:462-463): depth = clip(depth_scale) / depth_scale = 1, features = the
+  output void class 0, mask 0."""
+  w = 2 * height
+  return dict(proj_image=torch.zeros((n, height, w, 3), device=device), proj_depth=torch.ones((n, height, w, 1), device=device),
+              proj_mask=torch.zeros((n, height, w, 1), device=device))
+
+
+def rollout(images, depths, positions, generator_fn: Callable, convention: Conventions = EVAL_METRIC,
+            seq_len: Optional[int] = None, feed_depth: bool = True, depth_scale: float = constants.DEPTH_SCALE,
+            workspace: Optional[_lib.Workspace] = None) -> Dict[str, list]:
+  """Drop-in for the trajectory roll-out loops of the reference: trainers/gan_manager.py:458-556
+  (`_get_image_grid`, mode "eval"; convention GAN_MANAGER) and utils/eval_metric.py:144-240
+  (`_get_generated_pool`; convention EVAL_METRIC).  Per frame t:
+
+    guidance(t)  = projection of the memory (frames 0 .. t-1) to positions[:, t]   -- empty at t = 0
+    generated, depth_out = generator_fn(generator_inputs, t)                        -- the caller's generator
+    memory      += frame 0: the ground-truth image with its blurred rows masked (-1), ground-truth depth
+                   frame t > 0: the GENERATED image, and depth_out if feed_depth and it is not None
+
+  images (N,T,H,W,3) float32 in [0,1], depths (N,T,H,W,1), positions (N,T,3).  generator_inputs holds
+  prev_image, proj_image, proj_mask, proj_depth, blurred_mask, first_frame, exactly as the reference
+  builds them; everything else the generator needs (one_hot_mask, dataset_type, ...) is the caller's
+  closure.  generator_fn returns (generated (N,H,W,3) float32, depth_out (N,H,W,1) or None); tensors
+  travel as torch CUDA tensors (DLPack-compatible, see INTEGRATION.md for the TF hand-off).
+  Returns per-frame lists: guidance (dicts), generated, depth (the depth that went into the memory)."""
+  images = _lib.require_cuda(torch.as_tensor(images), 'images').to(torch.float32)
+  depths = _lib.require_cuda(torch.as_tensor(depths), 'depths').to(torch.float32)
+  positions = _lib.require_cuda(torch.as_tensor(positions), 'positions').to(torch.float32)
+  if images.dim() != 5 or images.shape[-1] != 3:
+    raise ValueError(f'images should have shape (N, T, H, W, 3), got {tuple(images.shape)} instead.')
+  n, t_all, h, w, _ = images.shape
+  assert w == 2 * h, 'Expected equirectangular input images'
+  steps = t_all if seq_len is None else int(seq_len)
+  if not 0 < steps <= t_all:
+    raise ValueError(f'seq_len must be in [1, {t_all}], got {seq_len}')
+  depths = depths.reshape(n, t_all, h, w, 1)
+  positions = positions.reshape(n, t_all, 3)
+  dev = images.device
+  ring = FrameRing(n, h, dev, torch.int32, capacity=steps)
+  prev = torch.zeros_like(images[:, 0])
+  result = dict(guidance=[], generated=[], depth=[])
+  for t in range(steps):
+    pos = positions[:, t]
+    if ring.count == 0:
+      g = empty_memory_guidance(n, h, dev)
+    else:
+      g = ring.reproject(pos, depth_scale=depth_scale, workspace=workspace, **convention.kwargs())
+      g = {k: g[k] for k in ('proj_image', 'proj_depth', 'proj_mask')}
+    g['blurred_mask'] = torch.zeros_like(g['proj_depth'])
+    first = torch.ones((n,), device=dev) if t == 0 else torch.zeros((n,), device=dev)
+    inputs = dict(prev_image=prev, proj_image=g['proj_image'], proj_mask=g['proj_mask'], proj_depth=g['proj_depth'],
+                  blurred_mask=g['blurred_mask'], first_frame=first)
+    generated, depth_out = generator_fn(inputs, t)
+    generated = _lib.require_cuda(torch.as_tensor(generated), 'generated').to(torch.float32)
+    depth_t = depths[:, t]
+    if t == 0:  # ground truth, blurred rows masked (the ring masks its first `masked` frames in the kernel)
+      prev = images[:, 0]
+      ring.append_image(images[:, 0].contiguous(), depth_t, pos, masked=True)
+    else:       # feed the generated frame back
+      prev = generated
+      if feed_depth and depth_out is not None:
+        depth_t = _lib.require_cuda(torch.as_tensor(depth_out), 'depth_out').to(torch.float32).reshape(n, h, w, 1)
+      ring.append_image(generated.contiguous(), depth_t, pos)
+    result['guidance'].append(g)
+    result['generated'].append(generated)
+    result['depth'].append(depth_t)
+  result['memory'] = ring
+  return result
+
+
 class MemoryState(NamedTuple):
-  """Frame-ring memory: the S observations instead of the reference's concatenated cloud
-  (models/models.py:77-87 keeps coords (N,4,M) / feats / rgb_coords / rgb)."""
-  rgb: List[torch.Tensor]        # each (N,H,W,3) uint8 or int32
-  semantic: List[torch.Tensor]   # each (N,H,W,1) uint8
-  depth: List[torch.Tensor]      # each (N,H,W) float32
-  position: List[torch.Tensor]   # each (N,3) float32
-  masked: List[bool]
+  """The reference's memory tuple (models/models.py:77-87): coords (N,4,M) float32 + feats (N,M,1)
+  uint8 = the semantic cloud, rgb_coords (N,4,M') float32 + rgb (N,M',3) int32 = the RGB cloud."""
+  coords: torch.Tensor
+  feats: torch.Tensor
+  rgb_coords: torch.Tensor
+  rgb: torch.Tensor
+
+
+class FrameState(NamedTuple):
+  """Native state of GuidanceMemory: the observed frames (see FrameRing)."""
+  rgb: torch.Tensor         # (N,S,H,W,3) uint8 or int32
+  semantic: torch.Tensor    # (N,S,H,W,1) uint8
+  depth: torch.Tensor       # (N,S,H,W) float32
+  position: torch.Tensor    # (N,S,3) float32
+  masked: int               # the first `masked` frames get mask_pano(., 0.125, -1)
 
 
 class GuidanceMemory(object):
   """The guidance half of the reference's SE3DSModel (models/models.py:90-321).
 
   add_to_memory(...) stores an observation; __call__(position) returns the generator inputs
-  `proj_image`, `proj_depth`, `proj_mask`, `blurred_mask` (+ `proj_semantic`) for a target
-  position.  The generator itself (models/models.py:323-366) is out of scope.
+  `proj_image`, `proj_depth`, `proj_mask`, `blurred_mask` (+ `proj_semantic`) for a target position --
+  or for P positions at once (the VLN pose sweep, inference/perturbation_utils.py + notebook cell 13):
+  position (P,3) gives P guidance sets from one call.  The generator itself
+  (models/models.py:323-366) is out of scope.
+
+  Natively the memory is a FrameRing.  `to_reference_state()` materialises the reference's
+  MemoryState; `from_reference_state()` accepts one (e.g. a state saved by reference code): such a
+  memory is a bare point cloud, so from then on the object works on clouds like the reference does
+  (unproject + concatenate in add_to_memory, project_feats_to_equirectangular in __call__).
   """
 
   def __init__(self, image_height: int, depth_scale: float = constants.DEPTH_SCALE, batch_size: int = 1,
@@ -247,18 +414,71 @@ class GuidanceMemory(object):
                        f'{self.batch_size}, got {input_batch_size} instead.')
 
   def reset_memory(self):
-    self._memory = MemoryState([], [], [], [], [])
+    self._ring: Optional[FrameRing] = None
+    self._semantic: Optional[torch.Tensor] = None  # (N,cap,H,W,1) uint8, slots as in the ring
+    self._cloud: Optional[MemoryState] = None      # cloud mode (after from_reference_state)
 
-  def get_memory_state(self) -> MemoryState:
-    m = self._memory
-    return MemoryState([t.clone() for t in m.rgb], [t.clone() for t in m.semantic],
-                       [t.clone() for t in m.depth], [t.clone() for t in m.position], list(m.masked))
+  # -- native state ---------------------------------------------------------------------------
+  def get_memory_state(self) -> FrameState:
+    if self._cloud is not None:
+      raise ValueError('the memory holds a reference point cloud: use to_reference_state()')
+    r = self._ring
+    if r is None:
+      raise ValueError('memory is empty: call add_to_memory first')
+    c = r.count
+    return FrameState(r.rgb[:, :c].clone(), self._semantic[:, :c].clone(), r.depth[:, :c].clone(),
+                      r.position[:, :c].clone(), r.masked)
 
-  def set_memory_state(self, state: MemoryState):
-    self._memory = MemoryState([t.clone() for t in state.rgb], [t.clone() for t in state.semantic],
-                               [t.clone() for t in state.depth], [t.clone() for t in state.position],
-                               list(state.masked))
+  def set_memory_state(self, state: FrameState):
+    self.reset_memory()
+    n, s = state.rgb.shape[:2]
+    self._check_batch_size(n)
+    r = self._ring = FrameRing(n, self.height, state.rgb.device, state.rgb.dtype, capacity=s)
+    r.rgb.copy_(state.rgb); r.depth.copy_(state.depth); r.position.copy_(state.position)
+    r.count, r.masked = s, int(state.masked)
+    self._semantic = state.semantic.clone()
 
+  # -- reference state (models/models.py:77-87,136-152) -----------------------------------------
+  def _frame_cloud(self, feats, depth, pos, void):
+    xyz1, f = pano_utils.equirectangular_to_pointcloud(feats, depth, void, self.depth_scale)
+    return xyz1 + torch.cat([pos, torch.zeros_like(pos[:, :1])], dim=1)[:, :, None], f
+
+  def to_reference_state(self) -> MemoryState:
+    """The memory as the reference holds it: masking, unprojection, offset and compaction of every
+    frame, concatenated (models/models.py:211-245).  Points appear frame by frame in ring order."""
+    if self._cloud is not None:
+      return MemoryState(*[t.clone() for t in self._cloud])
+    r = self._ring
+    dev = torch.device('cuda', torch.cuda.current_device()) if r is None else r.device
+    coords, feats, rgb_coords, rgbs = [], [], [], []
+    for i in range(0 if r is None else r.count):
+      rgb = r.rgb[:, i].to(torch.int32)
+      if i < r.masked:
+        rgb = pano_utils.mask_pano(rgb, masked_region_value=constants.INVALID_RGB_VALUE)
+      pos = r.position[:, i]
+      xyz1, f = self._frame_cloud(rgb, r.depth[:, i], pos, constants.INVALID_RGB_VALUE)
+      valid = (f != constants.INVALID_RGB_VALUE).any(dim=0).any(dim=-1)
+      rgb_coords.append(xyz1[:, :, valid]); rgbs.append(f[:, valid])
+      sxyz1, sf = self._frame_cloud(self._semantic[:, i], r.depth[:, i], pos, constants.INVALID_SEM_VALUE)
+      svalid = (sf != constants.INVALID_SEM_VALUE).any(dim=0).any(dim=-1)
+      coords.append(sxyz1[:, :, svalid]); feats.append(sf[:, svalid])
+    n = self.batch_size
+    if not coords:
+      return MemoryState(torch.zeros((n, 4, 0), device=dev), torch.zeros((n, 0, 1), dtype=torch.uint8, device=dev),
+                         torch.zeros((n, 4, 0), device=dev), torch.zeros((n, 0, 3), dtype=torch.int32, device=dev))
+    return MemoryState(torch.cat(coords, dim=2), torch.cat(feats, dim=1), torch.cat(rgb_coords, dim=2), torch.cat(rgbs, dim=1))
+
+  def from_reference_state(self, state: MemoryState):
+    """Adopts a reference MemoryState (coords, feats, rgb_coords, rgb).  A cloud cannot be turned back
+    into frames, so the memory switches to cloud mode (see the class docstring)."""
+    self._check_batch_size(state.coords.shape[0])
+    self.reset_memory()
+    self._cloud = MemoryState(_lib.require_cuda(torch.as_tensor(state.coords), 'coords').to(torch.float32),
+                              _lib.require_cuda(torch.as_tensor(state.feats), 'feats').to(torch.uint8),
+                              _lib.require_cuda(torch.as_tensor(state.rgb_coords), 'rgb_coords').to(torch.float32),
+                              _lib.require_cuda(torch.as_tensor(state.rgb), 'rgb').to(torch.int32))
+
+  # -- the SE3DSModel interface -------------------------------------------------------------------
   def add_to_memory(self, pano_rgb, pano_semantic, pano_depth, position, mask_blurred=True):
     """models/models.py:180-245 (the cloud is not built; the frame is kept)."""
     pano_semantic = _lib.require_cuda(torch.as_tensor(pano_semantic), 'pano_semantic')
@@ -266,52 +486,78 @@ class GuidanceMemory(object):
     pano_rgb = _lib.require_cuda(torch.as_tensor(pano_rgb), 'pano_rgb')
     assert pano_rgb.dtype in (torch.uint8, torch.int32)
     assert pano_semantic.dtype in (torch.uint8, torch.int32)
-    m = self._memory
-    m.rgb.append(pano_rgb)
-    m.semantic.append(pano_semantic.to(torch.uint8))
-    m.depth.append(_lib.require_cuda(torch.as_tensor(pano_depth), 'pano_depth').to(torch.float32))
-    m.position.append(_lib.require_cuda(torch.as_tensor(position), 'position').to(torch.float32).reshape(-1, 3))
-    m.masked.append(bool(mask_blurred))
+    n = self.batch_size
+    pano_depth = _lib.require_cuda(torch.as_tensor(pano_depth), 'pano_depth').to(torch.float32).reshape(n, self.height, self.width)
+    position = _lib.require_cuda(torch.as_tensor(position), 'position').to(torch.float32).reshape(-1, 3)
+    sem = pano_semantic.to(torch.uint8).reshape(n, self.height, self.width, 1)
+    if self._cloud is not None:  # cloud mode: what the reference does
+      rgb = pano_rgb.to(torch.int32)
+      if mask_blurred:
+        rgb = pano_utils.mask_pano(rgb, masked_region_value=constants.INVALID_RGB_VALUE)
+      xyz1, f = self._frame_cloud(rgb, pano_depth, position, constants.INVALID_RGB_VALUE)
+      valid = (f != constants.INVALID_RGB_VALUE).any(dim=0).any(dim=-1)
+      sxyz1, sf = self._frame_cloud(sem, pano_depth, position, constants.INVALID_SEM_VALUE)
+      svalid = (sf != constants.INVALID_SEM_VALUE).any(dim=0).any(dim=-1)
+      c = self._cloud
+      self._cloud = MemoryState(torch.cat([c.coords, sxyz1[:, :, svalid]], dim=2), torch.cat([c.feats, sf[:, svalid]], dim=1),
+                                torch.cat([c.rgb_coords, xyz1[:, :, valid]], dim=2), torch.cat([c.rgb, f[:, valid]], dim=1))
+      return
+    if self._ring is None:
+      self._ring = FrameRing(n, self.height, pano_rgb.device, pano_rgb.dtype)
+      self._semantic = torch.zeros((n, self._ring.capacity, self.height, self.width, 1), dtype=torch.uint8, device=pano_rgb.device)
+    r = self._ring
+    count = r.count
+    slot = r.append(pano_rgb, pano_depth, position, masked=bool(mask_blurred))
+    if self._semantic.shape[1] != r.capacity:
+      grown = torch.zeros((n, r.capacity, self.height, self.width, 1), dtype=torch.uint8, device=r.device)
+      grown[:, :self._semantic.shape[1]] = self._semantic
+      self._semantic = grown
+    if slot != count:  # the ring moved the frame of `slot` to the end to keep the masked frames in front
+      self._semantic[:, count] = self._semantic[:, slot]
+    self._semantic[:, slot] = sem
 
   def __call__(self, position) -> Dict[str, torch.Tensor]:
-    """The guidance half of models/models.py:247-321 for one (N,3) target position."""
-    position = _lib.require_cuda(torch.as_tensor(position), 'position').to(torch.float32).reshape(-1, 3)
-    self._check_batch_size(position.shape[0])
-    m = self._memory
-    if not m.rgb:
+    """The guidance half of models/models.py:247-321 for one target position (N,3) -- or for P target
+    positions (P,3) / (N,P,3) at once: the leading dimension of every output is then N * P."""
+    position = _lib.require_cuda(torch.as_tensor(position), 'position').to(torch.float32)
+    position = position.reshape(self.batch_size, -1, 3)
+    if self._cloud is not None:
+      return self._call_cloud(position)
+    r = self._ring
+    if r is None or r.count == 0:
       raise ValueError('memory is empty: call add_to_memory first')
-    # frames that want the blurred rows masked go first (mask_frames is a prefix count)
-    order = sorted(range(len(m.rgb)), key=lambda i: not m.masked[i])
-    dt = torch.int32 if any(t.dtype == torch.int32 for t in m.rgb) else torch.uint8
-    rgb = torch.stack([m.rgb[i].to(dt) for i in order], dim=1)
-    depth = torch.stack([m.depth[i] for i in order], dim=1)
-    src = torch.stack([m.position[i] for i in order], dim=1)
-    out = reproject(rgb, depth, src, position, self.depth_scale, mask_frames=sum(m.masked),
-                    unproject_void=SE3DS_MODEL.unproject_void, project_void=SE3DS_MODEL.project_void,
-                    filter_void=True, per_job_bin=True)
+    out = r.reproject(position, depth_scale=self.depth_scale, unproject_void=SE3DS_MODEL.unproject_void,
+                      project_void=SE3DS_MODEL.project_void, filter_void=True, per_job_bin=True)
     out['blurred_mask'] = torch.zeros_like(out['proj_mask'])
     if self.project_semantic:
       out['proj_semantic'] = self._project_semantic(position)
     return out
 
+  def _call_cloud(self, position):
+    """models/models.py:270-321 on the stored cloud, one reference call per target position."""
+    c = self._cloud
+    outs = []
+    for p in range(position.shape[1]):
+      pos = position[:, p]
+      rel = c.rgb_coords - torch.cat([pos, torch.zeros_like(pos[:, :1])], dim=1)[:, :, None]
+      d, f = pano_utils.project_feats_to_equirectangular(c.rgb, rel, self.height, self.width, constants.INVALID_RGB_VALUE,
+                                                         self.depth_scale)
+      mask = ((d > 0) & (d < 1) & (f != constants.INVALID_RGB_VALUE).all(dim=-1)).to(torch.float32)[..., None]
+      o = dict(proj_image=torch.clamp(f / 255, 0, 1), proj_depth=d[..., None], proj_mask=mask)
+      if self.project_semantic:
+        srel = c.coords - torch.cat([pos, torch.zeros_like(pos[:, :1])], dim=1)[:, :, None]
+        _, sf = pano_utils.project_feats_to_equirectangular(c.feats, srel, self.height, self.width,
+                                                            constants.INVALID_SEM_VALUE, self.depth_scale)
+        o['proj_semantic'] = sf[..., 0].to(torch.uint8)
+      outs.append(o)
+    out = {k: torch.cat([o[k] for o in outs], dim=0) for k in outs[0]}
+    out['blurred_mask'] = torch.zeros_like(out['proj_mask'])
+    return out
+
   def rgb_cloud(self):
-    """Materialises the RGB memory as the reference keeps it: rgb_coords (N,4,M'), rgb (N,M',3) int32
-    after masking, unprojection, offset and compaction (models/models.py:211-245)."""
-    m = self._memory
-    coords, feats = [], []
-    for rgb, depth, pos, masked in zip(m.rgb, m.depth, m.position, m.masked):
-      rgb = rgb.to(torch.int32)
-      if masked:
-        rgb = pano_utils.mask_pano(rgb, masked_region_value=constants.INVALID_RGB_VALUE)
-      xyz1, f = pano_utils.equirectangular_to_pointcloud(rgb, depth, constants.INVALID_RGB_VALUE, self.depth_scale)
-      xyz1 = xyz1 + torch.cat([pos, torch.zeros_like(pos[:, :1])], dim=1)[:, :, None]
-      valid = (f != constants.INVALID_RGB_VALUE).any(dim=0).any(dim=-1)
-      coords.append(xyz1[:, :, valid])
-      feats.append(f[:, valid])
-    if not coords:
-      dev = torch.device('cuda', torch.cuda.current_device())
-      return torch.zeros((self.batch_size, 4, 0), device=dev), torch.zeros((self.batch_size, 0, 3), dtype=torch.int32, device=dev)
-    return torch.cat(coords, dim=2), torch.cat(feats, dim=1)
+    """rgb_coords (N,4,M'), rgb (N,M',3) int32 of `to_reference_state()`."""
+    st = self.to_reference_state()
+    return st.rgb_coords, st.rgb
 
   def write_memory_as_pointcloud(self, filename):
     """Writes memory at batch position 0 to an ASCII .ply file, byte for byte in the reference's
@@ -339,12 +585,9 @@ class GuidanceMemory(object):
     replicated into the three feature channels (void class 0 on both sides, compaction on, no row
     mask), so validity, the near-min set and the per-channel maximum are those of the scalar
     feature, and channel 0 of the raw features is proj_semantic."""
-    m = self._memory
-    sem = torch.stack([t.reshape(t.shape[0], self.height, self.width) for t in m.semantic], dim=1)  # (N,S,H,W)
-    sem3 = sem[..., None].expand(-1, -1, -1, -1, 3).contiguous()
-    depth = torch.stack(m.depth, dim=1)
-    src = torch.stack(m.position, dim=1)
-    out = reproject(sem3, depth, src, position, self.depth_scale, mask_frames=0,
+    r = self._ring
+    sem3 = self._semantic[..., 0][..., None].expand(-1, -1, -1, -1, 3).contiguous()  # (N,cap,H,W,3)
+    out = reproject(sem3, r.depth, r.position, position, self.depth_scale, mask_frames=0, frames=r.count,
                     unproject_void=constants.INVALID_SEM_VALUE, project_void=constants.INVALID_SEM_VALUE,
                     filter_void=True, per_job_bin=True, raw_features=True)
     return out['proj_image'][..., 0].to(torch.uint8)

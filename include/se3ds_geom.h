@@ -68,6 +68,14 @@ typedef enum { SE3DS_U8 = 0, SE3DS_I32 = 1, SE3DS_F32 = 2 } se3ds_dtype;
                                        clip(x / 255, 0, 1): e.g. semantic class ids replicated into
                                        the three channels (models/models.py:276-278). */
 
+#define SE3DS_FLAG_COMPACT_OUT 32u /* compact guidance: proj_image points to a UINT8 (J,H,W,3) plane that
+                                     receives the per-channel maxima clamped to [0, 255], proj_depth stays
+                                     float32, proj_mask may be NULL and is not written -- 7 instead of 20
+                                     bytes per pixel (device->host copies, the NCCL all-gather).  Nothing
+                                     is lost: clip(x / 255, 0, 1) is a function of that byte and
+                                     mask = 0 < depth < 1; se3ds_expand_guidance restores the float32
+                                     tensors bit for bit.  Not combinable with SE3DS_FLAG_RAW_FEATURES. */
+
 int se3ds_version(void);
 const char* se3ds_status_string(int status);
 const char* se3ds_last_error(void);
@@ -113,12 +121,19 @@ int se3ds_plan_chunks(size_t l2_chunk_bytes, int lanes, long long min_points_per
                       int n, int s, int p, int h, int w, long long plan[5]);
 int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_dev[2]);
 
-/* Measurement hooks (bench.py): with profiling enabled se3ds_reproject brackets its three kernel
- * classes with cudaEvents on the caller's stream.  se3ds_ws_profile_read synchronises, returns the
- * accumulated device milliseconds of {splat_depth, splat_feat, resolve} since the last read and the
- * number of kernels this workspace has launched so far (counted always, profiling or not). */
-int se3ds_ws_profile(se3ds_ws* ws, int enable);
+/* Measurement hooks (bench.py).  mode 1: se3ds_reproject brackets its three kernel classes with cudaEvents
+ * on the caller's stream (programmatic dependent launch is switched off meanwhile, so the kernels run
+ * back to back without overlap); se3ds_ws_profile_read synchronises, returns the accumulated device
+ * milliseconds of {splat_depth, splat_feat, resolve} since the last read and the number of kernels this
+ * workspace has launched so far (counted always, profiling or not).
+ * mode 2: the pipeline runs as it does in production (programmatic dependent launch on, lanes on); every
+ * block stamps %globaltimer when it ends, and a kernel's share of the step is its last stamp minus the
+ * last stamp of the kernel launched before it.  se3ds_ws_profile_read_stamps synchronises and returns the
+ * summed shares in milliseconds over `chunks` job chunks (the first chunk after enabling has no
+ * predecessor and is skipped; at most 4096 chunks are recorded per read).  mode 0: off. */
+int se3ds_ws_profile(se3ds_ws* ws, int mode);
 int se3ds_ws_profile_read(se3ds_ws* ws, float ms[3], unsigned long long* launches);
+int se3ds_ws_profile_read_stamps(se3ds_ws* ws, double ms[3], long long* chunks);
 
 /* utils/pano_utils.py:245-265  mask_pano(pano, proportion, masked_region_value).
  * pano/out (N,H,W,C) of `dtype`; rows r < int(H*p) or r > H - int(H*p) become the value. */
@@ -197,6 +212,15 @@ int se3ds_reproject_ring(se3ds_ws* ws, const void* rgb, int rgb_dtype, const flo
 int se3ds_quantize_rgb(const float* image, int n, long long elems_per_item, int32_t* out, long long out_item_stride,
                        void* stream);
 
+/* Compact guidance (SE3DS_FLAG_COMPACT_OUT) -> the float32 tensors of models/models.py:282-293:
+ * proj_image (njobs,px_per_job,3) = clip(rgb_u8 / 255, 0, 1), proj_mask (njobs,px_per_job) = 0 < depth < 1.
+ * Bit-identical to what se3ds_reproject writes without the flag.  job_map (device, njobs int32, or NULL =
+ * identity): source job s is written as destination job job_map[s] -- a gather buffer that arrived piece by
+ * piece (se3ds_b200/parallel.py) is put into job order on the way; depth_out (or NULL) receives the depth
+ * plane in destination order. */
+int se3ds_expand_guidance(const uint8_t* rgb_u8, const float* proj_depth, long long njobs, long long px_per_job,
+                          const int32_t* job_map, float* proj_image, float* depth_out, float* proj_mask, void* stream);
+
 /* Multi-GPU support for the global reject bin.  When se3ds_reproject is given bin_out (device,
  * 5 floats) the call's reject bin is NOT applied to job 0's pixel (0,0) but exported as
  * (min depth or +inf, max R, max G, max B, depth of that pixel's own winner or +inf); ranks reduce
@@ -204,7 +228,8 @@ int se3ds_quantize_rgb(const float* image, int n, long long elems_per_item, int3
  * result with se3ds_apply_bin.  clip() and the divisions are monotone, so patching the finished
  * outputs is bit-identical to the single-call result; `winner` (job 0's winner plane, may be NULL)
  * gets -1 at the pixel when a rejected point is nearer than its own winner.  `flags`: pass
- * SE3DS_FLAG_RAW_FEATURES when the outputs were produced with it (raw maxima, no x / 255). */
+ * SE3DS_FLAG_RAW_FEATURES / SE3DS_FLAG_COMPACT_OUT when the outputs were produced with them (proj_mask
+ * may then be NULL). */
 int se3ds_apply_bin(const float* bin, float depth_scale, unsigned flags, float* proj_image, float* proj_depth,
                     float* proj_mask, int32_t* winner, void* stream);
 

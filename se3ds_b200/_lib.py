@@ -23,6 +23,7 @@ FLAG_BIN_PER_JOB = 2
 FLAG_KEY64 = 4
 FLAG_INPUTS_READY = 8
 FLAG_RAW_FEATURES = 16
+FLAG_COMPACT_OUT = 32
 
 _DTYPES = {torch.uint8: U8, torch.int32: I32, torch.float32: F32}
 
@@ -47,6 +48,7 @@ SIGNATURES = {
     'se3ds_ws_verify_read': [_vp, _c.POINTER(_c.c_ulonglong * 3), _c.POINTER(_f * 2)],
     'se3ds_ws_profile': [_vp, _i],
     'se3ds_ws_profile_read': [_vp, _c.POINTER(_f * 3), _c.POINTER(_c.c_ulonglong)],
+    'se3ds_ws_profile_read_stamps': [_vp, _c.POINTER(_d * 3), _c.POINTER(_ll)],
     'se3ds_mask_pano': [_vp, _i, _i, _i, _i, _i, _d, _d, _vp, _vp],
     'se3ds_unproject_equirect': [_vp, _vp, _i, _vp, _i, _i, _i, _i, _d, _f, _vp, _vp, _i, _vp],
     'se3ds_project_cloud': [_vp, _vp, _vp, _i, _i, _ll, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp],
@@ -56,6 +58,7 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp],
     'se3ds_reproject_ring': [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp,
                              _vp, _vp, _vp, _vp, _vp],
+    'se3ds_expand_guidance': [_vp, _vp, _ll, _ll, _vp, _vp, _vp, _vp, _vp],
     'se3ds_quantize_rgb': [_vp, _i, _ll, _vp, _ll, _vp],
     'se3ds_apply_bin': [_vp, _f, _u, _vp, _vp, _vp, _vp, _vp],
     'se3ds_reproject_host': [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp,
@@ -177,8 +180,16 @@ class Workspace:
     check(load().se3ds_ws_verify_read(self.handle, ctypes.byref(c), ctypes.byref(d)))
     return dict(points=c[0], certified=c[1], wrong=c[2], max_dev_x=d[0], max_dev_y=d[1])
 
-  def profile(self, enable: bool):
-    check(load().se3ds_ws_profile(self.handle, int(enable)))
+  def profile(self, mode):
+    """0 / False off, 1 / True cudaEvents between the launches (no overlap), 2 end-of-kernel stamps."""
+    check(load().se3ds_ws_profile(self.handle, int(mode)))
+
+  def profile_read_stamps(self):
+    """-> ((ms K2, K3, K4) summed shares of the pipelined step, chunks counted) since profile(2)."""
+    ms = (ctypes.c_double * 3)()
+    n = ctypes.c_longlong()
+    check(load().se3ds_ws_profile_read_stamps(self.handle, ctypes.byref(ms), ctypes.byref(n)))
+    return tuple(ms), n.value
 
   def profile_read(self):
     """-> ((ms_splat_depth, ms_splat_feat, ms_resolve) since the last read, kernels launched so far)."""

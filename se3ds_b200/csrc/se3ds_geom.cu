@@ -76,12 +76,21 @@ int device_of(const void* p) {
   return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
 }
 
+// Tile table of one job (kernels.cuh, "Work distribution of K2 / K3"): (frame << 16 | row) of its S * H
+// source rows, unmasked rows first.
+struct TileTabEntry {
+  int s, h, mask_frames, mh;
+  int heavy, light;
+  int* dev;
+};
+
 struct TableEntry {
   int h, w;
   float margin;  // certification margin scale the row table was built for
   float* dev;    // sin/cos of the row elevations (2 H), of the column headings (2 W), row certification table (2 H)
 };
 
+constexpr size_t kMaxStampChunks = 4096;
 constexpr size_t kDefaultMaxBytes = (size_t)2 << 30;
 constexpr size_t kDefaultChunkBytes = (size_t)112 << 20;
 
@@ -90,8 +99,9 @@ constexpr size_t kDefaultChunkBytes = (size_t)112 << 20;
 struct se3ds_ws {
   int device = 0, sm_count = 148;
   size_t max_bytes = kDefaultMaxBytes, chunk_bytes = kDefaultChunkBytes;
-  DevBuf zbuf, zbuf32, fbuf, scf, scr, bins, cbin;
+  DevBuf zbuf, zbuf32, fbuf, scf, scr, scc, bins, cbin;  // scc: colour scratch
   std::vector<TableEntry> tables;
+  std::vector<TileTabEntry> tile_tabs;
   bool dirty = false;  // a pass was enqueued but its resolve (which re-arms) was not
   // staging of the host-buffer entry point
   DevBuf s_rgb, s_depth, s_src, s_tgt, s_img, s_dep, s_msk, s_win;
@@ -99,6 +109,7 @@ struct se3ds_ws {
   std::vector<cudaEvent_t> pipe_ev;  // 2 per batch item: inputs on device, outputs computed
   float margin_scale = 1.0e-6f;  // certification margin: dx = W * scale, dy = 2 * H * scale pixels
   bool pdl = true;  // programmatic dependent launch between the fused kernels
+  bool discard_scratch = true;  // K3 drops consumed scratch lines from L2 without write-back
   // concurrent chunk lanes: lane 0 is the caller's stream, lanes 1.. are these (fork / join by events)
   static constexpr int kMaxLanes = 4;
   int lanes = 2;
@@ -109,23 +120,25 @@ struct se3ds_ws {
   int proj_mode = 1;  // 0 canonical only, 1 certified fast path (default), 2 verify
   DevBuf dbg;
   // measurement hooks
-  bool profile = false;
+  int profile = 0;  // 0 off, 1 cudaEvents between the launches (no PDL), 2 end-of-kernel stamps (pipeline as it runs)
   std::vector<cudaEvent_t> ev_pool;  // groups of 4 events per profiled chunk
   size_t ev_used = 0;
+  DevBuf stamps;  // mode 2: kMaxStampChunks x 3 end-of-kernel %globaltimer values
+  size_t stamp_used = 0;
   unsigned long long launches = 0;
 };
 
 namespace {
 
 size_t ws_total(const se3ds_ws* ws) {
-  size_t t = ws->zbuf.cap + ws->zbuf32.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->bins.cap + ws->cbin.cap +
+  size_t t = ws->zbuf.cap + ws->zbuf32.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->scc.cap + ws->bins.cap + ws->cbin.cap +
              ws->s_rgb.cap + ws->s_depth.cap + ws->s_src.cap + ws->s_tgt.cap + ws->s_img.cap +
              ws->s_dep.cap + ws->s_msk.cap + ws->s_win.cap;
   for (const auto& e : ws->tables) t += (size_t)(4 * e.h + 2 * e.w) * sizeof(float);
   return t;
 }
 
-// Job chunking: a chunk's z-buffer + feature buffer + scratch (16 + 8 S bytes per target pixel) should
+// Job chunking: a chunk's z-buffer + feature buffer + scratch (16 + 12 S bytes per target pixel) should
 // sit in L2.  The chunks are dealt round-robin to `lanes` concurrent streams which share that budget; a
 // call that cannot give every lane min_lane_chunks chunks of at least min_lane_points source points
 // uses fewer lanes (measured: c3 -4.4 %, c4 -8 % with two lanes; c2 would split into one chunk per lane
@@ -138,7 +151,7 @@ struct ChunkPlan {
 void plan_chunks(size_t budget_bytes, int lanes, long long min_lane_points, int min_lane_chunks, bool per_item, int n,
                  int s, int p, int h, int w, ChunkPlan* out) {
   const long long hw = (long long)h * w, J = (long long)n * p;
-  const size_t job_bytes = (size_t)hw * (16 + 8 * (size_t)s);
+  const size_t job_bytes = (size_t)hw * (16 + 12 * (size_t)s);
   lanes = std::max(1, lanes);
   int items_per_chunk = 1, PC = 1;
   long long chunk_jobs = 1, nchunks_total = 1;
@@ -242,6 +255,30 @@ int get_tables(se3ds_ws* ws, int h, int w, cudaStream_t stream, const float** ou
   return SE3DS_OK;
 }
 
+int get_tile_tab(se3ds_ws* ws, int s, int h, int mask_frames, int mh, cudaStream_t stream, const TileTabEntry** out) {
+  mask_frames = std::min(std::max(mask_frames, 0), s);
+  for (const auto& e : ws->tile_tabs)
+    if (e.s == s && e.h == h && e.mask_frames == mask_frames && e.mh == mh) { *out = &e; return SE3DS_OK; }
+  std::vector<int> heavy, light;
+  for (int f = 0; f < s; ++f)
+    for (int r = 0; r < h; ++r) {
+      const bool masked = f < mask_frames && (r < mh || r > h - mh);  // row_masked() of kernels.cuh
+      (masked ? light : heavy).push_back((f << 16) | r);
+    }
+  TileTabEntry e{s, h, mask_frames, mh, (int)heavy.size(), (int)light.size(), nullptr};
+  heavy.insert(heavy.end(), light.begin(), light.end());
+  CU(cudaMalloc(&e.dev, heavy.size() * sizeof(int)));
+  CU(cudaMemcpyAsync(e.dev, heavy.data(), heavy.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+  CU(cudaStreamSynchronize(stream));  // host vector goes out of scope
+  if (ws->tile_tabs.size() >= 16) {
+    cudaFree(ws->tile_tabs.front().dev);
+    ws->tile_tabs.erase(ws->tile_tabs.begin());
+  }
+  ws->tile_tabs.push_back(e);
+  *out = &ws->tile_tabs.back();
+  return SE3DS_OK;
+}
+
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 int launch_check(const char* what) {
@@ -266,15 +303,18 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-// K2 grid: a block walks several rows (kernels.cuh); rows_per_block is sized so that the grid is about
-// one resident wave of kK2BlocksPerSM blocks per SM, capped so that short panos still spread over the SMs.
-constexpr int kK2BlocksPerSM = 8;
-int k2_row_groups(const se3ds_ws* ws, int gx, int h, int job_frames) {
-  const long long row_blocks = (long long)gx * h * job_frames;
-  const long long resident = (long long)ws->sm_count * kK2BlocksPerSM;
-  long long rpb = (row_blocks + resident - 1) / resident;
-  rpb = std::max<long long>(1, std::min<long long>(rpb, 32));
-  return (int)((h + rpb - 1) / rpb);
+// K2 / K3 grids: (at most) one resident wave of persistent warps; a warp serves one (column quarter, job) and
+// shares that job's rows round-robin with the other warps of the pair (kernels.cuh).  The number of warps
+// per pair is chosen so that the expensive row class divides evenly: with k = ceil(rows / resident warps
+// per pair) rows per warp, ceil(rows / k) warps.
+constexpr int kK2BlocksPerSM = 8, kK3BlocksPerSM = 8;
+int tile_grid(const se3ds_ws* ws, int w, int jobs, long long heavy_rows, long long all_rows, int blocks_per_sm) {
+  const long long pairs = (long long)((w + 127) / 128) * jobs;
+  const long long rows = heavy_rows > 0 ? heavy_rows : all_rows;  // per pair
+  const long long max_warps = std::max<long long>(1, (long long)ws->sm_count * blocks_per_sm * kWarps / pairs);
+  const long long k = std::max<long long>(1, (rows + max_warps - 1) / max_warps);
+  const long long warps = std::max<long long>(1, (rows + k - 1) / k);
+  return (int)((warps * pairs + kWarps - 1) / kWarps);
 }
 
 template <typename RGB_T, int PPT, bool KEY64>
@@ -282,10 +322,13 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
   const int gx = (q.W + kThreads * PPT - 1) / (kThreads * PPT);
   const int jobs = nitems * q.PC;
   const dim3 grid(gx, q.H, jobs * q.S), block(kThreads);
-  const int gx2 = (q.W + kThreads * 4 - 1) / (kThreads * 4);
-  const dim3 grid2(gx2, k2_row_groups(ws, gx2, q.H, jobs * q.S), jobs * q.S);
+  FusedParams qs = q;  // + this chunk's job count (+ stamp slots in profile mode 2)
+  qs.chunk_jobs = jobs;
+  const long long th = q.tab_heavy, ta = th + q.tab_light;
+  const dim3 grid2(tile_grid(ws, q.W, jobs, th, ta, kK2BlocksPerSM)), grid3(tile_grid(ws, q.W, jobs, th, q.uv <= 0 ? th : ta, kK3BlocksPerSM));
   cudaEvent_t* ev = nullptr;
-  if (ws->profile) {
+  if (ws->profile == 2 && ws->stamp_used < kMaxStampChunks) qs.stamps = (unsigned long long*)ws->stamps.p + 3 * ws->stamp_used++;
+  if (ws->profile == 1) {
     if (ws->ev_used + 4 > ws->ev_pool.size())
       for (int i = 0; i < 4; ++i) {
         cudaEvent_t e;
@@ -296,24 +339,30 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
     ws->ev_used += 4;
     CU(cudaEventRecord(ev[0], st));
   }
-  // FAST feature mode: see splat_depth_kernel
-  const bool fast = std::is_same<RGB_T, uint8_t>::value && q.pv == -1 &&
-                    (!(q.flags & SE3DS_FLAG_FILTER_VOID) || q.uv == -1);
+  // how K2 decides the fate of a point (see splat_depth_kernel): 2 PLAIN, 1 FAST, 0 generic
+  const bool u8 = std::is_same<RGB_T, uint8_t>::value;
+  const int feat = (u8 && q.pv == -1 && q.uv == -1) ? 2
+                   : (u8 && q.pv == -1 && !(q.flags & SE3DS_FLAG_FILTER_VOID)) ? 1 : 0;
   const int proj = ws->proj_mode;
-  const bool pdl = ws->pdl && !ws->profile;
+  const bool pdl = ws->pdl && ws->profile != 1;
   constexpr bool VEC = PPT == 4;
 #define LAUNCH_K2(F, P)                                                                                         \
   do {                                                                                                         \
-    if (q.tgt_rot) CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, true>, grid2, block, st, pdl, q)); \
-    else CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, false>, grid2, block, st, pdl, q));          \
+    if (q.tgt_rot) CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, true>, grid2, block, st, pdl, qs)); \
+    else CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, false>, grid2, block, st, pdl, qs));          \
   } while (0)
-  if (fast) { if (proj == 0) LAUNCH_K2(true, 0); else if (proj == 1) LAUNCH_K2(true, 1); else LAUNCH_K2(true, 2); }
-  else { if (proj == 0) LAUNCH_K2(false, 0); else if (proj == 1) LAUNCH_K2(false, 1); else LAUNCH_K2(false, 2); }
+#define LAUNCH_K2_F(F)                                                                          \
+  do {                                                                                          \
+    if (proj == 0) LAUNCH_K2(F, 0); else if (proj == 1) LAUNCH_K2(F, 1); else LAUNCH_K2(F, 2); \
+  } while (0)
+  if (feat == 2) LAUNCH_K2_F(2); else if (feat == 1) LAUNCH_K2_F(1); else LAUNCH_K2_F(0);
+#undef LAUNCH_K2_F
 #undef LAUNCH_K2
   if (ev) CU(cudaEventRecord(ev[1], st));
-  CU(launch_pdl(splat_feat_kernel<RGB_T, PPT, KEY64>, grid, block, st, pdl, q));
+  CU(launch_pdl(splat_feat_kernel<RGB_T, KEY64>, grid3, block, st, pdl, qs));
   if (ev) CU(cudaEventRecord(ev[2], st));
-  CU(launch_pdl(resolve_kernel<PPT, KEY64>, dim3(gx, q.H, jobs), block, st, pdl, q));
+  if (q.flags & SE3DS_FLAG_COMPACT_OUT) CU(launch_pdl(resolve_kernel<PPT, KEY64, true>, dim3(gx, q.H, jobs), block, st, pdl, qs));
+  else CU(launch_pdl(resolve_kernel<PPT, KEY64, false>, dim3(gx, q.H, jobs), block, st, pdl, qs));
   if (ev) CU(cudaEventRecord(ev[3], st));
   ws->launches += 3;
   return launch_check("fused reprojection kernels");
@@ -370,10 +419,11 @@ int se3ds_ws_destroy(se3ds_ws* ws) {
   if (!ws) return SE3DS_OK;
   DeviceGuard guard_(ws->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&ws->zbuf, &ws->zbuf32, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->dbg, &ws->s_rgb, &ws->s_depth,
+  for (DevBuf* b : {&ws->zbuf, &ws->zbuf32, &ws->fbuf, &ws->scf, &ws->scr, &ws->scc, &ws->bins, &ws->cbin, &ws->dbg, &ws->stamps, &ws->s_rgb, &ws->s_depth,
                     &ws->s_src, &ws->s_tgt, &ws->s_img, &ws->s_dep, &ws->s_msk, &ws->s_win})
     if (b->p) cudaFree(b->p);
   for (auto& e : ws->tables) cudaFree(e.dev);
+  for (auto& e : ws->tile_tabs) cudaFree(e.dev);
   for (auto& e : ws->ev_pool) cudaEventDestroy(e);
   for (auto& e : ws->pipe_ev) cudaEventDestroy(e);
   for (cudaStream_t st : {ws->hstream, ws->h2d_stream, ws->d2h_stream, ws->lane_stream[0], ws->lane_stream[1], ws->lane_stream[2]})
@@ -443,10 +493,41 @@ int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_d
   return SE3DS_OK;
 }
 
-int se3ds_ws_profile(se3ds_ws* ws, int enable) {
-  if (!ws) return fail(SE3DS_ERR_BAD_ARG, "NULL workspace");
-  ws->profile = enable != 0;
+int se3ds_ws_profile(se3ds_ws* ws, int mode) {
+  if (!ws || mode < 0 || mode > 2) return fail(SE3DS_ERR_BAD_ARG, "mode must be 0, 1 or 2");
+  ws->profile = mode;
   ws->ev_used = 0;
+  ws->stamp_used = 0;
+  if (mode == 2) {
+    GUARD(ws->device);
+    CU(cudaDeviceSynchronize());
+    if (int rc = grow(ws->stamps, kMaxStampChunks * 3 * sizeof(unsigned long long), -1, nullptr)) return rc;
+    CU(cudaMemset(ws->stamps.p, 0, kMaxStampChunks * 3 * sizeof(unsigned long long)));
+  }
+  return SE3DS_OK;
+}
+
+int se3ds_ws_profile_read_stamps(se3ds_ws* ws, double ms[3], long long* chunks) {
+  if (!ws || !ms || !chunks) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  ms[0] = ms[1] = ms[2] = 0.0;
+  *chunks = 0;
+  if (!ws->stamps.p || ws->stamp_used < 2) return SE3DS_OK;
+  GUARD(ws->device);
+  CU(cudaDeviceSynchronize());
+  std::vector<unsigned long long> h(3 * ws->stamp_used);
+  CU(cudaMemcpy(h.data(), ws->stamps.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CU(cudaMemset(ws->stamps.p, 0, kMaxStampChunks * 3 * sizeof(unsigned long long)));
+  // chunk i: K2 ends at h[3i], K3 at h[3i+1], K4 at h[3i+2]; a kernel's share = its end - the previous end.
+  // The first chunk has no predecessor: it is skipped.
+  for (size_t i = 1; i < ws->stamp_used; ++i) {
+    const unsigned long long prev = h[3 * i - 1];
+    if (!prev || !h[3 * i] || !h[3 * i + 1] || !h[3 * i + 2]) continue;
+    ms[0] += (double)((long long)(h[3 * i] - prev)) * 1e-6;
+    ms[1] += (double)((long long)(h[3 * i + 1] - h[3 * i])) * 1e-6;
+    ms[2] += (double)((long long)(h[3 * i + 2] - h[3 * i + 1])) * 1e-6;
+    ++*chunks;
+  }
+  ws->stamp_used = 0;
   return SE3DS_OK;
 }
 
@@ -595,19 +676,22 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
                    float depth_scale, double mask_proportion, int mask_frames, int unproject_void,
                    int project_void, unsigned flags, float* proj_image, float* proj_depth,
                    float* proj_mask, int32_t* winner_out, float* bin_out, void* stream, const HostPipe* pipe) {
-  if (!ws || !rgb || !depth || !src_pos || !tgt_pos || !proj_image || !proj_depth || !proj_mask)
+  const bool compact = flags & SE3DS_FLAG_COMPACT_OUT;
+  if (!ws || !rgb || !depth || !src_pos || !tgt_pos || !proj_image || !proj_depth || (!proj_mask && !compact))
     return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (compact && (flags & SE3DS_FLAG_RAW_FEATURES)) return fail(SE3DS_ERR_BAD_ARG, "COMPACT_OUT and RAW_FEATURES exclude each other");
   if (n < 0 || s <= 0 || p <= 0 || h <= 0) return fail(SE3DS_ERR_BAD_SHAPE, "rgb must be (N,S,H,W,3), tgt_pos (N,P,3)");
   if (s_capacity == 0) s_capacity = s;
   if (s_capacity < s) return fail(SE3DS_ERR_BAD_SHAPE, "frame capacity %d < frames %d", s_capacity, s);
   if (w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "Expected equirectangular input images");
+  if (w > 128 * kMaxXq) return fail(SE3DS_ERR_BAD_SHAPE, "W > %d is not supported", 128 * kMaxXq);
   if (rgb_dtype != SE3DS_U8 && rgb_dtype != SE3DS_I32) return fail(SE3DS_ERR_BAD_DTYPE, "rgb must be uint8 or int32");
   if (unproject_void < -1 || unproject_void > 255 || project_void < -1 || project_void > 255)
     return fail(SE3DS_ERR_BAD_ARG, "void classes must be in [-1, 255]");
   const long long hw = (long long)h * w;
   if (hw > (long long)kScPixMask || (long long)s * hw >= (1ll << 31)) return fail(SE3DS_ERR_BAD_SHAPE, "S*H*W too large");
   if ((long long)n * (s_capacity ? s_capacity : s) >= (1ll << 31) / 3) return fail(SE3DS_ERR_BAD_SHAPE, "N*S too large");
-  if (s > 65535 || h > 65535) return fail(SE3DS_ERR_BAD_SHAPE, "S or H too large");
+  if (s > 32767 || h > 65535) return fail(SE3DS_ERR_BAD_SHAPE, "S or H too large");
   if (n == 0) return SE3DS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   GUARD(ws->device);
@@ -615,7 +699,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   // job chunking and lanes (plan_chunks below)
   const long long J = (long long)n * p;
   ChunkPlan plan;
-  plan_chunks(std::min(ws->chunk_bytes, ws->max_bytes), (pipe || ws->profile) ? 1 : ws->lanes, ws->min_lane_points,
+  plan_chunks(std::min(ws->chunk_bytes, ws->max_bytes), (pipe || ws->profile == 1) ? 1 : ws->lanes, ws->min_lane_points,
               ws->min_lane_chunks, pipe != nullptr, n, s, p, h, w, &plan);
   const int lanes = plan.lanes, items_per_chunk = plan.items_per_chunk, PC = plan.poses_per_chunk;
   const long long chunk_jobs = plan.chunk_jobs, nchunks_total = plan.nchunks;
@@ -632,14 +716,20 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   if (int rc = grow(ws->fbuf, lanes * lane_px * 8, 0, st)) return rc;
   if (int rc = grow(ws->scf, lanes * lane_px * s * 4, -1, st)) return rc;
   if (int rc = grow(ws->scr, lanes * lane_px * s * 4, -1, st)) return rc;
+  if (rgb_dtype == SE3DS_U8)
+    if (int rc = grow(ws->scc, lanes * lane_px * s * 4, -1, st)) return rc;
   if (int rc = grow(ws->bins, (size_t)(per_job ? J : 1) * sizeof(Bin), 0, st)) return rc;
   const float* tab = nullptr;
   if (int rc = get_tables(ws, h, w, st, &tab)) return rc;
+  const TileTabEntry* tt = nullptr;
+  if (int rc = get_tile_tab(ws, s, h, mask_frames, (int)(h * mask_proportion), st, &tt)) return rc;
 
   FusedParams q{};
+  q.tile_tab = tt->dev; q.tab_heavy = tt->heavy; q.tab_light = tt->light;
   q.rgb = rgb; q.depth = depth; q.src_pos = src_pos; q.tgt_pos = tgt_pos; q.tgt_rot = tgt_rot; q.tab = tab;
   q.zbuf = (unsigned long long*)ws->zbuf.p; q.zbuf32 = (uint32_t*)ws->zbuf32.p; q.fbuf = (uint2*)ws->fbuf.p;
-  q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.bins = (Bin*)ws->bins.p;
+  q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.sc_rgb = (uint32_t*)ws->scc.p; q.bins = (Bin*)ws->bins.p;
+  q.discard_scratch = ws->discard_scratch ? 1 : 0;
   q.out_image = proj_image; q.out_depth = proj_depth; q.out_mask = proj_mask; q.out_winner = winner_out;
   q.N = n; q.S = s; q.SC = s_capacity; q.P = p; q.H = h; q.W = w; q.HW = (int)hw;
   q.mh = (int)(h * mask_proportion);
@@ -669,7 +759,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   }
   // the 4-pixels-per-thread kernels use 128 / 256-bit accesses on the inputs AND on every output plane
   const bool vec = (w % 4 == 0) && aligned(depth, 16) && aligned(rgb, rgb_dtype == SE3DS_U8 ? 4 : 16) &&
-                   aligned(proj_image, 16) && aligned(proj_depth, 16) && aligned(proj_mask, 16) &&
+                   aligned(proj_image, compact ? 4 : 16) && aligned(proj_depth, 16) && (compact || aligned(proj_mask, 16)) &&
                    (!winner_out || aligned(winner_out, 16));
 
   ws->dirty = true;
@@ -698,6 +788,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
       q.fbuf = (uint2*)ws->fbuf.p + lane * lane_px;
       q.sc_flat = (uint32_t*)ws->scf.p + lane * lane_px * s;
       q.sc_rad = (float*)ws->scr.p + lane * lane_px * s;
+      q.sc_rgb = (uint32_t*)ws->scc.p + lane * lane_px * s;
       const int rc = rgb_dtype == SE3DS_U8 ? run_chunk<uint8_t>(ws, q, nitems, vec, key64, lane_st[lane])
                                            : run_chunk<int>(ws, q, nitems, vec, key64, lane_st[lane]);
       if (rc) { join(); return rc; }
@@ -706,9 +797,13 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
       CU(cudaEventRecord(pipe->out_ready[n0], st));
       CU(cudaStreamWaitEvent(pipe->d2h, pipe->out_ready[n0], 0));
       const size_t o = (size_t)n0 * p * hw, cnt = (size_t)p * hw;
-      CU(cudaMemcpyAsync(pipe->image_host + o * 3, proj_image + o * 3, cnt * 12, cudaMemcpyDeviceToHost, pipe->d2h));
+      if (compact) {
+        CU(cudaMemcpyAsync((uint8_t*)pipe->image_host + o * 3, (const uint8_t*)proj_image + o * 3, cnt * 3, cudaMemcpyDeviceToHost, pipe->d2h));
+      } else {
+        CU(cudaMemcpyAsync(pipe->image_host + o * 3, proj_image + o * 3, cnt * 12, cudaMemcpyDeviceToHost, pipe->d2h));
+        CU(cudaMemcpyAsync(pipe->mask_host + o, proj_mask + o, cnt * 4, cudaMemcpyDeviceToHost, pipe->d2h));
+      }
       CU(cudaMemcpyAsync(pipe->depth_host + o, proj_depth + o, cnt * 4, cudaMemcpyDeviceToHost, pipe->d2h));
-      CU(cudaMemcpyAsync(pipe->mask_host + o, proj_mask + o, cnt * 4, cudaMemcpyDeviceToHost, pipe->d2h));
       if (pipe->winner_host)
         CU(cudaMemcpyAsync(pipe->winner_host + o, winner_out + o, cnt * 4, cudaMemcpyDeviceToHost, pipe->d2h));
     }
@@ -725,9 +820,9 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
     if (pipe) {  // job 0's pixel (0,0) changed after it was shipped: send its 20 bytes again
       CU(cudaEventRecord(pipe->out_ready[0], st));
       CU(cudaStreamWaitEvent(pipe->d2h, pipe->out_ready[0], 0));
-      CU(cudaMemcpyAsync(pipe->image_host, proj_image, 12, cudaMemcpyDeviceToHost, pipe->d2h));
+      CU(cudaMemcpyAsync(pipe->image_host, proj_image, compact ? 3 : 12, cudaMemcpyDeviceToHost, pipe->d2h));
       CU(cudaMemcpyAsync(pipe->depth_host, proj_depth, 4, cudaMemcpyDeviceToHost, pipe->d2h));
-      CU(cudaMemcpyAsync(pipe->mask_host, proj_mask, 4, cudaMemcpyDeviceToHost, pipe->d2h));
+      if (!compact) CU(cudaMemcpyAsync(pipe->mask_host, proj_mask, 4, cudaMemcpyDeviceToHost, pipe->d2h));
       if (pipe->winner_host) CU(cudaMemcpyAsync(pipe->winner_host, winner_out, 4, cudaMemcpyDeviceToHost, pipe->d2h));
     }
   }
@@ -777,8 +872,9 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
                          int unproject_void, int project_void, unsigned flags,
                          float* proj_image_host, float* proj_depth_host, float* proj_mask_host,
                          int32_t* winner_out_host) {
+  const bool compact = flags & SE3DS_FLAG_COMPACT_OUT;
   if (!ws || !rgb_host || !depth_host || !src_pos_host || !tgt_pos_host || !proj_image_host ||
-      !proj_depth_host || !proj_mask_host)
+      !proj_depth_host || (!proj_mask_host && !compact))
     return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
   if (n <= 0 || s <= 0 || p <= 0 || h <= 0 || w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "bad shape");
   if (rgb_dtype != SE3DS_U8 && rgb_dtype != SE3DS_I32) return fail(SE3DS_ERR_BAD_DTYPE, "rgb must be uint8 or int32");
@@ -797,9 +893,10 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
   if (int rc = grow(ws->s_depth, npts * 4, -1, st)) return rc;
   if (int rc = grow(ws->s_src, (size_t)n * s * 12, -1, st)) return rc;
   if (int rc = grow(ws->s_tgt, (size_t)n * p * 12, -1, st)) return rc;
-  if (int rc = grow(ws->s_img, npix * 12, -1, st)) return rc;
+  if (int rc = grow(ws->s_img, npix * (compact ? 3 : 12), -1, st)) return rc;
   if (int rc = grow(ws->s_dep, npix * 4, -1, st)) return rc;
-  if (int rc = grow(ws->s_msk, npix * 4, -1, st)) return rc;
+  if (!compact)
+    if (int rc = grow(ws->s_msk, npix * 4, -1, st)) return rc;
   if (winner_out_host)
     if (int rc = grow(ws->s_win, npix * 4, -1, st)) return rc;
   // upload stream: poses first, then item by item (an event per item lets item i compute while
@@ -828,9 +925,9 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
 
 int se3ds_apply_bin(const float* bin, float depth_scale, unsigned flags, float* proj_image, float* proj_depth,
                     float* proj_mask, int32_t* winner, void* stream) {
-  if (!bin || !proj_image || !proj_depth || !proj_mask) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (!bin || !proj_image || !proj_depth || (!proj_mask && !(flags & SE3DS_FLAG_COMPACT_OUT))) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
   GUARD(device_of(proj_image));
-  apply_bin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bin, depth_scale, (flags & SE3DS_FLAG_RAW_FEATURES) != 0, proj_image, proj_depth, proj_mask, winner);
+  apply_bin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bin, depth_scale, (flags & SE3DS_FLAG_RAW_FEATURES) != 0, (flags & SE3DS_FLAG_COMPACT_OUT) != 0, proj_image, proj_depth, proj_mask, winner);
   return launch_check("apply_bin_kernel");
 }
 
@@ -936,6 +1033,20 @@ int se3ds_interpolate_bilinear(const float* grid, const float* query_points, int
   interpolate_bilinear_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(grid, query_points, b, h, w, c, num_queries,
                                                                             indexing_xy, out);
   return launch_check("interpolate_bilinear_kernel");
+}
+
+int se3ds_expand_guidance(const uint8_t* rgb_u8, const float* proj_depth, long long njobs, long long px_per_job,
+                          const int32_t* job_map, float* proj_image, float* depth_out, float* proj_mask, void* stream) {
+  if (!rgb_u8 || !proj_depth || !proj_image || !proj_mask) return fail(SE3DS_ERR_BAD_ARG, "NULL argument");
+  if (njobs < 0 || px_per_job < 0) return fail(SE3DS_ERR_BAD_SHAPE, "negative size");
+  if (njobs == 0 || px_per_job == 0) return SE3DS_OK;
+  GUARD(device_of(proj_image));
+  const int vec = px_per_job % 4 == 0 && aligned(rgb_u8, 4) && aligned(proj_depth, 16) && aligned(proj_image, 16) &&
+                  aligned(proj_mask, 16) && (!depth_out || aligned(depth_out, 16));
+  const long long work = njobs * (vec ? px_per_job / 4 : px_per_job);
+  expand_guidance_kernel<<<(int)std::min<long long>((work + kThreads - 1) / kThreads, 148 * 16), kThreads, 0, (cudaStream_t)stream>>>(
+      rgb_u8, proj_depth, njobs, px_per_job, vec, job_map, proj_image, depth_out, proj_mask);
+  return launch_check("expand_guidance_kernel");
 }
 
 int se3ds_quantize_rgb(const float* image, int n, long long elems_per_item, int32_t* out, long long out_item_stride,

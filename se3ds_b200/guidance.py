@@ -65,7 +65,7 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
               filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
               export_bin: bool = False, out: Optional[Dict[str, torch.Tensor]] = None,
               workspace: Optional[_lib.Workspace] = None, tgt_rot=None, key64: bool = False,
-              raw_features: bool = False, frames: Optional[int] = None) -> Dict[str, torch.Tensor]:
+              raw_features: bool = False, frames: Optional[int] = None, compact: bool = False) -> Dict[str, torch.Tensor]:
   """Re-projects S source RGB-D panos per item onto P target poses per item.
 
   Args:
@@ -80,6 +80,9 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
       reference only translates, models/models.py:120-125): q = R (local + src - tgt).
     frames: only the first `frames` of the S frame slots are in use (a partly filled frame ring, see
       `FrameRing`); the tensors are read in place, nothing is sliced or copied.
+    compact: the compact guidance format (SE3DS_FLAG_COMPACT_OUT): the dict holds proj_rgb_u8 (J,H,W,3) uint8
+      and proj_depth instead of the three float32 tensors -- 7 instead of 20 bytes per pixel for copies and
+      collectives; `expand_guidance` restores proj_image / proj_mask bit for bit.
   Returns dict with proj_image (J,H,W,3), proj_depth (J,H,W,1), proj_mask (J,H,W,1), and optionally
   winner (J,H,W) int32 and bin (5,) = (min depth, max R, G, B of the call's reject bin, depth of the
   owner pixel's own winner) with export_bin (see se3ds_apply_bin).
@@ -100,13 +103,16 @@ def reproject(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH
     if t is None or tuple(t.shape) != shape or t.dtype != dtype or t.device != dev or not t.is_contiguous():
       t = out[name] = torch.empty(shape, dtype=dtype, device=dev)
     return t
-  image = buf('proj_image', (j, h, w, 3))
+  if compact:
+    image, mask = buf('proj_rgb_u8', (j, h, w, 3), torch.uint8), None
+  else:
+    image, mask = buf('proj_image', (j, h, w, 3)), buf('proj_mask', (j, h, w, 1))
   pdepth = buf('proj_depth', (j, h, w, 1))
-  mask = buf('proj_mask', (j, h, w, 1))
   winner = buf('winner', (j, h, w), torch.int32) if return_winner else None
   binb = buf('bin', (5,)) if export_bin else None
   flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
-           (_lib.FLAG_KEY64 if key64 else 0) | (_lib.FLAG_RAW_FEATURES if raw_features else 0))
+           (_lib.FLAG_KEY64 if key64 else 0) | (_lib.FLAG_RAW_FEATURES if raw_features else 0) |
+           (_lib.FLAG_COMPACT_OUT if compact else 0))
   ws = workspace or _lib.default_workspace(dev)
   if tgt_rot is not None:
     tgt_rot = _lib.require_cuda(torch.as_tensor(tgt_rot), 'tgt_rot').to(device=dev, dtype=torch.float32)
@@ -127,7 +133,7 @@ class PreparedReprojection:
   def __init__(self, tensors, out, args, ws):
     self.tensors, self.out, self._args, self.workspace = tensors, out, args, ws
     self._fn = _lib.load().se3ds_reproject
-    self.device = out['proj_image'].device
+    self.device = out['proj_depth'].device
 
   def run(self, stream=None):
     st = _lib.stream_handle(self.device) if stream is None else ctypes.c_void_p(stream)
@@ -140,7 +146,7 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
             unproject_void: int = constants.INVALID_RGB_VALUE, project_void: int = constants.INVALID_RGB_VALUE,
             filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
             workspace: Optional[_lib.Workspace] = None, key64: bool = False,
-            inputs_ready: bool = False) -> PreparedReprojection:
+            inputs_ready: bool = False, compact: bool = False) -> PreparedReprojection:
   """Same arguments as `reproject`; allocates the outputs once and returns a PreparedReprojection.
   inputs_ready=True promises that the input tensors are not written by whatever kernel runs right
   before each `run()` on the stream (SE3DS_FLAG_INPUTS_READY)."""
@@ -149,18 +155,46 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
   p = tgt_pos.shape[1]
   j = n * p
   dev = rgb.device
-  out = dict(proj_image=torch.empty((j, h, w, 3), device=dev), proj_depth=torch.empty((j, h, w, 1), device=dev),
-             proj_mask=torch.empty((j, h, w, 1), device=dev))
+  if compact:
+    out = dict(proj_rgb_u8=torch.empty((j, h, w, 3), dtype=torch.uint8, device=dev), proj_depth=torch.empty((j, h, w, 1), device=dev))
+  else:
+    out = dict(proj_image=torch.empty((j, h, w, 3), device=dev), proj_depth=torch.empty((j, h, w, 1), device=dev),
+               proj_mask=torch.empty((j, h, w, 1), device=dev))
   if return_winner:
     out['winner'] = torch.empty((j, h, w), dtype=torch.int32, device=dev)
   flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
-           (_lib.FLAG_KEY64 if key64 else 0) | (_lib.FLAG_INPUTS_READY if inputs_ready else 0))
+           (_lib.FLAG_KEY64 if key64 else 0) | (_lib.FLAG_INPUTS_READY if inputs_ready else 0) |
+           (_lib.FLAG_COMPACT_OUT if compact else 0))
   ws = workspace or _lib.default_workspace(dev)
   args = (ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
           n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),
-          int(project_void), flags, _lib.ptr(out['proj_image']), _lib.ptr(out['proj_depth']),
-          _lib.ptr(out['proj_mask']), _lib.ptr(out.get('winner')), None)
+          int(project_void), flags, _lib.ptr(out['proj_rgb_u8'] if compact else out['proj_image']), _lib.ptr(out['proj_depth']),
+          _lib.ptr(out.get('proj_mask')), _lib.ptr(out.get('winner')), None)
   return PreparedReprojection((rgb, depth, src_pos, tgt_pos), out, args, ws)
+
+
+def expand_guidance(out: Dict[str, torch.Tensor], job_map: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+  """Compact guidance (proj_rgb_u8 + proj_depth) -> adds the float32 proj_image (J,H,W,3) and proj_mask
+  (J,H,W,1) of the reference contract, bit-identical to a non-compact `reproject` (se3ds_expand_guidance).
+  job_map (J,) int32: source job s becomes job job_map[s] of the outputs (proj_depth is re-ordered too)."""
+  rgb8, depth = out['proj_rgb_u8'].contiguous(), out['proj_depth'].contiguous()
+  j, h, w, _ = rgb8.shape
+  dev = rgb8.device
+  image = torch.empty((j, h, w, 3), dtype=torch.float32, device=dev)
+  mask = torch.empty((j, h, w, 1), dtype=torch.float32, device=dev)
+  depth_out = None
+  if job_map is not None:
+    job_map = _lib.require_cuda(torch.as_tensor(job_map), 'job_map').to(device=dev, dtype=torch.int32).contiguous()
+    depth_out = torch.empty_like(depth)
+  _lib.check(_lib.load().se3ds_expand_guidance(_lib.ptr(rgb8), _lib.ptr(depth), j, h * w, _lib.ptr(job_map), _lib.ptr(image),
+                                               _lib.ptr(depth_out), _lib.ptr(mask), _lib.stream_handle(dev)))
+  out['proj_image'], out['proj_mask'] = image, mask
+  if depth_out is not None:
+    out['proj_depth'] = depth_out
+    if 'winner' in out:
+      out['winner'] = torch.empty_like(out['winner']).index_copy_(0, job_map.long(), out['winner'])
+    out['proj_rgb_u8'] = torch.empty_like(rgb8).index_copy_(0, job_map.long(), rgb8)
+  return out
 
 
 def apply_bin(bin_values: torch.Tensor, out: Dict[str, torch.Tensor], depth_scale: float = constants.DEPTH_SCALE,
@@ -170,12 +204,13 @@ def apply_bin(bin_values: torch.Tensor, out: Dict[str, torch.Tensor], depth_scal
   bin_values: (5,) = reduced (min depth, max R, G, B) followed by the owner call's own fifth value
   (depth of that pixel's own winner, as exported).  raw_features: `out` was produced with
   raw_features=True (raw per-channel maxima instead of clip(x / 255, 0, 1))."""
-  dev = out['proj_image'].device
+  dev = out['proj_depth'].device
   assert bin_values.numel() == 5, 'bin is (min depth, max R, max G, max B, own winner depth)'
-  _lib.check(_lib.load().se3ds_apply_bin(_lib.ptr(bin_values.contiguous()), float(depth_scale),
-                                         _lib.FLAG_RAW_FEATURES if raw_features else 0,
-                                         _lib.ptr(out['proj_image']), _lib.ptr(out['proj_depth']),
-                                         _lib.ptr(out['proj_mask']), _lib.ptr(out.get('winner')),
+  compact = 'proj_rgb_u8' in out and 'proj_image' not in out
+  flags = (_lib.FLAG_RAW_FEATURES if raw_features else 0) | (_lib.FLAG_COMPACT_OUT if compact else 0)
+  _lib.check(_lib.load().se3ds_apply_bin(_lib.ptr(bin_values.contiguous()), float(depth_scale), flags,
+                                         _lib.ptr(out['proj_rgb_u8'] if compact else out['proj_image']), _lib.ptr(out['proj_depth']),
+                                         _lib.ptr(out.get('proj_mask')), _lib.ptr(out.get('winner')),
                                          _lib.stream_handle(dev)))
 
 
@@ -185,7 +220,7 @@ def reproject_host(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.
                    project_void: int = constants.INVALID_RGB_VALUE, filter_void: bool = False,
                    per_job_bin: bool = False, return_winner: bool = False,
                    out: Optional[Dict[str, torch.Tensor]] = None, device: int = 0,
-                   workspace: Optional[_lib.Workspace] = None) -> Dict[str, torch.Tensor]:
+                   workspace: Optional[_lib.Workspace] = None, compact: bool = False) -> Dict[str, torch.Tensor]:
   """`reproject` for HOST tensors (pinned memory recommended): host->device copies, the fused
   kernels and the device->host copies of the guidance tensors all happen inside the C ABI call
   (se3ds_reproject_host), which returns when the host outputs are complete."""
@@ -204,11 +239,14 @@ def reproject_host(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.
     if t is None or tuple(t.shape) != shape or t.dtype != dtype or t.is_cuda or not t.is_contiguous():
       t = out[name] = torch.empty(shape, dtype=dtype, pin_memory=pin)
     return t
-  image = buf('proj_image', (j, h, w, 3))
+  if compact:  # 7 instead of 20 bytes per pixel come back over PCIe
+    image, mask = buf('proj_rgb_u8', (j, h, w, 3), torch.uint8), None
+  else:
+    image, mask = buf('proj_image', (j, h, w, 3)), buf('proj_mask', (j, h, w, 1))
   pdepth = buf('proj_depth', (j, h, w, 1))
-  mask = buf('proj_mask', (j, h, w, 1))
   winner = buf('winner', (j, h, w), torch.int32) if return_winner else None
-  flags = (_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0)
+  flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
+           (_lib.FLAG_COMPACT_OUT if compact else 0))
   ws = workspace or _lib.default_workspace(torch.device('cuda', device), role='host')
   _lib.check(_lib.load().se3ds_reproject_host(
       ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
@@ -543,7 +581,8 @@ class GuidanceMemory(object):
       d, f = pano_utils.project_feats_to_equirectangular(c.rgb, rel, self.height, self.width, constants.INVALID_RGB_VALUE,
                                                          self.depth_scale)
       mask = ((d > 0) & (d < 1) & (f != constants.INVALID_RGB_VALUE).all(dim=-1)).to(torch.float32)[..., None]
-      o = dict(proj_image=torch.clamp(f / 255, 0, 1), proj_depth=d[..., None], proj_mask=mask)
+      # tensor / tensor is an IEEE division; tensor / python-scalar would be a multiplication by 1 / 255
+      o = dict(proj_image=torch.clamp(f / torch.full((), 255.0, device=f.device), 0, 1), proj_depth=d[..., None], proj_mask=mask)
       if self.project_semantic:
         srel = c.coords - torch.cat([pos, torch.zeros_like(pos[:, :1])], dim=1)[:, :, None]
         _, sf = pano_utils.project_feats_to_equirectangular(c.feats, srel, self.height, self.width,

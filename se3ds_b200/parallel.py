@@ -5,7 +5,9 @@ partitioned over the ranks and each rank runs the fused kernels on its shard wit
 collective.  The only exchange is the all-gather of the finished guidance
 tensors -- the reference gathers per-replica outputs on the host
 (trainers/gan_manager.py:612-615, utils/eval_metric.py:127-130) -- plus, for whole-call parity
-of the global reject bin (utils/point_cloud_utils.py:150-153), a 4-float all-reduce.
+of the global reject bin (utils/point_cloud_utils.py:150-153), a 5-float all-reduce.  The gather ships a
+compact wire format (uint8 colours + float32 depth, 7 B per pixel instead of 20) and runs in place in a
+pre-sized buffer, piece by piece while the next piece renders (see reproject_sharded).
 """
 from __future__ import annotations
 
@@ -56,24 +58,56 @@ def _merge_whole_items(segs, num_poses):
   return groups
 
 
+def _chunk_groups(groups, chunks: int):
+  """Deals the kernel-call groups of a shard into `chunks` consecutive runs (for the gather pipeline)."""
+  chunks = max(1, min(chunks, len(groups)))
+  base, rem = divmod(len(groups), chunks)
+  out, i = [], 0
+  for c in range(chunks):
+    k = base + (1 if c < rem else 0)
+    out.append(groups[i:i + k])
+    i += k
+  return out
+
+
 def reproject_sharded(rgb, depth, src_pos, tgt_pos, *, group=None, bin_mode: str = 'call',
-                      gather: bool = True, compute_fn: Optional[Callable] = None,
-                      apply_bin_fn: Optional[Callable] = None, depth_scale: float = constants.DEPTH_SCALE,
+                      gather: bool = True, wire: str = 'compact', chunks: int = 0, expand: bool = True,
+                      compute_fn: Optional[Callable] = None, apply_bin_fn: Optional[Callable] = None,
+                      expand_fn: Optional[Callable] = None, depth_scale: float = constants.DEPTH_SCALE,
                       **kwargs) -> Dict[str, torch.Tensor]:
   """Shards N*P jobs over the ranks of `group`, runs the fused path, all-gathers the guidance.
 
   Every rank passes the same full inputs (or at least its own shard's items; other items are
   never read).  bin_mode: 'call' = the reference's whole-call reject bin (pixel (0,0) of global
-  job 0, exact: a 4-float all-reduce), 'shard' = each rank's own first job (what the reference
+  job 0, exact: a 5-float all-reduce), 'shard' = each rank's own first job (what the reference
   does per replica under MirroredStrategy, trainers/gan_manager.py:577), 'job' = per job.
   Returns the dict of `guidance.reproject`; with gather=True the tensors cover all J jobs on
   every rank, otherwise only the local shard ('job_range' tells which).
-  compute_fn / apply_bin_fn exist so that the host logic can be exercised without a GPU.
+
+  The gather (the reference concatenates per-replica outputs on the host, trainers/gan_manager.py:612-615,
+  utils/eval_metric.py:255-266): every rank renders straight into its slot of one pre-sized gather buffer
+  per tensor and the all-gather runs in place -- no padding copy before, no concatenation after (only a
+  job count that does not divide by the world size costs one compaction).  wire='compact' (default)
+  ships uint8 colours + float32 depth (7 B per pixel instead of 20; the mask is a function of the depth)
+  and expands to the float32 tensors on arrival, bit-identical by construction (`expand=False` keeps the
+  compact tensors); wire='f32' ships the float32 tensors themselves.  With chunks > 1 the shard is rendered
+  in that many pieces and the collective of piece k travels (async, NCCL's stream) while piece k+1
+  renders; chunks=0 picks min(4, kernel calls of the shard).  The reject bin is reduced with one tiny
+  all-reduce and applied after the gather, on every rank's copy.
+  compute_fn / apply_bin_fn / expand_fn exist so that the host logic can be exercised without a GPU.
   """
   if compute_fn is None:
     from . import guidance
     compute_fn = guidance.reproject
     apply_bin_fn = guidance.apply_bin
+    expand_fn = guidance.expand_guidance
+  if wire not in ('compact', 'f32'):
+    raise ValueError(f"wire must be 'compact' or 'f32', got {wire!r}")
+  if bin_mode not in ('call', 'shard', 'job'):
+    raise ValueError(f"bin_mode must be 'call', 'shard' or 'job', got {bin_mode!r}")
+  raw = bool(kwargs.get('raw_features'))
+  compact = wire == 'compact' and gather and not raw
+  want_winner = bool(kwargs.get('return_winner'))
   rank = dist.get_rank(group) if dist.is_initialized() else 0
   world = dist.get_world_size(group) if dist.is_initialized() else 1
   rgb = torch.as_tensor(rgb)
@@ -82,62 +116,110 @@ def reproject_sharded(rgb, depth, src_pos, tgt_pos, *, group=None, bin_mode: str
   n = rgb.shape[0]
   tgt_pos = torch.as_tensor(tgt_pos).reshape(n, -1, 3)
   p = tgt_pos.shape[1]
-  lo, hi = shard_bounds(n * p, rank, world)
+  jobs = n * p
+  lo, hi = shard_bounds(jobs, rank, world)
   depth = torch.as_tensor(depth).reshape(rgb.shape[:4])
   src_pos = torch.as_tensor(src_pos).reshape(n, rgb.shape[1], 3)
-
-  outs, bins = [], []
-  for grp in _merge_whole_items(job_segments(lo, hi, p), p):
-    n0, n1 = grp[0][0], grp[-1][0] + 1
-    p0, p1 = grp[0][1], grp[0][2]
-    o = compute_fn(rgb[n0:n1], depth[n0:n1], src_pos[n0:n1], tgt_pos[n0:n1, p0:p1], depth_scale=depth_scale,
-                   per_job_bin=(bin_mode == 'job'), export_bin=(bin_mode in ('call', 'shard')), **kwargs)
-    if bin_mode in ('call', 'shard'):
-      bins.append(o.pop('bin'))
-    outs.append(o)
   h, w = rgb.shape[2], rgb.shape[3]
-  if outs:
-    local = {k: torch.cat([o[k] for o in outs], dim=0) for k in _KEYS if k in outs[0]}
-  else:  # a rank without jobs still takes part in the collectives
-    dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
-    local = dict(proj_image=torch.empty((0, h, w, 3), device=dev), proj_depth=torch.empty((0, h, w, 1), device=dev),
-                 proj_mask=torch.empty((0, h, w, 1), device=dev))
-    if kwargs.get('return_winner'):
-      local['winner'] = torch.empty((0, h, w), dtype=torch.int32, device=dev)
-  dev = local['proj_image'].device
+  on_gpu = torch.cuda.is_available() and compute_fn.__module__.startswith('se3ds_b200')
+  dev = torch.device('cuda', torch.cuda.current_device()) if on_gpu else torch.device('cpu')
 
-  # reject bin (min depth, max R, G, B): one MAX all-reduce of (-zmin, r, g, b)
+  # One gather buffer per tensor.  Layout: pieces x world x (jobs per piece): piece c of every rank is one
+  # contiguous block, so its all-gather runs in place while piece c + 1 renders.  With one piece that is
+  # rank-major, i.e. job order (up to the padding of ranks that hold one job less).
+  multi = gather and world > 1
+  cap = -(-jobs // world) if multi else hi - lo
+  npieces = 1
+  if multi and compact and expand and jobs % world == 0 and cap > 1:
+    npieces = min(cap, chunks if chunks > 0 else 4)
+    while cap % npieces:
+      npieces -= 1
+  jpp = cap // npieces                      # jobs per piece
+  slots = npieces * world * jpp if multi else cap
+  keys = {'proj_rgb_u8': ((h, w, 3), torch.uint8), 'proj_depth': ((h, w, 1), torch.float32)} if compact else \
+         {'proj_image': ((h, w, 3), torch.float32), 'proj_depth': ((h, w, 1), torch.float32), 'proj_mask': ((h, w, 1), torch.float32)}
+  if want_winner:
+    keys['winner'] = ((h, w), torch.int32)
+  bufs = {k: torch.empty((slots,) + shp, dtype=dt, device=dev) for k, (shp, dt) in keys.items()}
+
+  def slot_of(local_job):                   # slot of this rank's local job in the gather buffer
+    c, j = divmod(local_job, jpp)
+    return ((c * world + rank) * jpp + j) if multi else local_job
+
+  bins, handles = [], []
+  for c in range(npieces):
+    a0, a1 = lo + c * jpp, min(hi, lo + (c + 1) * jpp)
+    done = a0 - lo
+    for grp in _merge_whole_items(job_segments(a0, a1, p), p):
+      n0, n1 = grp[0][0], grp[-1][0] + 1
+      p0, p1 = grp[0][1], grp[0][2]
+      cnt = (n1 - n0) * (p1 - p0)
+      s0 = slot_of(done)
+      views = {k: b[s0:s0 + cnt] for k, b in bufs.items()}
+      o = compute_fn(rgb[n0:n1], depth[n0:n1], src_pos[n0:n1], tgt_pos[n0:n1, p0:p1], depth_scale=depth_scale,
+                     per_job_bin=(bin_mode == 'job'), export_bin=(bin_mode in ('call', 'shard')), out=dict(views),
+                     **(dict(kwargs, compact=True) if compact else kwargs))
+      if bin_mode in ('call', 'shard'):
+        bins.append(o['bin'].clone())
+      for k, v in views.items():  # a compute_fn that ignores `out` (the CPU stand-in) returned fresh tensors
+        if o[k].data_ptr() != v.data_ptr():
+          v.copy_(o[k])
+      done += cnt
+    if multi:  # in-place all-gather of piece c (async: it travels on NCCL's stream while the next piece renders)
+      for k, b in bufs.items():
+        blk = b[c * world * jpp:(c + 1) * world * jpp]
+        handles.append(dist.all_gather_into_tensor(blk, blk[rank * jpp:(rank + 1) * jpp], group=group, async_op=npieces > 1))
+  for hnd in handles:
+    if hnd is not None:
+      hnd.wait()
+
+  # slot -> job: slot (c, r, j) holds job r * cap + c * jpp + j
+  job_map = None
+  if multi and npieces > 1:
+    cs, rs, js = torch.meshgrid(torch.arange(npieces), torch.arange(world), torch.arange(jpp), indexing='ij')
+    job_map = (rs * cap + cs * jpp + js).reshape(-1).to(torch.int32)
+
+  # reject bin: one MAX all-reduce of (-min depth, max R, max G, max B, -own winner depth of global job 0)
+  owners = []  # (slot of the owner job, 5-vector) to apply on this rank's tensors
   if bin_mode in ('call', 'shard'):
+    ninf = -float('inf')
     if bins:
-      b = torch.stack(bins)
-      red = torch.cat([(-b[:, :1]).max(dim=0).values, b[:, 1:4].max(dim=0).values])
+      b = torch.stack(bins).to(torch.float32)
+      red = torch.cat([(-b[:, :1]).max(dim=0).values, b[:, 1:4].max(dim=0).values, -b[0, 4:5]])
     else:
-      red = torch.tensor([-float('inf'), 0.0, 0.0, 0.0], device=dev)
-    if bin_mode == 'call' and world > 1:
-      dist.all_reduce(red, op=dist.ReduceOp.MAX, group=group)
-    owner = (lo == 0 and hi > 0) if bin_mode == 'call' else hi > lo
-    if owner:
-      # fifth value: depth of the owner pixel's own winner, from the call that rendered this rank's first job
-      red = torch.cat([-red[:1], red[1:], bins[0][4:5].to(red.device)])
-      if kwargs.get('raw_features'):
-        apply_bin_fn(red, local, depth_scale, raw_features=True)
-      else:
-        apply_bin_fn(red, local, depth_scale)
+      red = torch.tensor([ninf, 0.0, 0.0, 0.0, ninf], device=dev)
+    if bin_mode == 'call':
+      if not (lo == 0 and hi > 0):
+        red[4] = ninf  # only the owner of global job 0 knows its pixel's own winner
+      if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX, group=group)
+      if jobs > 0 and (gather or (lo == 0 and hi > 0)):
+        owners.append((0, torch.cat([-red[:1], red[1:4], -red[4:5]])))
+    else:  # 'shard': every rank's first job owns that rank's bin
+      mine = torch.cat([-red[:1], red[1:4], -red[4:5]])
+      if gather and world > 1:
+        allb = torch.empty((world, 5), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allb, mine.contiguous(), group=group)
+        for r in range(world):
+          a, b_ = shard_bounds(jobs, r, world)
+          if b_ > a:
+            owners.append((r * jpp if npieces > 1 else r * cap, allb[r]))
+      elif hi > lo:
+        owners.append((0, mine))
+  for slot, vec in owners:
+    tgt = {k: b[slot:] for k, b in bufs.items()}
+    if raw:
+      apply_bin_fn(vec, tgt, depth_scale, raw_features=True)
+    else:
+      apply_bin_fn(vec, tgt, depth_scale)
 
-  result = dict(local)
+  # padded slots -> job order (only when the job count does not divide by the world size)
+  if multi and jobs % world != 0:
+    idx = torch.cat([torch.arange(r * cap, r * cap + (shard_bounds(jobs, r, world)[1] - shard_bounds(jobs, r, world)[0]))
+                     for r in range(world)]).to(dev)
+    bufs = {k: b.index_select(0, idx) for k, b in bufs.items()}
+  result = dict(bufs)
+  if compact and expand:
+    result = expand_fn(result) if job_map is None else expand_fn(result, job_map=job_map.to(dev))
   result['job_range'] = (lo, hi)
-  if gather and world > 1:
-    # equal-sized (padded) shards -> a single all_gather_into_tensor per guidance tensor
-    cap = -(-(n * p) // world)
-    for k, v in local.items():
-      send = v.contiguous()
-      if send.shape[0] < cap:
-        send = torch.cat([send, send.new_zeros((cap - send.shape[0],) + tuple(send.shape[1:]))], dim=0)
-      recv = send.new_empty((world * cap,) + tuple(send.shape[1:]))
-      dist.all_gather_into_tensor(recv, send, group=group)
-      parts = []
-      for r in range(world):
-        a, b = shard_bounds(n * p, r, world)
-        parts.append(recv[r * cap:r * cap + (b - a)])
-      result[k] = torch.cat(parts, dim=0)
   return result

@@ -21,8 +21,9 @@ F32 = np.float32
 
 
 def oracle_compute(rgb, depth, src_pos, tgt_pos, depth_scale=20.0, per_job_bin=False, export_bin=False,
-                   return_winner=False, **kw):
-  """Emulates guidance.reproject(export_bin=...) with the oracle (CPU tensors)."""
+                   return_winner=False, out=None, compact=False, **kw):
+  """Emulates guidance.reproject(export_bin=..., compact=...) with the oracle (CPU tensors); `out` is ignored
+  (fresh tensors are returned, reproject_sharded copies them into its gather buffer)."""
   rgb, depth, src_pos, tgt_pos = (np.asarray(t) for t in (rgb, depth, src_pos, tgt_pos))
   o = X.reproject(rgb, depth, src_pos, tgt_pos, mask_first_frame=False, per_job_bin=per_job_bin)
   out = dict(proj_image=o['image'].copy(), proj_depth=o['depth'].copy(), proj_mask=o['mask'].copy())
@@ -57,27 +58,51 @@ def oracle_compute(rgb, depth, src_pos, tgt_pos, depth_scale=20.0, per_job_bin=F
       out['winner'] = out['winner'].copy()
       out['winner'][0, 0, 0] = -1
     out['bin'] = np.array([binz, *binf, own], F32)
+  if compact:  # uint8 colours + depth; the mask is a function of the depth
+    out['proj_rgb_u8'] = np.rint(out.pop('proj_image') * F32(255)).astype(np.uint8)
+    out.pop('proj_mask')
   return {k: torch.as_tensor(v) for k, v in out.items()}
+
+
+def oracle_expand(out, job_map=None):
+  """Emulates guidance.expand_guidance."""
+  rgb8, depth = out['proj_rgb_u8'].numpy(), out['proj_depth'].numpy()
+  image = np.clip(rgb8.astype(F32) / F32(255), 0, 1).astype(F32)
+  mask = ((depth > 0) & (depth < 1)).astype(F32)
+  if job_map is not None:
+    inv = np.empty_like(job_map.numpy()); inv[job_map.numpy()] = np.arange(len(inv))
+    image, mask, depth = image[inv], mask[inv], depth[inv]
+    out['proj_depth'] = torch.as_tensor(depth)
+    out['proj_rgb_u8'] = torch.as_tensor(rgb8[inv])
+    if 'winner' in out:
+      out['winner'] = out['winner'][torch.as_tensor(inv)]
+  out['proj_image'], out['proj_mask'] = torch.as_tensor(image), torch.as_tensor(mask)
+  return out
 
 
 def oracle_apply_bin(bin_values, out, depth_scale=20.0):
   b = bin_values.numpy().astype(F32)
   d = min(out['proj_depth'][0, 0, 0, 0].item(), float(np.clip(b[0], 0, F32(depth_scale)) / F32(depth_scale)))
   out['proj_depth'][0, 0, 0, 0] = d
-  img = np.maximum(out['proj_image'][0, 0, 0].numpy(), np.clip(b[1:4] / F32(255), 0, 1))
-  out['proj_image'][0, 0, 0] = torch.as_tensor(img)
-  out['proj_mask'][0, 0, 0, 0] = float(0 < d < 1)
+  if 'proj_rgb_u8' in out and 'proj_image' not in out:
+    img8 = np.maximum(out['proj_rgb_u8'][0, 0, 0].numpy(), np.clip(b[1:4], 0, 255).astype(np.uint8))
+    out['proj_rgb_u8'][0, 0, 0] = torch.as_tensor(img8)
+  else:
+    img = np.maximum(out['proj_image'][0, 0, 0].numpy(), np.clip(b[1:4] / F32(255), 0, 1))
+    out['proj_image'][0, 0, 0] = torch.as_tensor(img)
+    out['proj_mask'][0, 0, 0, 0] = float(0 < d < 1)
   if 'winner' in out and b[0] < b[4]:
     out['winner'][0, 0, 0] = -1
 
 
-def _worker(rank, world, port, n, p, bin_mode, q):
+def _worker(rank, world, port, n, p, bin_mode, wire, chunks, q):
   os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
   dist.init_process_group('gloo', rank=rank, world_size=world)
   try:
     inp = synth.make_inputs(n, 2, p, 16, seed=3, dist='rand', sweep=p > 1)
     res = parallel.reproject_sharded(inp['rgb'], inp['depth'], inp['src_pos'], inp['tgt_pos'], bin_mode=bin_mode,
-                                     compute_fn=oracle_compute, apply_bin_fn=oracle_apply_bin, return_winner=True)
+                                     wire=wire, chunks=chunks, compute_fn=oracle_compute, apply_bin_fn=oracle_apply_bin,
+                                     expand_fn=oracle_expand, return_winner=True)
     q.put((rank, {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in res.items()}))
   finally:
     dist.destroy_process_group()
@@ -89,13 +114,15 @@ def _free_port():
     return s.getsockname()[1]
 
 
-@pytest.mark.parametrize('n,p,bin_mode', [(4, 1, 'call'), (1, 5, 'call'), (3, 3, 'call'), (3, 2, 'job'), (1, 1, 'call')])
-def test_sharded_equals_single_call(n, p, bin_mode):
+@pytest.mark.parametrize('n,p,bin_mode,wire,chunks', [
+    (4, 1, 'call', 'compact', 0), (1, 5, 'call', 'compact', 0), (3, 3, 'call', 'f32', 0), (3, 2, 'job', 'compact', 0),
+    (1, 1, 'call', 'compact', 0), (1, 8, 'call', 'compact', 2), (4, 2, 'call', 'compact', 4), (2, 2, 'call', 'f32', 1)])
+def test_sharded_equals_single_call(n, p, bin_mode, wire, chunks):
   world = 2
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
   port = _free_port()
-  procs = [ctx.Process(target=_worker, args=(r, world, port, n, p, bin_mode, q)) for r in range(world)]
+  procs = [ctx.Process(target=_worker, args=(r, world, port, n, p, bin_mode, wire, chunks, q)) for r in range(world)]
   for pr in procs:
     pr.start()
   results = dict(q.get(timeout=240) for _ in range(world))

@@ -89,11 +89,11 @@ struct FusedParams {
   uint2* fbuf;
   uint32_t* sc_flat;
   float* sc_rad;
-  uint32_t* sc_rgb;  // uint8 colours of the source points, r | g << 8 | b << 16 (written by K2 for K3)
   const int* tile_tab;  // per job: (frame << 16 | row) of its S*H source rows, the tab_heavy unmasked rows first
   int tab_heavy, tab_light;  // ... followed by the tab_light masked ones
   int chunk_jobs;       // jobs of this chunk: tiles per column quarter = chunk_jobs * (tab_heavy + tab_light)
   int discard_scratch;  // K3 drops consumed scratch lines from L2 (discard.global.L2)
+  int wait_first;       // K2 waits for the previous grid before anything else (else only before it exits)
   Bin* bins;  // J bins (per call: only bins[0] is used)
   float* out_image;
   float* out_depth;
@@ -161,12 +161,12 @@ __device__ __forceinline__ uint32_t ldg_u8_stream(const void* p, uint64_t pol) {
 // A pixel's raw colour held in registers: uint8 sources stay packed in one word until they are used.
 template <typename RGB_T> struct RawRGB;
 template <> struct RawRGB<uint8_t> {
-  uint32_t v = 0;
+  uint32_t r = 0, g = 0, b = 0;  // kept apart: combining them right after the loads would wait for the loads
   __device__ __forceinline__ void load(const uint8_t* rgb, size_t pix, uint64_t pol) {
     const uint8_t* p = rgb + pix * 3;
-    v = ldg_u8_stream(p, pol) | (ldg_u8_stream(p + 1, pol) << 8) | (ldg_u8_stream(p + 2, pol) << 16);
+    r = ldg_u8_stream(p, pol); g = ldg_u8_stream(p + 1, pol); b = ldg_u8_stream(p + 2, pol);
   }
-  __device__ __forceinline__ int3 get() const { return make_int3(v & 255u, (v >> 8) & 255u, v >> 16); }
+  __device__ __forceinline__ int3 get() const { return make_int3(r, g, b); }
 };
 template <> struct RawRGB<int> {
   int3 v = {0, 0, 0};
@@ -308,14 +308,16 @@ constexpr int kWarps = kThreads / 32;
 
 template <typename RGB_T, bool VEC, int FEAT, int PROJ, bool KEY64, bool ROT>
 __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedParams q) {
-  // K2 only reads caller inputs until it touches the z-buffer / scratch / bins / tile counters.  If the
-  // caller guarantees that those inputs were not produced by the kernel launched just before this call
-  // (SE3DS_FLAG_INPUTS_READY), the wait for the previous grid -- normally the resolve that re-arms
-  // the z-buffer -- is postponed until after the first tile's projection math; otherwise it comes first.
+  // The z-buffer and the reject bins are double-buffered (the host alternates the sets from chunk to chunk),
+  // and nobody else reads the scratch while K2 writes it, so K2 does not depend on the kernel launched
+  // before it -- the resolve of the previous chunk or call, which is still re-arming the OTHER z-buffer
+  // set -- except through the caller's inputs.  If the caller guarantees that those were not produced by
+  // that kernel (SE3DS_FLAG_INPUTS_READY) K2 runs alongside its tail and waits for it only before it exits
+  // (which keeps the completion order of the chain: whoever waits for this grid also has everything
+  // before it); otherwise, or when the workspace layout changed since the last call, it waits first.
   pdl_launch_dependents();
-  bool waited = !(q.flags & SE3DS_FLAG_INPUTS_READY);
+  const bool waited = q.wait_first != 0;
   if (waited) pdl_wait();
-  constexpr bool kHasRgbScratch = std::is_same<RGB_T, uint8_t>::value;  // colours travel to K3 in the scratch
   __shared__ float4 sq[kWarps][kStackCap];  // X, Y, Z, bits: source pixel | projected << 30 | depth-valid << 31
   __shared__ int sqz[kWarps][kStackCap];    // job-frame (local job * S + frame) of the entry
   __shared__ float4 left[kWarps * 32];      // what the warps did not drain themselves
@@ -454,7 +456,6 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
     tl = tile_at(q, t);
     load_depth(tl, d);
   }
-  if (!waited) pdl_wait();  // from here on: z-buffer, scratch and bins of this workspace
   while (warp_uniform(t < ntiles)) {
     // issue the depth load of the next tile; it arrives while this tile is processed
     const int t_next = t + wj.stride;
@@ -473,15 +474,7 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
     const bool masked = row_masked(q, cur_s, row);
     const int pix0 = row * W + col0;
     const size_t fpix = (size_t)(cur_n * q.SC + cur_s) * q.HW + pix0;
-    // the colours travel to K3 in the scratch: 12 bytes of the 4 pixels, needed at the end of the tile
-    uint32_t c0 = 0, c1 = 0, c2 = 0;
     const bool store_scratch = scratch_masked_rows || !masked;
-    if constexpr (VEC && kHasRgbScratch) {
-      if (act[0] && store_scratch) {
-        const uint32_t* cp = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(q.rgb) + fpix * 3);
-        c0 = ldg_u32_stream(cp, stream_pol); c1 = ldg_u32_stream(cp + 1, stream_pol); c2 = ldg_u32_stream(cp + 2, stream_pol);
-      }
-    }
     const float se = __ldg(sin_e + row), ce = __ldg(cos_e + row);
     // FAST / PLAIN: fate of a depth-valid point of this row (masked rows hold -1 features, pano_utils.py:262-265)
     const int a_row = masked ? (filt ? 0 : 1) : 2;
@@ -598,10 +591,6 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
         if (act[0]) {
           __stcg(reinterpret_cast<uint4*>(q.sc_flat + so), make_uint4(scf[0], scf[1], scf[2], scf[3]));
           __stcg(reinterpret_cast<float4*>(q.sc_rad + so), make_float4(scr[0], scr[1], scr[2], scr[3]));
-          if constexpr (kHasRgbScratch) {  // 12 colour bytes -> one word (r | g << 8 | b << 16) per pixel
-            __stcg(reinterpret_cast<uint4*>(q.sc_rgb + so),
-                   make_uint4(c0 & 0xffffffu, __byte_perm(c0, c1, 0x4543) & 0xffffffu, __byte_perm(c1, c2, 0x4432) & 0xffffffu, c2 >> 8));
-          }
         }
       } else {
 #pragma unroll
@@ -609,12 +598,6 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
           if (act[k]) {
             __stcg(q.sc_flat + so + k, scf[k]);
             __stcg(q.sc_rad + so + k, scr[k]);
-            if constexpr (kHasRgbScratch) {
-              uint32_t c;
-              if constexpr (FEAT == 0) { c = raw[k].v; }
-              else { RawRGB<uint8_t> r1; r1.load(static_cast<const uint8_t*>(q.rgb), fpix + k, stream_pol); c = r1.v; }
-              __stcg(q.sc_rgb + so + k, c);
-            }
           }
       }
     }
@@ -643,6 +626,7 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
     const int total = *reinterpret_cast<volatile int*>(&left_cnt);
     for (int i0 = 0; i0 < total; i0 += 32) drain(left + i0, leftz + i0, min(32, total - i0));
   }
+  if (!waited) pdl_wait();
   stamp_end(q.stamps, 0);
 }
 
@@ -655,15 +639,12 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
 // pixels mostly land on neighbouring target pixels, and the memory system merges the lanes of one
 // instruction that fall into the same line.  The kernel is bound by memory latency (a streaming load, a
 // dependent z-buffer gather and a reduction per point), so the tiles are software-pipelined: the scratch
-// loads of the next tile are in flight while the gathers of the current one are outstanding.  uint8
-// colours arrive in the scratch (one word per point, written by K2); int32 colours are read from the
-// source.  A consumed scratch tile is dropped from L2 without write-back (it is dead until the next
-// call rewrites it).
-template <typename RGB_T>
+// and colour loads of the next tile are in flight while the gathers of the current one are outstanding.
+// A consumed scratch tile is dropped from L2 without write-back (it is dead until the next call
+// rewrites it).
 struct FeatTile {
   uint32_t scf[4];
   float scr[4];
-  RawRGB<RGB_T> raw[4];
 };
 
 // exact float16 pair of two bytes: 0x6400 | x is 1024 + x in float16 (ulp 1), minus 1024 is exact
@@ -677,7 +658,7 @@ __device__ __forceinline__ uint2 pack_f16x4_u8(uint32_t c) {
 template <typename RGB_T, bool KEY64>
 __global__ void __launch_bounds__(kThreads, 8) splat_feat_kernel(const FusedParams q) {
   pdl_enter();
-  constexpr bool kRgbInScratch = std::is_same<RGB_T, uint8_t>::value;
+  constexpr bool kU8 = std::is_same<RGB_T, uint8_t>::value;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int W = q.W;
   const WarpJob wj = warp_job(q, blockIdx.x * kWarps + wid, gridDim.x * kWarps);
@@ -703,16 +684,13 @@ __global__ void __launch_bounds__(kThreads, 8) splat_feat_kernel(const FusedPara
   bool bin_has = false;
   int3 bin_f = make_int3(0, 0, 0);
 
-  auto load_tile = [&](const Tile& ti, FeatTile<RGB_T>& d) {
+  auto load_tile = [&](const Tile& ti, FeatTile& d) {
     const size_t so = ((size_t)lj * q.S + ti.s) * q.HW + (size_t)ti.row * W + col0;
-    const size_t fpix = (size_t)(n * q.SC + ti.s) * q.HW + (size_t)ti.row * W + col0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (col0 + 32 * k < W) {
         d.scf[k] = ldcg_u32_stream(q.sc_flat + so + 32 * k, stream_pol);
         d.scr[k] = __uint_as_float(ldcg_u32_stream(q.sc_rad + so + 32 * k, stream_pol));
-        if constexpr (kRgbInScratch) d.raw[k].v = ldcg_u32_stream(q.sc_rgb + so + 32 * k, stream_pol);
-        else d.raw[k].load(static_cast<const RGB_T*>(q.rgb), fpix + 32 * k, stream_pol);
       } else {  // past the end of the row
         d.scf[k] = kScDropped; d.scr[k] = 0.0f;
       }
@@ -720,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, 8) splat_feat_kernel(const FusedPara
   };
 
   Tile ti = {}, ti_next = {};
-  FeatTile<RGB_T> cur, nxt;
+  FeatTile cur, nxt;
   int t = wj.w;
   if (warp_uniform(t < ntiles)) {
     ti = tile_at(q, t);
@@ -732,18 +710,21 @@ __global__ void __launch_bounds__(kThreads, 8) splat_feat_kernel(const FusedPara
       ti_next = tile_at(q, t_next);
       load_tile(ti_next, nxt);
     }
-    // issue the z-buffer gathers first, then consume (only the depth half of the key is needed)
+    // issue the z-buffer gathers (only the depth half of the key is needed) and the colour loads of the
+    // tile together, then consume
     uint32_t zbits[4];
+    RawRGB<RGB_T> raw[4];
+    const size_t fpix = (size_t)(n * q.SC + ti.s) * q.HW + (size_t)ti.row * W + col0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const bool haspix = !(cur.scf[k] & (kScDropped | kScInvalid));
       if constexpr (KEY64) zbits[k] = haspix ? (uint32_t)(__ldcg(zb + (cur.scf[k] & kScPixMask)) >> 32) : 0xFFFFFFFFu;
       else zbits[k] = haspix ? __ldcg(zb32 + (cur.scf[k] & kScPixMask)) : 0xFFFFFFFFu;
+      if (!(cur.scf[k] & kScDropped)) raw[k].load(static_cast<const RGB_T*>(q.rgb), fpix + 32 * k, stream_pol);
     }
-    if (can_discard && lane < 12) {  // 3 arrays x 4 lines of 128 bytes
+    if (can_discard && lane < 8) {  // 2 arrays x 4 lines of 128 bytes
       const size_t so = ((size_t)lj * q.S + ti.s) * q.HW + (size_t)ti.row * W + wj.xq * 128 + (lane & 3) * 32;
-      const uint32_t* base = lane < 4 ? q.sc_flat : (lane < 8 ? reinterpret_cast<const uint32_t*>(q.sc_rad) : q.sc_rgb);
-      if (lane < 8 || kRgbInScratch) l2_discard_128(base + so);
+      l2_discard_128((lane < 4 ? q.sc_flat : reinterpret_cast<const uint32_t*>(q.sc_rad)) + so);
     }
     const bool masked = row_masked(q, ti.s, ti.row);
 #pragma unroll
@@ -752,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, 8) splat_feat_kernel(const FusedPara
       const bool haspix = live && !(cur.scf[k] & kScInvalid);
       const bool dinv = cur.scf[k] & kScDepthInv;
       const bool plain = !dinv && !masked;  // the feature is the raw colour
-      const int3 f = point_feat(q, dinv, masked, cur.raw[k].get());
+      const int3 f = point_feat(q, dinv, masked, raw[k].get());
       bool rejected = live && !haspix;
       if (haspix) {
         // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
@@ -770,8 +751,8 @@ __global__ void __launch_bounds__(kThreads, 8) splat_feat_kernel(const FusedPara
           }
           if (need) {
             uint2 packed = pack_f16x4(f);
-            if constexpr (kRgbInScratch) {
-              if (plain) packed = pack_f16x4_u8(cur.raw[k].v);
+            if constexpr (kU8) {
+              if (plain) packed = pack_f16x4_u8(raw[k].r | (raw[k].g << 8) | (raw[k].b << 16));
             }
             red_max_f16x4(fb + (cur.scf[k] & kScPixMask), packed);
           }

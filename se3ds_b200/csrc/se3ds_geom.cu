@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <utility>
@@ -99,7 +100,7 @@ constexpr size_t kDefaultChunkBytes = (size_t)112 << 20;
 struct se3ds_ws {
   int device = 0, sm_count = 148;
   size_t max_bytes = kDefaultMaxBytes, chunk_bytes = kDefaultChunkBytes;
-  DevBuf zbuf, zbuf32, fbuf, scf, scr, scc, bins, cbin;  // scc: colour scratch
+  DevBuf zbuf, zbuf32, fbuf, scf, scr, bins, cbin;
   std::vector<TableEntry> tables;
   std::vector<TileTabEntry> tile_tabs;
   bool dirty = false;  // a pass was enqueued but its resolve (which re-arms) was not
@@ -110,6 +111,10 @@ struct se3ds_ws {
   float margin_scale = 1.0e-6f;  // certification margin: dx = W * scale, dy = 2 * H * scale pixels
   bool pdl = true;  // programmatic dependent launch between the fused kernels
   bool discard_scratch = true;  // K3 drops consumed scratch lines from L2 without write-back
+  // double-buffered z-buffer / bins: the set the next chunk of a lane / the next call uses, and the layout
+  // they were laid out for (a call with another layout must not overlap the previous call's resolve)
+  int zset[4] = {}, binset = 0;
+  size_t layout_sig = 0;
   // concurrent chunk lanes: lane 0 is the caller's stream, lanes 1.. are these (fork / join by events)
   static constexpr int kMaxLanes = 4;
   int lanes = 2;
@@ -131,14 +136,14 @@ struct se3ds_ws {
 namespace {
 
 size_t ws_total(const se3ds_ws* ws) {
-  size_t t = ws->zbuf.cap + ws->zbuf32.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->scc.cap + ws->bins.cap + ws->cbin.cap +
+  size_t t = ws->zbuf.cap + ws->zbuf32.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->bins.cap + ws->cbin.cap +
              ws->s_rgb.cap + ws->s_depth.cap + ws->s_src.cap + ws->s_tgt.cap + ws->s_img.cap +
              ws->s_dep.cap + ws->s_msk.cap + ws->s_win.cap;
   for (const auto& e : ws->tables) t += (size_t)(4 * e.h + 2 * e.w) * sizeof(float);
   return t;
 }
 
-// Job chunking: a chunk's z-buffer + feature buffer + scratch (16 + 12 S bytes per target pixel) should
+// Job chunking: a chunk's z-buffer + feature buffer + scratch (16 + 8 S bytes per target pixel) should
 // sit in L2.  The chunks are dealt round-robin to `lanes` concurrent streams which share that budget; a
 // call that cannot give every lane min_lane_chunks chunks of at least min_lane_points source points
 // uses fewer lanes (measured: c3 -4.4 %, c4 -8 % with two lanes; c2 would split into one chunk per lane
@@ -151,7 +156,7 @@ struct ChunkPlan {
 void plan_chunks(size_t budget_bytes, int lanes, long long min_lane_points, int min_lane_chunks, bool per_item, int n,
                  int s, int p, int h, int w, ChunkPlan* out) {
   const long long hw = (long long)h * w, J = (long long)n * p;
-  const size_t job_bytes = (size_t)hw * (16 + 12 * (size_t)s);
+  const size_t job_bytes = (size_t)hw * (16 + 8 * (size_t)s);
   lanes = std::max(1, lanes);
   int items_per_chunk = 1, PC = 1;
   long long chunk_jobs = 1, nchunks_total = 1;
@@ -304,16 +309,14 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
 }
 
 // K2 / K3 grids: (at most) one resident wave of persistent warps; a warp serves one (column quarter, job) and
-// shares that job's rows round-robin with the other warps of the pair (kernels.cuh).  The number of warps
-// per pair is chosen so that the expensive row class divides evenly: with k = ceil(rows / resident warps
-// per pair) rows per warp, ceil(rows / k) warps.
+// shares that job's rows round-robin with the other warps of the pair (kernels.cuh).  Full residency beats
+// an even split of the expensive rows (measured: 65 instead of 74 warps per pair so that each gets exactly
+// 6 unmasked rows made K2 4 us slower: the kernel needs the warps to hide its latencies).
 constexpr int kK2BlocksPerSM = 8, kK3BlocksPerSM = 8;
-int tile_grid(const se3ds_ws* ws, int w, int jobs, long long heavy_rows, long long all_rows, int blocks_per_sm) {
+int tile_grid(const se3ds_ws* ws, int w, int jobs, long long rows, int blocks_per_sm) {
   const long long pairs = (long long)((w + 127) / 128) * jobs;
-  const long long rows = heavy_rows > 0 ? heavy_rows : all_rows;  // per pair
   const long long max_warps = std::max<long long>(1, (long long)ws->sm_count * blocks_per_sm * kWarps / pairs);
-  const long long k = std::max<long long>(1, (rows + max_warps - 1) / max_warps);
-  const long long warps = std::max<long long>(1, (rows + k - 1) / k);
+  const long long warps = std::max<long long>(1, std::min(rows, max_warps));
   return (int)((warps * pairs + kWarps - 1) / kWarps);
 }
 
@@ -325,7 +328,7 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
   FusedParams qs = q;  // + this chunk's job count (+ stamp slots in profile mode 2)
   qs.chunk_jobs = jobs;
   const long long th = q.tab_heavy, ta = th + q.tab_light;
-  const dim3 grid2(tile_grid(ws, q.W, jobs, th, ta, kK2BlocksPerSM)), grid3(tile_grid(ws, q.W, jobs, th, q.uv <= 0 ? th : ta, kK3BlocksPerSM));
+  const dim3 grid2(tile_grid(ws, q.W, jobs, ta, kK2BlocksPerSM)), grid3(tile_grid(ws, q.W, jobs, q.uv <= 0 ? th : ta, kK3BlocksPerSM));
   cudaEvent_t* ev = nullptr;
   if (ws->profile == 2 && ws->stamp_used < kMaxStampChunks) qs.stamps = (unsigned long long*)ws->stamps.p + 3 * ws->stamp_used++;
   if (ws->profile == 1) {
@@ -419,7 +422,7 @@ int se3ds_ws_destroy(se3ds_ws* ws) {
   if (!ws) return SE3DS_OK;
   DeviceGuard guard_(ws->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&ws->zbuf, &ws->zbuf32, &ws->fbuf, &ws->scf, &ws->scr, &ws->scc, &ws->bins, &ws->cbin, &ws->dbg, &ws->stamps, &ws->s_rgb, &ws->s_depth,
+  for (DevBuf* b : {&ws->zbuf, &ws->zbuf32, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->dbg, &ws->stamps, &ws->s_rgb, &ws->s_depth,
                     &ws->s_src, &ws->s_tgt, &ws->s_img, &ws->s_dep, &ws->s_msk, &ws->s_win})
     if (b->p) cudaFree(b->p);
   for (auto& e : ws->tables) cudaFree(e.dev);
@@ -632,6 +635,7 @@ int se3ds_project_cloud(se3ds_ws* ws, const float* coords, const void* feats, in
   q.M = m; q.N = n; q.C = c; q.H = h; q.W = w; q.HW = h * w; q.mode = mode;
   q.void_in = input_void_class; q.void_out = output_void_class; q.depth_scale = depth_scale;
   ws->dirty = true;
+  ws->layout_sig = 0;  // the compat path lays the z-buffer out its own way
   fill_f32_kernel<<<(int)std::min<long long>((npix * c + kThreads - 1) / kThreads, 148 * 16), kThreads, 0, st>>>(feats_out, npix * c, output_void_class);
   if (m > 0) {
     const dim3 grid((unsigned)((m + kThreads - 1) / kThreads), n);
@@ -711,14 +715,14 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   // 64-bit packed (depth | index) keys when winner indices are wanted (or forced), else depth-only keys
   const bool key64 = winner_out != nullptr || (flags & SE3DS_FLAG_KEY64);
   const size_t lane_px = (size_t)chunk_jobs * hw;  // every lane owns one chunk's slice of each buffer
-  if (key64) { if (int rc = grow(ws->zbuf, lanes * lane_px * 8, 0xFF, st)) return rc; }
-  else { if (int rc = grow(ws->zbuf32, lanes * lane_px * 4, 0xFF, st)) return rc; }
+  // two z-buffer sets per lane (see splat_depth_kernel)
+  if (key64) { if (int rc = grow(ws->zbuf, 2 * lanes * lane_px * 8, 0xFF, st)) return rc; }
+  else { if (int rc = grow(ws->zbuf32, 2 * lanes * lane_px * 4, 0xFF, st)) return rc; }
   if (int rc = grow(ws->fbuf, lanes * lane_px * 8, 0, st)) return rc;
   if (int rc = grow(ws->scf, lanes * lane_px * s * 4, -1, st)) return rc;
   if (int rc = grow(ws->scr, lanes * lane_px * s * 4, -1, st)) return rc;
-  if (rgb_dtype == SE3DS_U8)
-    if (int rc = grow(ws->scc, lanes * lane_px * s * 4, -1, st)) return rc;
-  if (int rc = grow(ws->bins, (size_t)(per_job ? J : 1) * sizeof(Bin), 0, st)) return rc;
+  const size_t nbins = (size_t)(per_job ? J : 1);
+  if (int rc = grow(ws->bins, 2 * nbins * sizeof(Bin), 0, st)) return rc;
   const float* tab = nullptr;
   if (int rc = get_tables(ws, h, w, st, &tab)) return rc;
   const TileTabEntry* tt = nullptr;
@@ -728,7 +732,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   q.tile_tab = tt->dev; q.tab_heavy = tt->heavy; q.tab_light = tt->light;
   q.rgb = rgb; q.depth = depth; q.src_pos = src_pos; q.tgt_pos = tgt_pos; q.tgt_rot = tgt_rot; q.tab = tab;
   q.zbuf = (unsigned long long*)ws->zbuf.p; q.zbuf32 = (uint32_t*)ws->zbuf32.p; q.fbuf = (uint2*)ws->fbuf.p;
-  q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.sc_rgb = (uint32_t*)ws->scc.p; q.bins = (Bin*)ws->bins.p;
+  q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.bins = (Bin*)ws->bins.p + (size_t)ws->binset * nbins;
   q.discard_scratch = ws->discard_scratch ? 1 : 0;
   q.out_image = proj_image; q.out_depth = proj_depth; q.out_mask = proj_mask; q.out_winner = winner_out;
   q.N = n; q.S = s; q.SC = s_capacity; q.P = p; q.H = h; q.W = w; q.HW = (int)hw;
@@ -762,6 +766,11 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
                    aligned(proj_image, compact ? 4 : 16) && aligned(proj_depth, 16) && (compact || aligned(proj_mask, 16)) &&
                    (!winner_out || aligned(winner_out, 16));
 
+  // K2 may run alongside the previous call's resolve only if both calls agree on where everything lies
+  const size_t sig = ((size_t)lanes * lane_px * 31 + nbins) * 4 + (key64 ? 2 : 0) + 1;
+  const bool same_layout = sig == ws->layout_sig;
+  ws->layout_sig = sig;
+  ws->binset ^= 1;
   ws->dirty = true;
   // fork: everything enqueued so far on the caller's stream (its inputs, re-arming, tables) comes first
   cudaStream_t lane_st[se3ds_ws::kMaxLanes] = {st, ws->lane_stream[0], ws->lane_stream[1], ws->lane_stream[2]};
@@ -783,12 +792,15 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
     for (int p0 = 0; p0 < p; p0 += PC, ++chunk_no) {
       const int lane = (int)(chunk_no % lanes);
       q.n0 = n0; q.p0 = p0; q.PC = std::min(PC, p - p0);
-      q.zbuf = (unsigned long long*)ws->zbuf.p + (key64 ? lane * lane_px : 0);
-      q.zbuf32 = (uint32_t*)ws->zbuf32.p + (key64 ? 0 : lane * lane_px);
+      static const bool kNoFlip = getenv("SE3DS_NOFLIP") != nullptr, kWaitFirst = getenv("SE3DS_WAITFIRST") != nullptr;
+      const size_t zslice = (size_t)(2 * lane + ws->zset[lane]) * lane_px;
+      if (!kNoFlip) ws->zset[lane] ^= 1;
+      q.zbuf = (unsigned long long*)ws->zbuf.p + (key64 ? zslice : 0);
+      q.zbuf32 = (uint32_t*)ws->zbuf32.p + (key64 ? 0 : zslice);
+      q.wait_first = (!(flags & SE3DS_FLAG_INPUTS_READY) || !same_layout || pipe != nullptr || kNoFlip || kWaitFirst) ? 1 : 0;
       q.fbuf = (uint2*)ws->fbuf.p + lane * lane_px;
       q.sc_flat = (uint32_t*)ws->scf.p + lane * lane_px * s;
       q.sc_rad = (float*)ws->scr.p + lane * lane_px * s;
-      q.sc_rgb = (uint32_t*)ws->scc.p + lane * lane_px * s;
       const int rc = rgb_dtype == SE3DS_U8 ? run_chunk<uint8_t>(ws, q, nitems, vec, key64, lane_st[lane])
                                            : run_chunk<int>(ws, q, nitems, vec, key64, lane_st[lane]);
       if (rc) { join(); return rc; }

@@ -11,7 +11,7 @@ MIB = 1 << 20
 
 
 def job_bytes(s, h):
-  return h * 2 * h * (16 + 12 * s)  # z-buffer (<= 8) + feature buffer (8) + scratch (12 per frame), per target pixel
+  return h * 2 * h * (16 + 8 * s)  # z-buffer (<= 8) + feature buffer (8) + scratch (8 per frame), per target pixel
 
 
 def check_plan(n, s, p, h, budget, lanes, min_pts, min_chunks):
@@ -37,7 +37,7 @@ def test_plan_of_the_baseline_configs():
   c2 = check_plan(8, 1, 1, 512, 0, 2, 0, 0)          # configs[1]: one chunk, no fork / join
   assert (c2['lanes'], c2['nchunks'], c2['chunk_jobs']) == (1, 1, 8)
   c3 = check_plan(32, 4, 1, 512, 0, 2, 0, 0)
-  assert c3['lanes'] == 2 and c3['nchunks'] == 32
+  assert c3['lanes'] == 2 and c3['nchunks'] == 16
   c4 = check_plan(1, 1, 64, 512, 0, 2, 0, 0)         # 64 poses of one pano: blocks of poses
   assert c4['lanes'] == 2 and c4['items_per_chunk'] == 1 and c4['poses_per_chunk'] * c4['nchunks'] >= 64
   c5 = check_plan(64, 8, 1, 2048, 0, 2, 0, 0)        # one 8-frame 2048x4096 job exceeds the budget: a chunk per job

@@ -130,7 +130,7 @@ int se3ds_ws_verify_read(se3ds_ws* ws, unsigned long long counts[3], float max_d
  * block stamps %globaltimer when it ends, and a kernel's share of the step is its last stamp minus the
  * last stamp of the kernel launched before it.  se3ds_ws_profile_read_stamps synchronises and returns the
  * summed shares in milliseconds over `chunks` job chunks (the first chunk after enabling has no
- * predecessor and is skipped; at most 4096 chunks are recorded per read).  mode 0: off. */
+ * predecessor and is skipped; at most 2048 chunks are recorded per read).  mode 0: off. */
 int se3ds_ws_profile(se3ds_ws* ws, int mode);
 int se3ds_ws_profile_read(se3ds_ws* ws, float ms[3], unsigned long long* launches);
 int se3ds_ws_profile_read_stamps(se3ds_ws* ws, double ms[3], long long* chunks);

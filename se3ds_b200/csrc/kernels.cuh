@@ -38,7 +38,6 @@
 namespace se3ds {
 
 constexpr int kThreads = 128;
-constexpr int kMaxXq = 64;  // column quarters (128 columns each) that have their own tile counter: W <= 8192
 
 // Programmatic dependent launch: the three kernels of a chunk (and of consecutive calls) are
 // launched with programmatic stream serialization, so the blocks of the next kernel are scheduled
@@ -54,12 +53,14 @@ __device__ __forceinline__ void pdl_enter() {
 // Profiling (se3ds_ws_profile mode 2): every block stamps the end of its kernel; the latest stamp of a
 // kernel minus the latest stamp of the kernel before it is that kernel's share of the pipelined step
 // (programmatic dependent launch stays on, unlike with events between the launches).
+constexpr int kStampSlots = 64;  // the blocks of a kernel spread their stamps over this many words (same-address atomics serialise)
 __device__ __forceinline__ void stamp_end(const unsigned long long* stamps_const, int k) {
   unsigned long long* stamps = const_cast<unsigned long long*>(stamps_const);
   if (stamps != nullptr && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    atomicMax(stamps + k, t);
+    const unsigned b = blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * gridDim.x * gridDim.y;
+    atomicMax(stamps + k * kStampSlots + (b % kStampSlots), t);
   }
 }
 constexpr unsigned long long kZArmed = 0xFFFFFFFFFFFFFFFFull;
@@ -89,11 +90,6 @@ struct FusedParams {
   uint2* fbuf;
   uint32_t* sc_flat;
   float* sc_rad;
-  const int* tile_tab;  // per job: (frame << 16 | row) of its S*H source rows, the tab_heavy unmasked rows first
-  int tab_heavy, tab_light;  // ... followed by the tab_light masked ones
-  int chunk_jobs;       // jobs of this chunk: tiles per column quarter = chunk_jobs * (tab_heavy + tab_light)
-  int discard_scratch;  // K3 drops consumed scratch lines from L2 (discard.global.L2)
-  int wait_first;       // K2 waits for the previous grid before anything else (else only before it exits)
   Bin* bins;  // J bins (per call: only bins[0] is used)
   float* out_image;
   float* out_depth;
@@ -222,120 +218,100 @@ __device__ __forceinline__ void bin_max_feat_block(Bin* bin, bool has, int3 f) {
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Work distribution of K2 / K3: balanced static tiles, one warp at a time
-// ------------------------------------------------------------------------------------------
-// A tile is one source row of one job-frame (job = (item, pose), frame = source pano), restricted to the
-// 128 columns [128 xq, 128 xq + 128) a warp covers (32 lanes x 4 pixels).  The grid is (at most) one
-// resident wave of persistent warps; warp g serves ONE column quarter xq and ONE job of the chunk for
-// its whole life (its column sines / cosines and the poses stay in registers) and walks the rows
-// w, w + G, w + 2G, ... of that job's tile table (G = warps per (quarter, job)).  Rows differ in cost --
-// the masked rows of a pano are 3x cheaper in K2 and free in K3 -- so the host-built table lists the
-// unmasked rows of the job's S frames first, then the masked ones, and the host picks G such that the
-// expensive class divides evenly: every warp gets the same number of expensive tiles.  (Measured on
-// configs[1]: with rows dealt out block by block a quarter of the SM time was idle in the tail of K2 and
-// K3, profiles/r02_*; dynamic tile fetching from one counter per quarter serialises at the L2 atomic
-// unit and was 2-4x slower.)
-struct WarpJob {
-  int xq, lj, w, stride;  // column quarter, local job, first table entry, entries to skip per step
+// Launch geometry shared by K2 / K3: blockIdx.y = source row, blockIdx.z = local job * S + frame, a
+// block covers kThreads * PPT consecutive columns and a warp 32 * PPT of them.  Point k of a lane
+// sits at column col0 + 32 * k, i.e. every load, store and -- what matters -- every reduction
+// instruction of a warp covers 32 *consecutive* source pixels: neighbouring source pixels mostly
+// land on neighbouring target pixels, and the memory system merges the lanes of one instruction
+// that fall into the same line (measured, scripts/micro/scatter_micro.cu: a thread owning 4
+// consecutive points instead costs 1.2-1.5x more for the same REDG / gather traffic on the room
+// workload, 2.5x on an identity map).
+struct SrcIdx {
+  int lj, s, n, p, job, row, col0;
 };
-__device__ __forceinline__ WarpJob warp_job(const FusedParams& q, int gwarp, int nwarps) {
-  const int xq_count = (q.W + 127) >> 7;
-  WarpJob j;
-  j.xq = gwarp % xq_count;
-  const int rest = gwarp / xq_count;
-  const int per_xq = (nwarps - j.xq + xq_count - 1) / xq_count;  // warps serving this quarter
-  j.lj = rest % q.chunk_jobs;
-  j.w = rest / q.chunk_jobs;
-  j.stride = (per_xq - j.lj + q.chunk_jobs - 1) / q.chunk_jobs;   // ... and this job
-  return j;
+// K3 uses that mapping (STRIDE = 32).  K2 is bound by instruction issue, its reductions are hidden
+// behind the projection math: it keeps 4 consecutive pixels per thread (STRIDE = 1) for the 128-bit
+// depth / table loads and scratch stores (c3: K2 699 us against 735 us with the strided mapping).
+// The scratch is indexed by source pixel, so the two kernels need not agree.
+template <int PPT, int STRIDE>
+__device__ __forceinline__ SrcIdx src_index(const FusedParams& q) {
+  SrcIdx i;
+  const int z = blockIdx.z;
+  if (q.S == 1) { i.lj = z; i.s = 0; } else { i.lj = z / q.S; i.s = z - i.lj * q.S; }
+  if (q.PC == 1) { i.n = q.n0 + i.lj; i.p = q.p0; } else { const int a = i.lj / q.PC; i.n = q.n0 + a; i.p = q.p0 + (i.lj - a * q.PC); }
+  i.job = i.n * q.P + i.p;
+  i.row = blockIdx.y;
+  if constexpr (STRIDE == 1) i.col0 = (blockIdx.x * kThreads + threadIdx.x) * PPT;
+  else i.col0 = blockIdx.x * (kThreads * PPT) + (threadIdx.x >> 5) * (32 * PPT) + (threadIdx.x & 31);
+  return i;
 }
-struct Tile {
-  int s, row;
-};
-__device__ __forceinline__ Tile tile_at(const FusedParams& q, int i) {
-  const int e = __ldg(q.tile_tab + i);
-  return Tile{e >> 16, e & 0xffff};
-}
-// Tile numbers are warp-uniform by construction, but the compiler cannot see that (they derive from the
-// warp index): branches on them would count as divergent, which costs the uniform datapath (constants then
-// live in vector registers) and puts divergence checks around every vote.  A vote makes it explicit.
-__device__ __forceinline__ bool warp_uniform(bool p) { return __any_sync(0xffffffffu, p); }
 
-// Predicated reductions (the compiler turns `if (p) atomicMin(...)` into a branch around the REDG).
-__device__ __forceinline__ void red_min_u32_if(bool p, uint32_t* addr, uint32_t v) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p red.global.min.u32 [%0], %1;\n}" ::"l"(addr), "r"(v), "r"((int)p) : "memory");
-}
-__device__ __forceinline__ void red_min_u64_if(bool p, unsigned long long* addr, unsigned long long v) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p red.global.min.u64 [%0], %1;\n}" ::"l"(addr), "l"(v), "r"((int)p) : "memory");
-}
-// The scratch of a chunk is dead once K3 has read it: dropping the lines from L2 without a write-back
-// saves their DRAM traffic (they were written by K2 moments ago and are still resident).
-__device__ __forceinline__ void l2_discard_128(const void* p) {
-  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------
 // K2: fused unproject + translate + project + depth splat
 // ------------------------------------------------------------------------------------------
-// A thread owns 4 consecutive columns of its warp's tile (VEC: one 128-bit depth load, three 32-bit
-// colour loads and three 128-bit scratch stores per row); the depth and colours of the next tile are
-// loaded while the current one is processed.
+// Launch geometry: blockIdx.z = local job * S + frame, blockIdx.x = block of kThreads * 4 columns,
+// blockIdx.y = row group: a block walks the rows blockIdx.y + k * gridDim.y (k = 0 .. rows_per_block),
+// so the per-thread set-up (index math, poses, the column sines / cosines) is paid once per ~28 points
+// and the masked and unmasked rows of a pano are spread evenly over the blocks.  A thread owns 4
+// consecutive columns (VEC: one 128-bit depth load and two 128-bit scratch stores per row); the depth
+// of the next row is loaded while the current one is processed.  The host sizes rows_per_block so
+// that the grid is about one resident wave (8 blocks per SM).
 //
-// The kernel is bound by instruction issue, so the per-point path is kept short (~75 instructions):
+// The kernel is bound by instruction issue, so the per-point path is kept to ~90 instructions:
 //  * rad: the two-fma refinement of MUFU.RSQ (fast_rad, = __fsqrt_rn for normal operands); its
 //    reciprocal square root doubles as 1 / rad for the elevation.
 //  * pixel: certified fast projection in pixel units (project_pixel_fast).
 //  * Points the fast path cannot certify (a few in a thousand), and points whose squared radius is
 //    zero / denormal / huge / not finite, are pushed on a warp-private stack in shared memory (one
 //    vote per point on the common path) and projected canonically 32 at a time by the whole warp
-//    (drain): no divergence in the slow path.  What is left when a warp runs out of tiles goes to a
-//    block-wide list that the last warp of the block drains -- a warp defers only a handful of points,
-//    and a canonical projection costs the same ~420 instructions for 3 lanes as for 32.
-// FEAT: how the fate of a point (0 dropped / 1 rejected: only its depth feeds the reject bin /
-// 2 projected) is decided.  2 = PLAIN: uint8 colours, project_void == unproject_void == -1 (SE3DSModel,
-// eval_metric): a raw colour never equals a void class, a depth-valid point of an unmasked row is
-// projected and nothing else is.  1 = FAST: uint8 colours, project_void == -1 (gan_manager: depth-invalid
-// points carry unproject_void = 0 and ARE projected): decided from the depth validity and the row mask.
-// 0 = generic: the colours are read and compared with the void classes.
+//    (drain): no divergence in the slow path, no block barrier anywhere in the kernel.
+// FAST: uint8 RGB with project_void == -1 (every reference caller) and, if the compaction is on,
+// unproject_void == -1: a raw colour can then never equal a void class, so the fate of a point
+// (0 dropped / 1 rejected: only its depth feeds the reject bin / 2 projected) follows from its depth
+// validity and the row mask alone; otherwise the colours are read and compared.
 // PROJ: 0 = every point takes the canonical path (through the stack), 1 = certified fast path,
 // 2 = verify (both projections for every point, disagreements counted into q.dbg).
 // KEY64: the z-buffer holds the 64-bit packed (depth | point index) key -- the deterministic winner
 // (nearest depth, lowest index).  When the caller does not ask for winner indices the same minimum
 // depth comes from a 32-bit key (depth bits only): half the z-buffer traffic, identical guidance.
 constexpr int kStackCap = 160;  // < 32 entries survive a row, a row pushes at most 128 per warp
-constexpr int kWarps = kThreads / 32;
 
-template <typename RGB_T, bool VEC, int FEAT, int PROJ, bool KEY64, bool ROT>
+template <typename RGB_T, bool VEC, bool FAST, int PROJ, bool KEY64, bool ROT>
 __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedParams q) {
-  // The z-buffer and the reject bins are double-buffered (the host alternates the sets from chunk to chunk),
-  // and nobody else reads the scratch while K2 writes it, so K2 does not depend on the kernel launched
-  // before it -- the resolve of the previous chunk or call, which is still re-arming the OTHER z-buffer
-  // set -- except through the caller's inputs.  If the caller guarantees that those were not produced by
-  // that kernel (SE3DS_FLAG_INPUTS_READY) K2 runs alongside its tail and waits for it only before it exits
-  // (which keeps the completion order of the chain: whoever waits for this grid also has everything
-  // before it); otherwise, or when the workspace layout changed since the last call, it waits first.
+  // K2 only reads caller inputs until it touches the z-buffer / scratch / bins.  If the caller
+  // guarantees that those inputs were not produced by the kernel launched just before this call
+  // (SE3DS_FLAG_INPUTS_READY), the wait for the previous grid -- normally the resolve that re-arms
+  // the z-buffer -- is postponed until after the first row's projection math; otherwise it comes first.
   pdl_launch_dependents();
-  const bool waited = q.wait_first != 0;
+  bool waited = !(q.flags & SE3DS_FLAG_INPUTS_READY);
   if (waited) pdl_wait();
+  constexpr int kWarps = kThreads / 32;
   __shared__ float4 sq[kWarps][kStackCap];  // X, Y, Z, bits: source pixel | projected << 30 | depth-valid << 31
-  __shared__ int sqz[kWarps][kStackCap];    // job-frame (local job * S + frame) of the entry
-  __shared__ float4 left[kWarps * 32];      // what the warps did not drain themselves
-  __shared__ int leftz[kWarps * 32];
-  __shared__ int left_cnt, warps_done;
-  if (threadIdx.x == 0) { left_cnt = 0; warps_done = 0; }
-  __syncthreads();
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int zz = blockIdx.z;
+  int lj, s;
+  if (q.S == 1) { lj = zz; s = 0; } else { lj = zz / q.S; s = zz - lj * q.S; }
+  int n, p;
+  if (q.PC == 1) { n = q.n0 + lj; p = q.p0; } else { const int a = lj / q.PC; n = q.n0 + a; p = q.p0 + (lj - a * q.PC); }
+  const int job = n * q.P + p;
+  const int col0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
   const int W = q.W, H = q.H;
-  const WarpJob wj = warp_job(q, blockIdx.x * kWarps + wid, gridDim.x * kWarps);
-  const int ntiles = q.tab_heavy + q.tab_light;
-  const int col0 = wj.xq * 128 + lane * 4;
   bool act[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) act[k] = col0 + (VEC ? 0 : k) < W;  // VEC: W % 4 == 0, the four points are active together
 
+  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? job : 0);
+  unsigned long long* zb = q.zbuf + (size_t)lj * q.HW;
+  uint32_t* zb32 = q.zbuf32 + (size_t)lj * q.HW;
+  const size_t sc_frame = ((size_t)lj * q.S + s) * q.HW;
+  const uint32_t idx_frame = (uint32_t)(s * q.HW);
+  const size_t frame = (size_t)(n * q.SC + s) * q.HW;
+  const float* dframe = q.depth + frame;
   const float *sin_e = q.tab, *cos_e = q.tab + H, *sin_h = q.tab + 2 * H, *cos_h = sin_h + W;
   const uint64_t stream_pol = l2_policy_evict_first();
+
   float sh[4] = {}, ch[4] = {};
   if constexpr (VEC) {
     if (act[0]) {
@@ -349,42 +325,28 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
     for (int k = 0; k < 4; ++k)
       if (act[k]) { sh[k] = __ldg(sin_h + col0 + k); ch[k] = __ldg(cos_h + col0 + k); }
   }
+  const float* sp = q.src_pos + (size_t)(n * q.SC + s) * 3;
+  const float* tp = q.tgt_pos + (size_t)job * 3;
+  const float sx = __ldg(sp), sy = __ldg(sp + 1), sz = __ldg(sp + 2);
+  const float tx = __ldg(tp), ty = __ldg(tp + 1), tz = __ldg(tp + 2);
+  float rot[ROT ? 9 : 1];  // ROT: full SE(3) target pose (q.tgt_rot != nullptr), a separate instantiation
+  if constexpr (ROT) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rot[i] = __ldg(q.tgt_rot + (size_t)job * 9 + i);
+  }
   const bool filt = q.flags & SE3DS_FLAG_FILTER_VOID;
   const bool prefilter = q.prefilter_z != 0;
-  // FAST / PLAIN: fate of a depth-invalid point (feature = unproject_void everywhere, pano_utils.py:225)
+  // FAST: fate of a depth-invalid point (feature = unproject_void everywhere, pano_utils.py:225)
   const int a_void = filt ? 0 : (q.uv != -1 ? 2 : 1);
-  // masked rows hold only -1 / unproject_void features: K3 skips them when unproject_void <= 0 and then
-  // needs no scratch for them
-  const bool scratch_masked_rows = q.uv > 0;
 
-  uint32_t minb = 0x7fffffffu;  // smallest depth bits among this warp's rejected points (depths are > 0 here)
+  uint32_t minb = 0x7fffffffu;  // smallest depth bits among this thread's rejected points (depths are > 0 here)
   int wq = 0;                   // entries on the warp's stack (warp-uniform)
 
-  // per job-frame state, reloaded when the tile belongs to another job-frame
-  int cur_lj = -1, cur_s = -1;
-  float sx = 0.f, sy = 0.f, sz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
-  float rot[ROT ? 9 : 1];
-  Bin* bin = q.bins;
-  unsigned long long* zb = q.zbuf;
-  uint32_t* zb32 = q.zbuf32;
-  size_t sc_frame = 0;
-  uint32_t idx_frame = 0;
-
-  // canonical projection of up to 32 stacked points by the whole warp; an entry carries its job-frame, so
-  // the points of a batch may belong to different ones
-  auto drain = [&](const float4* list, const int* listz, int m) {
+  // canonical projection of up to 32 listed points by the whole warp (all entries of a block belong to its
+  // job-frame)
+  auto drain_list = [&](const float4* list, int m) {
     if (lane < m) {
       const float4 e = list[lane];
-      const int zz = listz[lane];
-      int lj, fs;
-      if (q.S == 1) { lj = zz; fs = 0; } else { lj = zz / q.S; fs = zz - lj * q.S; }
-      Bin* ebin = q.bins;
-      if (q.flags & SE3DS_FLAG_BIN_PER_JOB) {
-        int n, p;
-        if (q.PC == 1) { n = q.n0 + lj; p = q.p0; } else { const int a = lj / q.PC; n = q.n0 + a; p = q.p0 + (lj - a * q.PC); }
-        ebin += n * q.P + p;
-      }
-      const size_t ezb = (size_t)lj * q.HW, esc = ((size_t)lj * q.S + fs) * q.HW;
       const uint32_t meta = __float_as_uint(e.w);
       const int pix = (int)(meta & kScPixMask);
       const bool dvalid = meta >> 31, isproj = (meta >> 30) & 1u;
@@ -395,350 +357,258 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
       if (tpix >= 0) {
         word = (uint32_t)tpix | dflag;
         if constexpr (KEY64) {
-          const unsigned long long key = ((unsigned long long)__float_as_uint(rad) << 32) | (((uint32_t)(fs * q.HW) + (uint32_t)pix) << 1) | (dvalid ? 0u : 1u);
-          if (!prefilter || key < __ldcg(q.zbuf + ezb + tpix)) atomicMin(q.zbuf + ezb + tpix, key);
+          const unsigned long long key = ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)pix) << 1) | (dvalid ? 0u : 1u);
+          if (!prefilter || key < __ldcg(zb + tpix)) atomicMin(zb + tpix, key);
         } else {
           const uint32_t key = __float_as_uint(rad);
-          if (!prefilter || key < __ldcg(q.zbuf32 + ezb + tpix)) atomicMin(q.zbuf32 + ezb + tpix, key);
+          if (!prefilter || key < __ldcg(zb32 + tpix)) atomicMin(zb32 + tpix, key);
         }
       } else {  // rejected: only its depth feeds the reject bin (point_cloud_utils.py:146-159)
         word = kScInvalid | dflag;
         const uint32_t zneg = ~f32_ordered(rad);
-        if (zneg) bin_update_z(ebin, zneg);
+        if (zneg) bin_update_z(bin, zneg);
       }
-      __stcg(q.sc_flat + esc + pix, word);
-      __stcg(q.sc_rad + esc + pix, rad);
+      __stcg(q.sc_flat + sc_frame + pix, word);
+      __stcg(q.sc_rad + sc_frame + pix, rad);
     }
   };
-  auto drain_stack = [&]() {  // whole batches of 32
+  auto drain = [&]() {  // the top min(wq, 32) entries of the warp's stack
     __syncwarp();
-    while (wq >= 32) {
-      drain(&sq[wid][wq - 32], &sqz[wid][wq - 32], 32);
-      wq -= 32;
-    }
+    const int m = min(wq, 32);
+    drain_list(&sq[wid][wq - m], m);
+    wq -= m;
     __syncwarp();
   };
 
-  // inputs of a tile: the depth of the thread's 4 pixels (loaded one tile ahead)
-  // this warp's job
-  cur_lj = wj.lj;
-  const int cur_n = q.PC == 1 ? q.n0 + cur_lj : q.n0 + cur_lj / q.PC;
-  const int cur_job = cur_n * q.P + (q.PC == 1 ? q.p0 : q.p0 + (cur_lj - (cur_lj / q.PC) * q.PC));
-  bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? cur_job : 0);
-  zb = q.zbuf + (size_t)cur_lj * q.HW;
-  zb32 = q.zbuf32 + (size_t)cur_lj * q.HW;
-  {
-    const float* tp = q.tgt_pos + (size_t)cur_job * 3;
-    tx = __ldg(tp); ty = __ldg(tp + 1); tz = __ldg(tp + 2);
-    if constexpr (ROT) {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) rot[i] = __ldg(q.tgt_rot + (size_t)cur_job * 9 + i);
-    }
-  }
-  auto load_depth = [&](const Tile& tl, float (&d)[4]) {
-    const size_t pix = (size_t)(cur_n * q.SC + tl.s) * q.HW + (size_t)tl.row * W + col0;
+  const int row_step = gridDim.y;
+  int row = blockIdx.y;
+  // depth of the first row
+  float dn[4] = {};
+  auto load_depth = [&](int r) {
     if constexpr (VEC) {
       if (act[0]) {
-        const uint4 dv = ldg_u128_stream(q.depth + pix, stream_pol);
-        d[0] = __uint_as_float(dv.x); d[1] = __uint_as_float(dv.y); d[2] = __uint_as_float(dv.z); d[3] = __uint_as_float(dv.w);
+        const uint4 dv = ldg_u128_stream(dframe + (size_t)r * W + col0, stream_pol);
+        dn[0] = __uint_as_float(dv.x); dn[1] = __uint_as_float(dv.y); dn[2] = __uint_as_float(dv.z); dn[3] = __uint_as_float(dv.w);
       }
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (act[k]) d[k] = __uint_as_float(ldg_u32_stream(q.depth + pix + k, stream_pol));
+        if (act[k]) dn[k] = __uint_as_float(ldg_u32_stream(dframe + (size_t)r * W + col0 + k, stream_pol));
     }
   };
-
-  int t = wj.w;
-  float d[4] = {}, d_next[4] = {};
-  Tile tl = {}, tl_next = {};
-  if (warp_uniform(t < ntiles)) {
-    tl = tile_at(q, t);
-    load_depth(tl, d);
-  }
-  while (warp_uniform(t < ntiles)) {
-    // issue the depth load of the next tile; it arrives while this tile is processed
-    const int t_next = t + wj.stride;
-    if (warp_uniform(t_next < ntiles)) {
-      tl_next = tile_at(q, t_next);
-      load_depth(tl_next, d_next);
-    }
-    const int row = tl.row;
-    if (warp_uniform(tl.s != cur_s)) {  // another frame of the job: its position
-      cur_s = tl.s;
-      const float* sp = q.src_pos + (size_t)(cur_n * q.SC + cur_s) * 3;
-      sx = __ldg(sp); sy = __ldg(sp + 1); sz = __ldg(sp + 2);
-      sc_frame = ((size_t)cur_lj * q.S + cur_s) * q.HW;
-      idx_frame = (uint32_t)(cur_s * q.HW);
-    }
-    const bool masked = row_masked(q, cur_s, row);
-    const int pix0 = row * W + col0;
-    const size_t fpix = (size_t)(cur_n * q.SC + cur_s) * q.HW + pix0;
-    const bool store_scratch = scratch_masked_rows || !masked;
+  if (row < H) load_depth(row);
+  for (; row < H; row += row_step) {
+    float d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = dn[k];
+    if (row + row_step < H) load_depth(row + row_step);
     const float se = __ldg(sin_e + row), ce = __ldg(cos_e + row);
-    // FAST / PLAIN: fate of a depth-valid point of this row (masked rows hold -1 features, pano_utils.py:262-265)
+    const bool masked = row_masked(q, s, row);
+    const int pix0 = row * W + col0;
+    // FAST: fate of a depth-valid point of this row (masked rows hold -1 features, pano_utils.py:262-265)
     const int a_row = masked ? (filt ? 0 : 1) : 2;
     RawRGB<RGB_T> raw[4];
-    if constexpr (FEAT == 0) {
+    if constexpr (!FAST) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (act[k]) raw[k].load(static_cast<const RGB_T*>(q.rgb), fpix + k, stream_pol);
+        if (act[k]) raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + k, stream_pol);
     }
     uint32_t scf[4];
     float scr[4];
-    // LEAN rows (FAST / PLAIN): no point of the row is projected (a masked row whose depth-invalid points
+    bool hit[4];  // certified and projected: splat below
+    // LEAN rows (FAST only): no point of the row is projected (a masked row whose depth-invalid points
     // are not projected either) -- only the depths of the rejected points are needed, for the reject bin.
     auto points = [&](auto lean_tag) {
       constexpr bool LEAN = decltype(lean_tag)::value;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        // pano_utils.py:220-236
-        const float dk = d[k];
-        const bool dvalid = dk > 0.0f && dk < 1.0f;
-        const float rad0 = __fmul_rn(__fmul_rn(dk, q.depth_scale), dvalid ? 1.0f : 0.0f);
-        const float tt = __fmul_rn(rad0, se);
-        // models.py:225-226 then :273-275 -- two roundings
-        float X = __fsub_rn(__fadd_rn(__fmul_rn(tt, ch[k]), sx), tx);
-        float Y = __fsub_rn(__fadd_rn(__fmul_rn(tt, sh[k]), sy), ty);
-        float Z = __fsub_rn(__fadd_rn(__fmul_rn(rad0, ce), sz), tz);
-        if constexpr (ROT) {  // into the target camera frame: row-wise fma(r2, z, fma(r1, y, r0 * x))
-          const float a = X, b = Y, c = Z;
-          X = __fmaf_rn(rot[2], c, __fmaf_rn(rot[1], b, __fmul_rn(rot[0], a)));
-          Y = __fmaf_rn(rot[5], c, __fmaf_rn(rot[4], b, __fmul_rn(rot[3], a)));
-          Z = __fmaf_rn(rot[8], c, __fmaf_rn(rot[7], b, __fmul_rn(rot[6], a)));
-        }
-        bool proj, rej;  // projected / rejected (void feature: only its depth feeds the reject bin); else dropped
-        if constexpr (FEAT == 2) {  // a_void is 0 or 1 here
-          proj = !LEAN && dvalid;   // an inactive lane holds depth 0
-          rej = act[k] && (dvalid ? a_row == 1 : a_void == 1);
-        } else if constexpr (FEAT == 1) {
-          const int action = act[k] ? (dvalid ? a_row : a_void) : 0;
-          proj = !LEAN && action == 2; rej = action == 1;
-        } else {
-          const int3 f = point_feat(q, !dvalid, masked, raw[k].get());
-          const bool dropped = filt && f.x == q.uv && f.y == q.uv && f.z == q.uv;
-          const bool fv = f.x != q.pv && f.y != q.pv && f.z != q.pv;
-          proj = act[k] && !dropped && fv; rej = act[k] && !dropped && !fv;
-        }
-        const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(X, X), __fmul_rn(Y, Y)), __fmul_rn(Z, Z));
-        float rs;
-        bool sq_ok;
-        const float rad = fast_rad(r2, rs, sq_ok);
-        int tpix = 0, frow = 0;
-        float fx = 0.f;
-        bool certain = false;
-        if constexpr (!LEAN && PROJ != 0) certain = project_pixel_fast(X, Y, Z, rs, H, W, q.fast, tpix, fx, frow) && sq_ok;
-        if constexpr (PROJ == 2 && !LEAN) {
-          if (proj) {
-            const float radx = canon_rad(X, Y, Z);
-            const int exact = project_pixel_rad(X, Y, Z, H, W, radx);
-            atomicAdd(q.dbg, 1ull);
-            if (certain) {
-              atomicAdd(q.dbg + 1, 1ull);
-              if (exact != tpix || __float_as_uint(radx) != __float_as_uint(rad)) atomicAdd(q.dbg + 2, 1ull);
-            }
-            if (exact >= 0 && fabsf(Z) < 0.984375f * radx) {  // how far the fast column falls outside the canonical pixel
-              // (the fast row is a certified candidate, not a coordinate: it only counts when it was certified)
-              const float cx = (float)(exact % W);
-              const float ex = fmaxf(fmaxf(cx - fx, fx - (cx + 1.0f)), 0.0f);
-              const float ey = (certain && frow != exact / W) ? 1.0f : 0.0f;
-              atomicMax(q.dbg + 3, ((unsigned long long)__float_as_uint(ex) << 32) | __float_as_uint(ey));
-            }
-            certain = false;  // the results are the canonical ones
+    for (int k = 0; k < 4; ++k) {
+      // pano_utils.py:220-236
+      const bool dvalid = d[k] > 0.0f && d[k] < 1.0f;
+      const float rad0 = __fmul_rn(__fmul_rn(d[k], q.depth_scale), dvalid ? 1.0f : 0.0f);
+      const float t = __fmul_rn(rad0, se);
+      // models.py:225-226 then :273-275 -- two roundings
+      float X = __fsub_rn(__fadd_rn(__fmul_rn(t, ch[k]), sx), tx);
+      float Y = __fsub_rn(__fadd_rn(__fmul_rn(t, sh[k]), sy), ty);
+      float Z = __fsub_rn(__fadd_rn(__fmul_rn(rad0, ce), sz), tz);
+      if constexpr (ROT) {  // into the target camera frame: row-wise fma(r2, z, fma(r1, y, r0 * x))
+        const float a = X, b = Y, c = Z;
+        X = __fmaf_rn(rot[2], c, __fmaf_rn(rot[1], b, __fmul_rn(rot[0], a)));
+        Y = __fmaf_rn(rot[5], c, __fmaf_rn(rot[4], b, __fmul_rn(rot[3], a)));
+        Z = __fmaf_rn(rot[8], c, __fmaf_rn(rot[7], b, __fmul_rn(rot[6], a)));
+      }
+      int action;  // 0 dropped (compaction, or past the end of the row), 1 rejected (void feature), 2 projected
+      if constexpr (FAST) {
+        action = dvalid ? a_row : a_void;
+        if (!act[k]) action = 0;
+      } else {
+        const int3 f = point_feat(q, !dvalid, masked, raw[k].get());
+        const bool dropped = filt && f.x == q.uv && f.y == q.uv && f.z == q.uv;
+        const bool fv = f.x != q.pv && f.y != q.pv && f.z != q.pv;
+        action = (dropped || !act[k]) ? 0 : (fv ? 2 : 1);
+      }
+      const bool proj = !LEAN && action == 2, rej = action == 1;
+      const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(X, X), __fmul_rn(Y, Y)), __fmul_rn(Z, Z));
+      float rs;
+      bool sq_ok;
+      const float rad = fast_rad(r2, rs, sq_ok);
+      int tpix = 0, frow = 0;
+      float fx = 0.f;
+      bool certain = false;
+      if constexpr (!LEAN && PROJ != 0) certain = project_pixel_fast(X, Y, Z, rs, H, W, q.fast, tpix, fx, frow) && sq_ok;
+      if constexpr (PROJ == 2 && !LEAN) {
+        if (proj) {
+          const float radx = canon_rad(X, Y, Z);
+          const int exact = project_pixel_rad(X, Y, Z, H, W, radx);
+          atomicAdd(q.dbg, 1ull);
+          if (certain) {
+            atomicAdd(q.dbg + 1, 1ull);
+            if (exact != tpix || __float_as_uint(radx) != __float_as_uint(rad)) atomicAdd(q.dbg + 2, 1ull);
           }
-        }
-        const bool hit = proj && certain;
-        const uint32_t dflag = dvalid ? 0u : kScDepthInv;
-        scr[k] = rad;
-        scf[k] = (proj ? (uint32_t)tpix : (rej ? kScInvalid : kScDropped)) | dflag;
-        minb = min(minb, (rej && sq_ok) ? __float_as_uint(rad) : 0x7fffffffu);
-        // the splat of a certified point.  Multi-frame jobs: most points arrive at a pixel that already holds
-        // something nearer; a plain read (the entry only decreases, so a stale value is a safe filter) saves
-        // the reduction.
-        if constexpr (!LEAN) {
-          if constexpr (KEY64) {
-            const unsigned long long key = ((unsigned long long)__float_as_uint(rad) << 32) | ((idx_frame + (uint32_t)(pix0 + k)) << 1) | (dvalid ? 0u : 1u);
-            bool go = hit;
-            if (prefilter) go = hit && key < __ldcg(zb + (hit ? tpix : 0));
-            red_min_u64_if(go, zb + tpix, key);
-          } else {
-            bool go = hit;
-            if (prefilter) go = hit && __float_as_uint(rad) < __ldcg(zb32 + (hit ? tpix : 0));
-            red_min_u32_if(go, zb32 + tpix, __float_as_uint(rad));
+          if (exact >= 0 && fabsf(Z) < 0.984375f * radx) {  // how far the fast column falls outside the canonical pixel
+            // (the fast row is a certified candidate, not a coordinate: it only counts when it was certified)
+            const float cx = (float)(exact % W);
+            const float ex = fmaxf(fmaxf(cx - fx, fx - (cx + 1.0f)), 0.0f);
+            const float ey = (certain && frow != exact / W) ? 1.0f : 0.0f;
+            atomicMax(q.dbg + 3, ((unsigned long long)__float_as_uint(ex) << 32) | __float_as_uint(ey));
           }
-        }
-        // the rest goes to the warp's stack: projected but uncertified, or a radius the fast square root
-        // does not cover; drain() finishes those points (pixel, splat, scratch, reject bin)
-        const bool defer = (proj && !certain) || (rej && !sq_ok);
-        if (__any_sync(0xffffffffu, defer)) {
-          const unsigned dmask = __ballot_sync(0xffffffffu, defer);
-          if (defer) {
-            const int slot = wq + __popc(dmask & ((1u << lane) - 1u));
-            sq[wid][slot] = make_float4(X, Y, Z, __uint_as_float((uint32_t)(pix0 + k) | (proj ? 1u << 30 : 0u) | (dvalid ? 1u << 31 : 0u)));
-            sqz[wid][slot] = cur_lj * q.S + cur_s;
-          }
-          wq += __popc(dmask);
+          certain = false;  // the results are the canonical ones
         }
       }
+      const uint32_t dflag = dvalid ? 0u : kScDepthInv;
+      hit[k] = proj && certain;
+      scr[k] = rad;
+      scf[k] = (proj ? (uint32_t)tpix : (rej ? kScInvalid : kScDropped)) | dflag;
+      minb = min(minb, (rej && sq_ok) ? __float_as_uint(rad) : 0x7fffffffu);
+      // the rest goes to the warp's stack: projected but uncertified, or a radius the fast square root
+      // does not cover; drain() finishes those points (pixel, splat, scratch, reject bin)
+      const bool defer = (proj && !certain) || (rej && !sq_ok);
+      if (__any_sync(0xffffffffu, defer)) {
+        const unsigned dmask = __ballot_sync(0xffffffffu, defer);
+        if (defer)
+          sq[wid][wq + __popc(dmask & ((1u << lane) - 1u))] =
+              make_float4(X, Y, Z, __uint_as_float((uint32_t)(pix0 + k) | (proj ? 1u << 30 : 0u) | (dvalid ? 1u << 31 : 0u)));
+        wq += __popc(dmask);
+      }
+    }
     };
-    const bool lean = FEAT != 0 && a_row != 2 && a_void != 2;
-    if (warp_uniform(lean)) points(std::true_type{});
+    if (FAST && a_row != 2 && a_void != 2) points(std::true_type{});
     else points(std::false_type{});
-
-    if (warp_uniform(store_scratch)) {
-      const size_t so = sc_frame + pix0;
+    if (!waited) { pdl_wait(); waited = true; }  // from here on: z-buffer, scratch and bins of this workspace
+    if (prefilter) {
+      // multi-frame jobs: most points arrive at a pixel that already holds something nearer; a plain read
+      // (the entry only decreases, so a stale value is a safe filter) saves the reduction.  The four
+      // filter reads are issued together.
+      unsigned long long cur[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (KEY64) cur[k] = hit[k] ? __ldcg(zb + (scf[k] & kScPixMask)) : 0ull;
+        else cur[k] = hit[k] ? (unsigned long long)__ldcg(zb32 + (scf[k] & kScPixMask)) : 0ull;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (KEY64) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(scr[k]) << 32) | ((idx_frame + (uint32_t)(pix0 + k)) << 1) | ((scf[k] & kScDepthInv) ? 1u : 0u);
+          if (hit[k] && key < cur[k]) atomicMin(zb + (scf[k] & kScPixMask), key);
+        } else {
+          const uint32_t key = __float_as_uint(scr[k]);
+          if (hit[k] && key < (uint32_t)cur[k]) atomicMin(zb32 + (scf[k] & kScPixMask), key);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!hit[k]) continue;
+        if constexpr (KEY64) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(scr[k]) << 32) | ((idx_frame + (uint32_t)(pix0 + k)) << 1) | ((scf[k] & kScDepthInv) ? 1u : 0u);
+          atomicMin(zb + (scf[k] & kScPixMask), key);
+        } else {
+          atomicMin(zb32 + (scf[k] & kScPixMask), __float_as_uint(scr[k]));
+        }
+      }
+    }
+    // K3 skips the masked rows altogether when their features (-1 / unproject_void) cannot raise a maximum
+    if (!(masked && q.uv <= 0)) {
       if constexpr (VEC) {
         if (act[0]) {
-          __stcg(reinterpret_cast<uint4*>(q.sc_flat + so), make_uint4(scf[0], scf[1], scf[2], scf[3]));
-          __stcg(reinterpret_cast<float4*>(q.sc_rad + so), make_float4(scr[0], scr[1], scr[2], scr[3]));
+          __stcg(reinterpret_cast<uint4*>(q.sc_flat + sc_frame + pix0), make_uint4(scf[0], scf[1], scf[2], scf[3]));
+          __stcg(reinterpret_cast<float4*>(q.sc_rad + sc_frame + pix0), make_float4(scr[0], scr[1], scr[2], scr[3]));
         }
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (act[k]) {
-            __stcg(q.sc_flat + so + k, scf[k]);
-            __stcg(q.sc_rad + so + k, scr[k]);
+            __stcg(q.sc_flat + sc_frame + pix0 + k, scf[k]);
+            __stcg(q.sc_rad + sc_frame + pix0 + k, scr[k]);
           }
       }
     }
-    if (warp_uniform(wq >= 32)) drain_stack();
-    t = t_next;
-    tl = tl_next;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) d[k] = d_next[k];
-  }
-  // reject bin: smallest depth of this warp's rejected points (drain() adds its own)
-  const uint32_t wmin = __reduce_min_sync(0xffffffffu, minb);
-  if (lane == 0 && wmin != 0x7fffffffu) bin_update_z(bin, 0x7fffffffu - wmin);
-  // What is still stacked (< 32 entries) goes to the block-wide list; the last warp of the block to get
-  // here drains it.
-  __syncwarp();
-  int base = 0;
-  if (lane == 0) base = atomicAdd(&left_cnt, wq);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (lane < wq) { left[base + lane] = sq[wid][lane]; leftz[base + lane] = sqz[wid][lane]; }
-  __threadfence_block();
-  __syncwarp();
-  int last = 0;
-  if (lane == 0) last = atomicAdd(&warps_done, 1) == kWarps - 1;
-  if (__shfl_sync(0xffffffffu, last, 0)) {
-    __threadfence_block();
-    const int total = *reinterpret_cast<volatile int*>(&left_cnt);
-    for (int i0 = 0; i0 < total; i0 += 32) drain(left + i0, leftz + i0, min(32, total - i0));
+    while (wq >= 32) drain();
   }
   if (!waited) pdl_wait();
+  // (a block-wide drain by the last warp was tried: fewer instructions, but the canonical projection is a long
+  // dependent chain and serialising it at the end of every block made the kernel 6 us slower)
+  while (wq > 0) drain();
+  // reject bin: smallest depth of this warp's rejected points (the drains add their own)
+  const uint32_t wmin = __reduce_min_sync(0xffffffffu, minb);
+  if (lane == 0 && wmin != 0x7fffffffu) bin_update_z(bin, 0x7fffffffu - wmin);
   stamp_end(q.stamps, 0);
 }
 
 // ------------------------------------------------------------------------------------------
 // K3: tolerance test + per-channel max of the surviving features
 // ------------------------------------------------------------------------------------------
-// Same dynamic tiles as K2, with the lane mapping of the scatter measurements
-// (scripts/micro/scatter_micro.cu): point k of a lane sits at column 128 xq + lane + 32 k, so every
-// gather / reduction instruction of a warp covers 32 consecutive source pixels -- neighbouring source
-// pixels mostly land on neighbouring target pixels, and the memory system merges the lanes of one
-// instruction that fall into the same line.  The kernel is bound by memory latency (a streaming load, a
-// dependent z-buffer gather and a reduction per point), so the tiles are software-pipelined: the scratch
-// and colour loads of the next tile are in flight while the gathers of the current one are outstanding.
-// A consumed scratch tile is dropped from L2 without write-back (it is dead until the next call
-// rewrites it).
-struct FeatTile {
-  uint32_t scf[4];
-  float scr[4];
-};
-
-// exact float16 pair of two bytes: 0x6400 | x is 1024 + x in float16 (ulp 1), minus 1024 is exact
-__device__ __forceinline__ uint2 pack_f16x4_u8(uint32_t c) {
-  const __half2 k = __halves2half2(__ushort_as_half((unsigned short)0x6400), __ushort_as_half((unsigned short)0x6400));
-  const uint32_t rg = __byte_perm(c, 0x64u, 0x4140), b0 = __byte_perm(c, 0x64u, 0x4542);
-  const __half2 hrg = __hsub2(*reinterpret_cast<const __half2*>(&rg), k), hb0 = __hsub2(*reinterpret_cast<const __half2*>(&b0), k);
-  return make_uint2(*reinterpret_cast<const uint32_t*>(&hrg), *reinterpret_cast<const uint32_t*>(&hb0));
-}
-
-template <typename RGB_T, bool KEY64>
-__global__ void __launch_bounds__(kThreads, 8) splat_feat_kernel(const FusedParams q) {
+template <typename RGB_T, int PPT, bool KEY64>
+__global__ void __launch_bounds__(kThreads, 16) splat_feat_kernel(const FusedParams q) {
   pdl_enter();
-  constexpr bool kU8 = std::is_same<RGB_T, uint8_t>::value;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int W = q.W;
-  const WarpJob wj = warp_job(q, blockIdx.x * kWarps + wid, gridDim.x * kWarps);
-  const int col0 = wj.xq * 128 + lane;  // point k: col0 + 32 k
-  const uint64_t stream_pol = l2_policy_evict_first();  // last use of the scratch, only use of the colours
+  constexpr int kLaneStride = PPT == 1 ? 1 : 32;
+  const SrcIdx ix = src_index<PPT, kLaneStride>(q);
   // The feature buffer and the reject bin start at 0 (output_void_class) and only take maxima, so a
   // point whose channels are all <= 0 changes nothing.  A masked row holds only -1 / unproject_void
-  // features: with unproject_void <= 0 there is nothing to do in it (K2 does not write its scratch).
-  const bool skip_masked = q.uv <= 0;
-  const int ntiles = skip_masked ? q.tab_heavy : q.tab_heavy + q.tab_light;  // the masked rows come last
-  // a full, line-aligned tile of the scratch can be dropped from L2 once it is consumed
-  const bool can_discard = (W & 127) == 0 && q.discard_scratch;
-
-  // this warp's job
-  const int lj = wj.lj;
-  const int n = q.PC == 1 ? q.n0 + lj : q.n0 + lj / q.PC;
-  const int job = n * q.P + (q.PC == 1 ? q.p0 : q.p0 + (lj - (lj / q.PC) * q.PC));
-  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? job : 0);
-  const unsigned long long* zb = q.zbuf + (size_t)lj * q.HW;
-  const uint32_t* zb32 = q.zbuf32 + (size_t)lj * q.HW;
-  uint2* fb = q.fbuf + (size_t)lj * q.HW;
-
+  // features: the whole block (= one row segment) has nothing to do.
+  if (row_masked(q, ix.s, ix.row) && q.uv <= 0) return;
+  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
   bool bin_has = false;
   int3 bin_f = make_int3(0, 0, 0);
-
-  auto load_tile = [&](const Tile& ti, FeatTile& d) {
-    const size_t so = ((size_t)lj * q.S + ti.s) * q.HW + (size_t)ti.row * W + col0;
+  if (ix.col0 < q.W) {
+    const int pix0 = ix.row * q.W + ix.col0;  // point k: pixel pix0 + kLaneStride * k
+    const size_t frame = (size_t)(ix.n * q.SC + ix.s) * q.HW;
+    const size_t sc0 = ((size_t)ix.lj * q.S + ix.s) * q.HW + pix0;
+    uint32_t scf[PPT];
+    float scr[PPT];
+    RawRGB<RGB_T> raw[PPT];
+    const uint64_t stream_pol = l2_policy_evict_first();  // last use of the scratch, only use of the colours
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (col0 + 32 * k < W) {
-        d.scf[k] = ldcg_u32_stream(q.sc_flat + so + 32 * k, stream_pol);
-        d.scr[k] = __uint_as_float(ldcg_u32_stream(q.sc_rad + so + 32 * k, stream_pol));
+    for (int k = 0; k < PPT; ++k) {
+      if (ix.col0 + kLaneStride * k < q.W) {
+        scf[k] = ldcg_u32_stream(q.sc_flat + sc0 + kLaneStride * k, stream_pol);
+        scr[k] = __uint_as_float(ldcg_u32_stream(q.sc_rad + sc0 + kLaneStride * k, stream_pol));
+        raw[k].load(static_cast<const RGB_T*>(q.rgb), frame + pix0 + kLaneStride * k, stream_pol);
       } else {  // past the end of the row
-        d.scf[k] = kScDropped; d.scr[k] = 0.0f;
+        scf[k] = kScDropped; scr[k] = 0.0f;
       }
     }
-  };
-
-  Tile ti = {}, ti_next = {};
-  FeatTile cur, nxt;
-  int t = wj.w;
-  if (warp_uniform(t < ntiles)) {
-    ti = tile_at(q, t);
-    load_tile(ti, cur);
-  }
-  while (warp_uniform(t < ntiles)) {
-    const int t_next = t + wj.stride;
-    if (warp_uniform(t_next < ntiles)) {
-      ti_next = tile_at(q, t_next);
-      load_tile(ti_next, nxt);
-    }
-    // issue the z-buffer gathers (only the depth half of the key is needed) and the colour loads of the
-    // tile together, then consume
-    uint32_t zbits[4];
-    RawRGB<RGB_T> raw[4];
-    const size_t fpix = (size_t)(n * q.SC + ti.s) * q.HW + (size_t)ti.row * W + col0;
+    const unsigned long long* zb = q.zbuf + (size_t)ix.lj * q.HW;
+    const uint32_t* zb32 = q.zbuf32 + (size_t)ix.lj * q.HW;
+    uint2* fb = q.fbuf + (size_t)ix.lj * q.HW;
+    // issue the z-buffer gathers first, then consume (only the depth half of the key is needed)
+    uint32_t zbits[PPT];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool haspix = !(cur.scf[k] & (kScDropped | kScInvalid));
-      if constexpr (KEY64) zbits[k] = haspix ? (uint32_t)(__ldcg(zb + (cur.scf[k] & kScPixMask)) >> 32) : 0xFFFFFFFFu;
-      else zbits[k] = haspix ? __ldcg(zb32 + (cur.scf[k] & kScPixMask)) : 0xFFFFFFFFu;
-      if (!(cur.scf[k] & kScDropped)) raw[k].load(static_cast<const RGB_T*>(q.rgb), fpix + 32 * k, stream_pol);
+    for (int k = 0; k < PPT; ++k) {
+      const bool haspix = !(scf[k] & (kScDropped | kScInvalid));
+      if constexpr (KEY64) zbits[k] = haspix ? (uint32_t)(__ldcg(zb + (scf[k] & kScPixMask)) >> 32) : 0xFFFFFFFFu;
+      else zbits[k] = haspix ? __ldcg(zb32 + (scf[k] & kScPixMask)) : 0xFFFFFFFFu;
     }
-    if (can_discard && lane < 8) {  // 2 arrays x 4 lines of 128 bytes
-      const size_t so = ((size_t)lj * q.S + ti.s) * q.HW + (size_t)ti.row * W + wj.xq * 128 + (lane & 3) * 32;
-      l2_discard_128((lane < 4 ? q.sc_flat : reinterpret_cast<const uint32_t*>(q.sc_rad)) + so);
-    }
-    const bool masked = row_masked(q, ti.s, ti.row);
+    const bool masked = row_masked(q, ix.s, ix.row);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool live = !(cur.scf[k] & kScDropped);
-      const bool haspix = live && !(cur.scf[k] & kScInvalid);
-      const bool dinv = cur.scf[k] & kScDepthInv;
-      const bool plain = !dinv && !masked;  // the feature is the raw colour
-      const int3 f = point_feat(q, dinv, masked, raw[k].get());
+    for (int k = 0; k < PPT; ++k) {
+      const bool live = !(scf[k] & kScDropped);
+      const bool haspix = live && !(scf[k] & kScInvalid);
+      const int3 f = point_feat(q, scf[k] & kScDepthInv, masked, raw[k].get());
       bool rejected = live && !haspix;
       if (haspix) {
         // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
         const float zmin = fminf(__uint_as_float(zbits[k]), q.depth_scale);  // armed bits are a NaN: fminf -> depth_scale
-        const bool keep = cur.scr[k] < __fadd_rn(zmin, 0.1f);
+        const bool keep = scr[k] < __fadd_rn(zmin, 0.1f);
         if (keep) {
           // With several source frames many points share a pixel and most of them cannot raise the
           // maximum any more: a plain read (the buffer only grows, a stale value is a safe filter)
@@ -746,16 +616,10 @@ __global__ void __launch_bounds__(kThreads, 8) splat_feat_kernel(const FusedPara
           // costs more than it saves (measured: c3 -25 %, c5 +19 % for K3), so the host decides.
           bool need = true;
           if (q.prefilter_f) {
-            const float3 c = unpack_f16x4(__ldcg(fb + (cur.scf[k] & kScPixMask)));
-            need = (float)f.x > c.x || (float)f.y > c.y || (float)f.z > c.z;
+            const float3 cur = unpack_f16x4(__ldcg(fb + (scf[k] & kScPixMask)));
+            need = (float)f.x > cur.x || (float)f.y > cur.y || (float)f.z > cur.z;
           }
-          if (need) {
-            uint2 packed = pack_f16x4(f);
-            if constexpr (kU8) {
-              if (plain) packed = pack_f16x4_u8(raw[k].r | (raw[k].g << 8) | (raw[k].b << 16));
-            }
-            red_max_f16x4(fb + (cur.scf[k] & kScPixMask), packed);
-          }
+          if (need) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
         }
         rejected = !keep;
       }
@@ -764,20 +628,8 @@ __global__ void __launch_bounds__(kThreads, 8) splat_feat_kernel(const FusedPara
         bin_f.x = max(bin_f.x, f.x); bin_f.y = max(bin_f.y, f.y); bin_f.z = max(bin_f.z, f.z);
       }
     }
-    cur = nxt;
-    ti = ti_next;
-    t = t_next;
   }
-  // reject bin: per-channel maxima of this warp's rejected points (the warps of a block may serve different jobs)
-  if (__any_sync(0xffffffffu, bin_has)) {
-    const int r = __reduce_max_sync(0xffffffffu, bin_has ? bin_f.x : 0);
-    const int g = __reduce_max_sync(0xffffffffu, bin_has ? bin_f.y : 0);
-    const int b = __reduce_max_sync(0xffffffffu, bin_has ? bin_f.z : 0);
-    if (lane < 3) {
-      const int m = lane == 0 ? r : (lane == 1 ? g : b);
-      if (m > 0 && m > __ldcg(&bin->f[lane])) atomicMax(&bin->f[lane], m);
-    }
-  }
+  bin_max_feat_block(bin, bin_has, bin_f);
   stamp_end(q.stamps, 1);
 }
 

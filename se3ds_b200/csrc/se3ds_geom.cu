@@ -10,7 +10,6 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <utility>
@@ -77,21 +76,14 @@ int device_of(const void* p) {
   return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
 }
 
-// Tile table of one job (kernels.cuh, "Work distribution of K2 / K3"): (frame << 16 | row) of its S * H
-// source rows, unmasked rows first.
-struct TileTabEntry {
-  int s, h, mask_frames, mh;
-  int heavy, light;
-  int* dev;
-};
-
 struct TableEntry {
   int h, w;
   float margin;  // certification margin scale the row table was built for
   float* dev;    // sin/cos of the row elevations (2 H), of the column headings (2 W), row certification table (2 H)
 };
 
-constexpr size_t kMaxStampChunks = 4096;
+constexpr size_t kMaxStampChunks = 2048;
+constexpr size_t kStampWords = 3 * kStampSlots;  // per chunk: three kernels x kStampSlots
 constexpr size_t kDefaultMaxBytes = (size_t)2 << 30;
 constexpr size_t kDefaultChunkBytes = (size_t)112 << 20;
 
@@ -102,7 +94,6 @@ struct se3ds_ws {
   size_t max_bytes = kDefaultMaxBytes, chunk_bytes = kDefaultChunkBytes;
   DevBuf zbuf, zbuf32, fbuf, scf, scr, bins, cbin;
   std::vector<TableEntry> tables;
-  std::vector<TileTabEntry> tile_tabs;
   bool dirty = false;  // a pass was enqueued but its resolve (which re-arms) was not
   // staging of the host-buffer entry point
   DevBuf s_rgb, s_depth, s_src, s_tgt, s_img, s_dep, s_msk, s_win;
@@ -110,11 +101,6 @@ struct se3ds_ws {
   std::vector<cudaEvent_t> pipe_ev;  // 2 per batch item: inputs on device, outputs computed
   float margin_scale = 1.0e-6f;  // certification margin: dx = W * scale, dy = 2 * H * scale pixels
   bool pdl = true;  // programmatic dependent launch between the fused kernels
-  bool discard_scratch = true;  // K3 drops consumed scratch lines from L2 without write-back
-  // double-buffered z-buffer / bins: the set the next chunk of a lane / the next call uses, and the layout
-  // they were laid out for (a call with another layout must not overlap the previous call's resolve)
-  int zset[4] = {}, binset = 0;
-  size_t layout_sig = 0;
   // concurrent chunk lanes: lane 0 is the caller's stream, lanes 1.. are these (fork / join by events)
   static constexpr int kMaxLanes = 4;
   int lanes = 2;
@@ -260,30 +246,6 @@ int get_tables(se3ds_ws* ws, int h, int w, cudaStream_t stream, const float** ou
   return SE3DS_OK;
 }
 
-int get_tile_tab(se3ds_ws* ws, int s, int h, int mask_frames, int mh, cudaStream_t stream, const TileTabEntry** out) {
-  mask_frames = std::min(std::max(mask_frames, 0), s);
-  for (const auto& e : ws->tile_tabs)
-    if (e.s == s && e.h == h && e.mask_frames == mask_frames && e.mh == mh) { *out = &e; return SE3DS_OK; }
-  std::vector<int> heavy, light;
-  for (int f = 0; f < s; ++f)
-    for (int r = 0; r < h; ++r) {
-      const bool masked = f < mask_frames && (r < mh || r > h - mh);  // row_masked() of kernels.cuh
-      (masked ? light : heavy).push_back((f << 16) | r);
-    }
-  TileTabEntry e{s, h, mask_frames, mh, (int)heavy.size(), (int)light.size(), nullptr};
-  heavy.insert(heavy.end(), light.begin(), light.end());
-  CU(cudaMalloc(&e.dev, heavy.size() * sizeof(int)));
-  CU(cudaMemcpyAsync(e.dev, heavy.data(), heavy.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-  CU(cudaStreamSynchronize(stream));  // host vector goes out of scope
-  if (ws->tile_tabs.size() >= 16) {
-    cudaFree(ws->tile_tabs.front().dev);
-    ws->tile_tabs.erase(ws->tile_tabs.begin());
-  }
-  ws->tile_tabs.push_back(e);
-  *out = &ws->tile_tabs.back();
-  return SE3DS_OK;
-}
-
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 int launch_check(const char* what) {
@@ -308,16 +270,15 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-// K2 / K3 grids: (at most) one resident wave of persistent warps; a warp serves one (column quarter, job) and
-// shares that job's rows round-robin with the other warps of the pair (kernels.cuh).  Full residency beats
-// an even split of the expensive rows (measured: 65 instead of 74 warps per pair so that each gets exactly
-// 6 unmasked rows made K2 4 us slower: the kernel needs the warps to hide its latencies).
-constexpr int kK2BlocksPerSM = 8, kK3BlocksPerSM = 8;
-int tile_grid(const se3ds_ws* ws, int w, int jobs, long long rows, int blocks_per_sm) {
-  const long long pairs = (long long)((w + 127) / 128) * jobs;
-  const long long max_warps = std::max<long long>(1, (long long)ws->sm_count * blocks_per_sm * kWarps / pairs);
-  const long long warps = std::max<long long>(1, std::min(rows, max_warps));
-  return (int)((warps * pairs + kWarps - 1) / kWarps);
+// K2 grid: a block walks several rows (kernels.cuh); rows_per_block is sized so that the grid is about
+// one resident wave of kK2BlocksPerSM blocks per SM, capped so that short panos still spread over the SMs.
+constexpr int kK2BlocksPerSM = 8;
+int k2_row_groups(const se3ds_ws* ws, int gx, int h, int job_frames) {
+  const long long row_blocks = (long long)gx * h * job_frames;
+  const long long resident = (long long)ws->sm_count * kK2BlocksPerSM;
+  long long rpb = (row_blocks + resident - 1) / resident;
+  rpb = std::max<long long>(1, std::min<long long>(rpb, 32));
+  return (int)((h + rpb - 1) / rpb);
 }
 
 template <typename RGB_T, int PPT, bool KEY64>
@@ -325,12 +286,11 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
   const int gx = (q.W + kThreads * PPT - 1) / (kThreads * PPT);
   const int jobs = nitems * q.PC;
   const dim3 grid(gx, q.H, jobs * q.S), block(kThreads);
-  FusedParams qs = q;  // + this chunk's job count (+ stamp slots in profile mode 2)
-  qs.chunk_jobs = jobs;
-  const long long th = q.tab_heavy, ta = th + q.tab_light;
-  const dim3 grid2(tile_grid(ws, q.W, jobs, ta, kK2BlocksPerSM)), grid3(tile_grid(ws, q.W, jobs, q.uv <= 0 ? th : ta, kK3BlocksPerSM));
+  const int gx2 = (q.W + kThreads * 4 - 1) / (kThreads * 4);
+  const dim3 grid2(gx2, k2_row_groups(ws, gx2, q.H, jobs * q.S), jobs * q.S);
   cudaEvent_t* ev = nullptr;
-  if (ws->profile == 2 && ws->stamp_used < kMaxStampChunks) qs.stamps = (unsigned long long*)ws->stamps.p + 3 * ws->stamp_used++;
+  FusedParams qs = q;  // + this chunk's stamp slots in profile mode 2
+  if (ws->profile == 2 && ws->stamp_used < kMaxStampChunks) qs.stamps = (unsigned long long*)ws->stamps.p + kStampWords * ws->stamp_used++;
   if (ws->profile == 1) {
     if (ws->ev_used + 4 > ws->ev_pool.size())
       for (int i = 0; i < 4; ++i) {
@@ -342,10 +302,9 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
     ws->ev_used += 4;
     CU(cudaEventRecord(ev[0], st));
   }
-  // how K2 decides the fate of a point (see splat_depth_kernel): 2 PLAIN, 1 FAST, 0 generic
-  const bool u8 = std::is_same<RGB_T, uint8_t>::value;
-  const int feat = (u8 && q.pv == -1 && q.uv == -1) ? 2
-                   : (u8 && q.pv == -1 && !(q.flags & SE3DS_FLAG_FILTER_VOID)) ? 1 : 0;
+  // FAST feature mode: see splat_depth_kernel
+  const bool fast = std::is_same<RGB_T, uint8_t>::value && q.pv == -1 &&
+                    (!(q.flags & SE3DS_FLAG_FILTER_VOID) || q.uv == -1);
   const int proj = ws->proj_mode;
   const bool pdl = ws->pdl && ws->profile != 1;
   constexpr bool VEC = PPT == 4;
@@ -354,15 +313,11 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
     if (q.tgt_rot) CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, true>, grid2, block, st, pdl, qs)); \
     else CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, false>, grid2, block, st, pdl, qs));          \
   } while (0)
-#define LAUNCH_K2_F(F)                                                                          \
-  do {                                                                                          \
-    if (proj == 0) LAUNCH_K2(F, 0); else if (proj == 1) LAUNCH_K2(F, 1); else LAUNCH_K2(F, 2); \
-  } while (0)
-  if (feat == 2) LAUNCH_K2_F(2); else if (feat == 1) LAUNCH_K2_F(1); else LAUNCH_K2_F(0);
-#undef LAUNCH_K2_F
+  if (fast) { if (proj == 0) LAUNCH_K2(true, 0); else if (proj == 1) LAUNCH_K2(true, 1); else LAUNCH_K2(true, 2); }
+  else { if (proj == 0) LAUNCH_K2(false, 0); else if (proj == 1) LAUNCH_K2(false, 1); else LAUNCH_K2(false, 2); }
 #undef LAUNCH_K2
   if (ev) CU(cudaEventRecord(ev[1], st));
-  CU(launch_pdl(splat_feat_kernel<RGB_T, KEY64>, grid3, block, st, pdl, qs));
+  CU(launch_pdl(splat_feat_kernel<RGB_T, PPT, KEY64>, grid, block, st, pdl, qs));
   if (ev) CU(cudaEventRecord(ev[2], st));
   if (q.flags & SE3DS_FLAG_COMPACT_OUT) CU(launch_pdl(resolve_kernel<PPT, KEY64, true>, dim3(gx, q.H, jobs), block, st, pdl, qs));
   else CU(launch_pdl(resolve_kernel<PPT, KEY64, false>, dim3(gx, q.H, jobs), block, st, pdl, qs));
@@ -426,7 +381,6 @@ int se3ds_ws_destroy(se3ds_ws* ws) {
                     &ws->s_src, &ws->s_tgt, &ws->s_img, &ws->s_dep, &ws->s_msk, &ws->s_win})
     if (b->p) cudaFree(b->p);
   for (auto& e : ws->tables) cudaFree(e.dev);
-  for (auto& e : ws->tile_tabs) cudaFree(e.dev);
   for (auto& e : ws->ev_pool) cudaEventDestroy(e);
   for (auto& e : ws->pipe_ev) cudaEventDestroy(e);
   for (cudaStream_t st : {ws->hstream, ws->h2d_stream, ws->d2h_stream, ws->lane_stream[0], ws->lane_stream[1], ws->lane_stream[2]})
@@ -504,8 +458,8 @@ int se3ds_ws_profile(se3ds_ws* ws, int mode) {
   if (mode == 2) {
     GUARD(ws->device);
     CU(cudaDeviceSynchronize());
-    if (int rc = grow(ws->stamps, kMaxStampChunks * 3 * sizeof(unsigned long long), -1, nullptr)) return rc;
-    CU(cudaMemset(ws->stamps.p, 0, kMaxStampChunks * 3 * sizeof(unsigned long long)));
+    if (int rc = grow(ws->stamps, kMaxStampChunks * kStampWords * sizeof(unsigned long long), -1, nullptr)) return rc;
+    CU(cudaMemset(ws->stamps.p, 0, kMaxStampChunks * kStampWords * sizeof(unsigned long long)));
   }
   return SE3DS_OK;
 }
@@ -517,9 +471,11 @@ int se3ds_ws_profile_read_stamps(se3ds_ws* ws, double ms[3], long long* chunks) 
   if (!ws->stamps.p || ws->stamp_used < 2) return SE3DS_OK;
   GUARD(ws->device);
   CU(cudaDeviceSynchronize());
-  std::vector<unsigned long long> h(3 * ws->stamp_used);
-  CU(cudaMemcpy(h.data(), ws->stamps.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  CU(cudaMemset(ws->stamps.p, 0, kMaxStampChunks * 3 * sizeof(unsigned long long)));
+  std::vector<unsigned long long> raw(kStampWords * ws->stamp_used), h(3 * ws->stamp_used);
+  CU(cudaMemcpy(raw.data(), ws->stamps.p, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CU(cudaMemset(ws->stamps.p, 0, kMaxStampChunks * kStampWords * sizeof(unsigned long long)));
+  for (size_t i = 0; i < h.size(); ++i)  // end of a kernel = the latest of its blocks' stamps
+    h[i] = *std::max_element(raw.begin() + i * kStampSlots, raw.begin() + (i + 1) * kStampSlots);
   // chunk i: K2 ends at h[3i], K3 at h[3i+1], K4 at h[3i+2]; a kernel's share = its end - the previous end.
   // The first chunk has no predecessor: it is skipped.
   for (size_t i = 1; i < ws->stamp_used; ++i) {
@@ -635,7 +591,6 @@ int se3ds_project_cloud(se3ds_ws* ws, const float* coords, const void* feats, in
   q.M = m; q.N = n; q.C = c; q.H = h; q.W = w; q.HW = h * w; q.mode = mode;
   q.void_in = input_void_class; q.void_out = output_void_class; q.depth_scale = depth_scale;
   ws->dirty = true;
-  ws->layout_sig = 0;  // the compat path lays the z-buffer out its own way
   fill_f32_kernel<<<(int)std::min<long long>((npix * c + kThreads - 1) / kThreads, 148 * 16), kThreads, 0, st>>>(feats_out, npix * c, output_void_class);
   if (m > 0) {
     const dim3 grid((unsigned)((m + kThreads - 1) / kThreads), n);
@@ -688,7 +643,6 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   if (s_capacity == 0) s_capacity = s;
   if (s_capacity < s) return fail(SE3DS_ERR_BAD_SHAPE, "frame capacity %d < frames %d", s_capacity, s);
   if (w != 2 * h) return fail(SE3DS_ERR_BAD_SHAPE, "Expected equirectangular input images");
-  if (w > 128 * kMaxXq) return fail(SE3DS_ERR_BAD_SHAPE, "W > %d is not supported", 128 * kMaxXq);
   if (rgb_dtype != SE3DS_U8 && rgb_dtype != SE3DS_I32) return fail(SE3DS_ERR_BAD_DTYPE, "rgb must be uint8 or int32");
   if (unproject_void < -1 || unproject_void > 255 || project_void < -1 || project_void > 255)
     return fail(SE3DS_ERR_BAD_ARG, "void classes must be in [-1, 255]");
@@ -715,25 +669,19 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   // 64-bit packed (depth | index) keys when winner indices are wanted (or forced), else depth-only keys
   const bool key64 = winner_out != nullptr || (flags & SE3DS_FLAG_KEY64);
   const size_t lane_px = (size_t)chunk_jobs * hw;  // every lane owns one chunk's slice of each buffer
-  // two z-buffer sets per lane (see splat_depth_kernel)
-  if (key64) { if (int rc = grow(ws->zbuf, 2 * lanes * lane_px * 8, 0xFF, st)) return rc; }
-  else { if (int rc = grow(ws->zbuf32, 2 * lanes * lane_px * 4, 0xFF, st)) return rc; }
+  if (key64) { if (int rc = grow(ws->zbuf, lanes * lane_px * 8, 0xFF, st)) return rc; }
+  else { if (int rc = grow(ws->zbuf32, lanes * lane_px * 4, 0xFF, st)) return rc; }
   if (int rc = grow(ws->fbuf, lanes * lane_px * 8, 0, st)) return rc;
   if (int rc = grow(ws->scf, lanes * lane_px * s * 4, -1, st)) return rc;
   if (int rc = grow(ws->scr, lanes * lane_px * s * 4, -1, st)) return rc;
-  const size_t nbins = (size_t)(per_job ? J : 1);
-  if (int rc = grow(ws->bins, 2 * nbins * sizeof(Bin), 0, st)) return rc;
+  if (int rc = grow(ws->bins, (size_t)(per_job ? J : 1) * sizeof(Bin), 0, st)) return rc;
   const float* tab = nullptr;
   if (int rc = get_tables(ws, h, w, st, &tab)) return rc;
-  const TileTabEntry* tt = nullptr;
-  if (int rc = get_tile_tab(ws, s, h, mask_frames, (int)(h * mask_proportion), st, &tt)) return rc;
 
   FusedParams q{};
-  q.tile_tab = tt->dev; q.tab_heavy = tt->heavy; q.tab_light = tt->light;
   q.rgb = rgb; q.depth = depth; q.src_pos = src_pos; q.tgt_pos = tgt_pos; q.tgt_rot = tgt_rot; q.tab = tab;
   q.zbuf = (unsigned long long*)ws->zbuf.p; q.zbuf32 = (uint32_t*)ws->zbuf32.p; q.fbuf = (uint2*)ws->fbuf.p;
-  q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.bins = (Bin*)ws->bins.p + (size_t)ws->binset * nbins;
-  q.discard_scratch = ws->discard_scratch ? 1 : 0;
+  q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p; q.bins = (Bin*)ws->bins.p;
   q.out_image = proj_image; q.out_depth = proj_depth; q.out_mask = proj_mask; q.out_winner = winner_out;
   q.N = n; q.S = s; q.SC = s_capacity; q.P = p; q.H = h; q.W = w; q.HW = (int)hw;
   q.mh = (int)(h * mask_proportion);
@@ -766,11 +714,6 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
                    aligned(proj_image, compact ? 4 : 16) && aligned(proj_depth, 16) && (compact || aligned(proj_mask, 16)) &&
                    (!winner_out || aligned(winner_out, 16));
 
-  // K2 may run alongside the previous call's resolve only if both calls agree on where everything lies
-  const size_t sig = ((size_t)lanes * lane_px * 31 + nbins) * 4 + (key64 ? 2 : 0) + 1;
-  const bool same_layout = sig == ws->layout_sig;
-  ws->layout_sig = sig;
-  ws->binset ^= 1;
   ws->dirty = true;
   // fork: everything enqueued so far on the caller's stream (its inputs, re-arming, tables) comes first
   cudaStream_t lane_st[se3ds_ws::kMaxLanes] = {st, ws->lane_stream[0], ws->lane_stream[1], ws->lane_stream[2]};
@@ -792,12 +735,8 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
     for (int p0 = 0; p0 < p; p0 += PC, ++chunk_no) {
       const int lane = (int)(chunk_no % lanes);
       q.n0 = n0; q.p0 = p0; q.PC = std::min(PC, p - p0);
-      static const bool kNoFlip = getenv("SE3DS_NOFLIP") != nullptr, kWaitFirst = getenv("SE3DS_WAITFIRST") != nullptr;
-      const size_t zslice = (size_t)(2 * lane + ws->zset[lane]) * lane_px;
-      if (!kNoFlip) ws->zset[lane] ^= 1;
-      q.zbuf = (unsigned long long*)ws->zbuf.p + (key64 ? zslice : 0);
-      q.zbuf32 = (uint32_t*)ws->zbuf32.p + (key64 ? 0 : zslice);
-      q.wait_first = (!(flags & SE3DS_FLAG_INPUTS_READY) || !same_layout || pipe != nullptr || kNoFlip || kWaitFirst) ? 1 : 0;
+      q.zbuf = (unsigned long long*)ws->zbuf.p + (key64 ? lane * lane_px : 0);
+      q.zbuf32 = (uint32_t*)ws->zbuf32.p + (key64 ? 0 : lane * lane_px);
       q.fbuf = (uint2*)ws->fbuf.p + lane * lane_px;
       q.sc_flat = (uint32_t*)ws->scf.p + lane * lane_px * s;
       q.sc_rad = (float*)ws->scr.p + lane * lane_px * s;

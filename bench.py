@@ -7,7 +7,9 @@
 A "step" is one pass of the fused path over one batch of synthetic RGB-D panoramas
 (config c2 = 512x1024, batch 8, one source frame, one target pose -- BASELINE.json configs[1]).
 Weak scaling: every rank (one process per GPU) runs the full config on its own batch; no
-data-path collective.  Prints ONE JSON line on rank 0.
+data-path collective.  Prints ONE JSON line on rank 0; `extra` holds short sub-records of the other
+configs / modes (64-bit key, compact outputs, c1 / c3 / c4 / c5) and, on several GPUs, the strong-scaling
+sharded form of c4 with and without the NCCL all-gather of the guidance.
 """
 from __future__ import annotations
 
@@ -153,11 +155,18 @@ def run_reference_arm(args, cfg):
   c = dict(cfg)
   inp = synth.make_inputs(1, c['s'], c['p'], c['h'], seed=100, dist=args.dist, sweep=c['sweep'])
   # one step = `workers` items (a bounded sample of the config's batch), one per worker
-  steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+  steps, warmup = max(1, args.steps), max(1, args.warmup)
+  budget_s = 150.0  # the whole arm has to end within a few minutes: fewer steps than asked only beyond this
   which = 'c'
+  capped = None
   with mp.get_context('fork').Pool(workers) as pool:
+    t0 = time.perf_counter()
     for _ in range(warmup):
       pool.map(_cpu_one_batch, [(inp, which)] * workers)
+    per_step = (time.perf_counter() - t0) / warmup
+    if per_step * steps > budget_s:
+      capped = f'{steps} steps asked; {per_step:.2f} s per step would exceed the {budget_s:.0f} s budget of the CPU arm'
+      steps = max(1, int(budget_s / per_step))
     t0 = time.perf_counter()
     for _ in range(steps):
       pool.map(_cpu_one_batch, [(inp, which)] * workers)
@@ -168,7 +177,8 @@ def run_reference_arm(args, cfg):
       'impl': 'reference', 'metric': 'reprojected panoramas/s', 'value': value, 'unit': 'panos/s', 'n_gpus': args.gpus,
       'steps': steps, 'warmup': warmup, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': workload_name(args.config, c, args.dist), 'sample_items_per_step': workers},
+      'config': {'workload': workload_name(args.config, c, args.dist)},
+      'sample_items_per_step': workers, 'steps_capped': capped,
       'cpu_baseline': {'value': value, 'unit': 'panos/s', 'cores': workers, 'kind': 'port',
                        'sample': f'{workers} items per step (one per worker process), scalar C restatement of the '
                                  'reference path (TensorFlow not installed)'},
@@ -183,47 +193,191 @@ def workload_name(name, c, dist):
           f"depth={dist}, mask frame 0, void -1/-1")
 
 
-def run_sharded(args, cfg, world, rank, local_rank, dev):
-  """Strong scaling of one call (e.g. c4: 64 poses of one pano): every rank renders its block of the
-  job list, then the finished guidance tensors are all-gathered (NCCL over NVLink) and the reject
-  bin is all-reduced -- all inside the timed step."""
+def sharded_record(args, world, rank, dev, steps=60, warmup=5):
+  """Strong scaling of ONE call (config c4: 64 poses of one pano): every rank renders its block of the job list;
+  `gather`: the finished guidance is all-gathered to every rank inside the step (compact wire format, in place,
+  pipelined, expanded to float32 on arrival -- se3ds_b200/parallel.py); `local`: the shards stay where they
+  were rendered (no data-path collective).  Returns the sub-record (max over ranks)."""
   import torch
   import torch.distributed as dist
   from se3ds_b200 import parallel, synth
+  cfg = CONFIGS['c4']
   n, s, p, h = cfg['n'], cfg['s'], cfg['p'], cfg['h']
-  inp = synth.make_inputs(n, s, p, h, seed=7, dist=args.dist, sweep=cfg['sweep'])
+  inp = synth.make_inputs(n, s, p, h, seed=7, dist=args.dist, sweep=True)
   t = {k: torch.as_tensor(v).to(dev) for k, v in inp.items()}
-  def step():
-    return parallel.reproject_sharded(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1)
-  for _ in range(max(args.warmup, 3)):
-    step()
-  torch.cuda.synchronize()
+  rec = {'workload': workload_name('c4', cfg, args.dist), 'scaling': 'strong', 'steps': steps}
+  for label, kw in (('gather_compact', dict(gather=True, wire='compact')), ('gather_f32', dict(gather=True, wire='f32')),
+                    ('local', dict(gather=False))):
+    def step():
+      return parallel.reproject_sharded(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, **kw)
+    for _ in range(warmup):
+      out = step()
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rec[label] = {'ms_per_step': ms.item(), 'panos_per_s': n * p / (ms.item() * 1e-3),
+                  'bytes_held_per_rank': sum(v.numel() * v.element_size() for v in out.values() if torch.is_tensor(v))}
+  return rec
+
+
+def gpu_measure(guidance, synth, lib, torch, dist, cfg, args, dev, local_rank, world, rank, steps, warmup,
+                key64=False, compact=False, clocks=False):
+  """Device-resident throughput of one config: K timed steps of the fused path over a ring of input / output sets
+  larger than 2x L2, stream launches with programmatic dependent launch, CUDA events, max over ranks."""
+  n, s, p, h = cfg['n'], cfg['s'], cfg['p'], cfg['h']
+  src_bytes, out_bytes = alg_bytes(cfg)
+  set_bytes = src_bytes + out_bytes
+  ring = max(2, min(16, -(-2 * L2_BYTES // set_bytes) + 1))
+  ws = lib.Workspace(local_rank, 0, args.chunk_mb << 20)
+  ws.projection_mode(args.proj_mode)
+  ws.pdl(not args.no_pdl)
+  if args.lanes:
+    ws.lanes(args.lanes, 0, args.lane_chunks)
+  plans = []
+  for r in range(ring):
+    gen_n = min(n, 8)  # large configs reuse one generated block of items per set
+    inp = synth.make_inputs(gen_n, s, p, h, seed=1000 * rank + r, dist=args.dist, sweep=cfg['sweep'])
+    if gen_n < n:
+      inp = {k: np.concatenate([v] * (n // gen_n), axis=0) for k, v in inp.items()}
+    t = {k: torch.as_tensor(v).to(dev) for k, v in inp.items()}
+    plans.append(guidance.prepare(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, workspace=ws,
+                                  key64=key64, inputs_ready=True, compact=compact))
+  stream = torch.cuda.Stream(dev)
+
+  def barrier():
+    stream.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  with torch.cuda.stream(stream):
+    for pl in plans:  # grows the workspace, uploads the tables
+      pl.run()
+    stream.synchronize()
+    graphs = None
+    if args.graph:
+      graphs = []
+      for pl in plans:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+          pl.run()
+        graphs.append(g)
+
+    def step(i):
+      if graphs is not None:
+        graphs[i % ring].replay()
+      else:
+        plans[i % ring].run()
+
+    l0 = ws.profile_read()[1]
+    plans[0].run()
+    stream.synchronize()
+    launches_per_step = ws.profile_read()[1] - l0
+    for i in range(warmup):
+      step(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if clocks else None
+    if sampler:
+      sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+      step(i)
+    e1.record(stream)
+    barrier()
+    clk = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+
+    # the kernels' shares of the pipelined step: end-of-kernel stamps, programmatic dependent launch on
+    prof_steps = min(steps, 300)
+    ws.profile(2)
+    for i in range(prof_steps + 1):
+      plans[i % ring].run()
+    shares, chunks = ws.profile_read_stamps()
+    ws.profile(0)
+    steps_counted = max(1, chunks) / max(1, launches_per_step // 3)
+    shares = [x / steps_counted for x in shares]
+    # ... and their durations run one at a time (cudaEvents between the launches, no overlap)
+    ws.profile(1)
+    for i in range(prof_steps):
+      plans[i % ring].run()
+    serial, _ = ws.profile_read()
+    ws.profile(0)
+    serial = [x / prof_steps for x in serial]
+  t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_step = float(t.item()) / steps
+  del plans
+  ws.close()
+  return dict(ms_step=ms_step, launches_per_step=launches_per_step, clocks=clk, shares=shares, serial=serial, ring=ring,
+              set_bytes=set_bytes, src_bytes=src_bytes, out_bytes=out_bytes, graph=graphs is not None)
+
+
+def e2e_measure(guidance, torch, dist, host_inp, args, local_rank, world, compact, ws):
+  """The same metric through the reference-facing call with HOST buffers: se3ds_reproject_host copies the inputs
+  from pinned memory, runs the kernels and copies the guidance back, all inside the timed region."""
+  out = {}
+  kw = dict(mask_frames=1, out=out, device=local_rank, workspace=ws, compact=compact)
+  for _ in range(3):
+    guidance.reproject_host(host_inp['rgb'], host_inp['depth'], host_inp['src_pos'], host_inp['tgt_pos'], **kw)
   if world > 1:
     dist.barrier()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  steps = min(args.steps, 200)
-  e0.record()
-  for _ in range(steps):
-    out = step()
-  e1.record()
   torch.cuda.synchronize()
-  ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+  t0 = time.perf_counter()
+  for _ in range(args.e2e_steps):
+    guidance.reproject_host(host_inp['rgb'], host_inp['depth'], host_inp['src_pos'], host_inp['tgt_pos'], **kw)
+  torch.cuda.synchronize()
+  ms = (time.perf_counter() - t0) / args.e2e_steps * 1e3
+  t = torch.tensor([ms], device=torch.device('cuda', local_rank), dtype=torch.float64)
   if world > 1:
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-  if rank == 0:
-    hw = h * 2 * h
-    gathered = sum(v.numel() * v.element_size() for k, v in out.items() if torch.is_tensor(v))
-    print(json.dumps({
-        'metric': 'reprojected panoramas/s', 'value': n * p / (ms.item() * 1e-3), 'unit': 'panos/s', 'n_gpus': world,
-        'steps': steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms.item(), 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.config, cfg, args.dist), 'sharding': 'jobs block-partitioned over ranks',
-                   'collective': 'all_gather_into_tensor of proj_image/proj_depth/proj_mask + 4-float bin all-reduce',
-                   'gathered_bytes_per_rank': gathered},
-        'mpoints_per_s': n * s * p * hw / (ms.item() * 1e-3) / 1e6}), flush=True)
-  if world > 1:
-    dist.barrier()
-    dist.destroy_process_group()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  h2d = sum(host_inp[k].numel() * host_inp[k].element_size() for k in host_inp)
+  d2h = sum(v.numel() * v.element_size() for v in out.values())
+  return float(t.item()), h2d, d2h, out
+
+
+def copy_ceiling(torch, dev, h2d_bytes, d2h_bytes, reps=10):
+  """What the host link gives this rank for the same byte counts: pinned H2D and D2H copies alone, each timed by itself."""
+  hb = torch.empty(max(h2d_bytes, d2h_bytes), dtype=torch.uint8, pin_memory=True)
+  db = torch.empty(max(h2d_bytes, d2h_bytes), dtype=torch.uint8, device=dev)
+  res = {}
+  for name, nbytes, fn in (('h2d_gbs', h2d_bytes, lambda: db[:h2d_bytes].copy_(hb[:h2d_bytes], non_blocking=True)),
+                           ('d2h_gbs', d2h_bytes, lambda: hb[:d2h_bytes].copy_(db[:d2h_bytes], non_blocking=True))):
+    fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+      fn()
+    torch.cuda.synchronize()
+    res[name] = nbytes * reps / (time.perf_counter() - t0) / 1e9
+  return res
+
+
+def parity_vs_libm(guidance, torch, inp, dev):
+  """GPU result of one item of the workload against the literal numpy (libm) restatement: the two float32
+  pipelines differ only where an ulp of a transcendental moves a point across a pixel border
+  (tests/test_oracle_disagreement.py).  Part of the CPU-baseline leg (the only place bench.py runs oracle/)."""
+  from oracle import ref_numpy as R
+  one = {k: v[:1] for k, v in inp.items()}
+  t = {k: torch.as_tensor(v).to(dev) for k, v in one.items()}
+  out = guidance.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1)
+  torch.cuda.synchronize()
+  image, depth, mask, _ = R.reproject_trajectory(one['rgb'], one['depth'], one['src_pos'], one['tgt_pos'][:, 0], mask_first_frame=True)
+  gd, gi, gm = (out[k].cpu().numpy() for k in ('proj_depth', 'proj_image', 'proj_mask'))
+  bad_d = np.abs(gd - depth) > 1e-5 * np.abs(depth) + 1e-7
+  return {'pixels': int(depth.size), 'depth_differs': float(bad_d.mean()), 'rgb_differs': float(np.any(gi != image, axis=-1).mean()),
+          'mask_differs': float((gm != mask).mean()),
+          'note': 'GPU (canonical float32 arithmetic) vs numpy restatement (libm); differences sit on pixel borders'}
 
 
 # ------------------------------------------------------------------------------------------
@@ -237,19 +391,15 @@ def main():
   ap.add_argument('--dist', default='room', choices=['room', 'rand'])
   ap.add_argument('--graph', action='store_true', help='CUDA-graph replay instead of stream launches (measured slower: '
                   'stream launches keep the programmatic dependent launch overlap)')
-  ap.add_argument('--no-graph', action='store_true', help='(default) plain stream launches')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-extras', action='store_true', help='skip the sub-records of the other configs / modes')
   ap.add_argument('--e2e-steps', type=int, default=20)
   ap.add_argument('--chunk-mb', type=int, default=0, help='workspace L2 chunk size (0 = library default)')
   ap.add_argument('--n-override', type=int, default=0, help='override the batch size of the config (memory-bounded runs)')
   ap.add_argument('--key64', action='store_true', help='force the 64-bit packed depth|index z-buffer key')
-  ap.add_argument('--streams', type=int, default=1, help='independent batches alternate between this many (workspace, stream) '
-                  'pairs, the way a server overlaps independent requests; 1 = every step on one stream')
   ap.add_argument('--lanes', type=int, default=0, help='concurrent chunk lanes of one call (0 = library default, 2)')
   ap.add_argument('--lane-chunks', type=int, default=0, help='minimum chunks per lane (0 = library default, 2)')
   ap.add_argument('--no-pdl', action='store_true', help='disable programmatic dependent launch')
-  ap.add_argument('--sharded', action='store_true', help='strong scaling: shard the jobs of ONE call over the ranks and '
-                  'all-gather the guidance tensors (NCCL) inside the timed step (se3ds_b200.parallel)')
   ap.add_argument('--proj-mode', type=int, default=1, help='0 canonical projection only, 1 certified fast path (default)')
   args = ap.parse_args()
   cfg = dict(CONFIGS[args.config])
@@ -280,170 +430,99 @@ def main():
 
   n, s, p, h = cfg['n'], cfg['s'], cfg['p'], cfg['h']
   w = 2 * h
-  if args.sharded:
-    run_sharded(args, cfg, world, rank, local_rank, dev)
-    return
-  src_bytes, out_bytes = alg_bytes(cfg)
-  # ring of distinct input/output sets larger than 2x L2, so every step starts cold in L2
-  set_bytes = src_bytes + out_bytes
-  ring = max(2, min(16, -(-2 * L2_BYTES // set_bytes) + 1))
-  nst = 1 if args.graph else max(1, args.streams)
-  wss = []
-  for _ in range(nst):
-    w_ = _lib.Workspace(local_rank, 0, args.chunk_mb << 20)
-    w_.projection_mode(args.proj_mode)
-    w_.pdl(not args.no_pdl)
-    if args.lanes:
-      w_.lanes(args.lanes, 0, args.lane_chunks)
-    wss.append(w_)
-  ws = wss[0]
-  plans = []
-  for r in range(ring):
-    # every set differs only in its seed; large configs reuse one generated item per set
-    gen_n = min(n, 8)
-    inp = synth.make_inputs(gen_n, s, p, h, seed=1000 * rank + r, dist=args.dist, sweep=cfg['sweep'])
-    if gen_n < n:
-      inp = {k: np.concatenate([v] * (n // gen_n), axis=0) for k, v in inp.items()}
-    t = {k: torch.as_tensor(v).to(dev) for k, v in inp.items()}
-    plans.append([guidance.prepare(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, workspace=w_,
-                                   key64=args.key64, inputs_ready=True) for w_ in wss])
-  host_inp = {k: torch.as_tensor(v).pin_memory() for k, v in inp.items()}
-
-  streams = [torch.cuda.Stream(dev) for _ in range(nst)]
-  stream = streams[0]
-
-  def launches_so_far():
-    return sum(w_.profile_read()[1] for w_ in wss)
-
-  with torch.cuda.stream(stream):
-    for row in plans:  # grows the workspaces, uploads tables
-      for pl in row:
-        pl.run()
-    stream.synchronize()
-    graphs = None
-    if args.graph:
-      graphs = []
-      for row in plans:
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=stream):
-          row[0].run()
-        graphs.append(g)
-    launches_a = launches_so_far()
-    plans[0][0].run()
-    stream.synchronize()
-    launches0 = launches_so_far()
-    launches_per_step = launches0 - launches_a
-
-    def step(i):
-      if graphs is not None:
-        graphs[i % ring].replay()
-      elif nst == 1:
-        plans[i % ring][0].run()
-      else:
-        with torch.cuda.stream(streams[i % nst]):
-          plans[i % ring][i % nst].run()
-
-    def barrier():
-      stream.synchronize()
-      if world > 1:
-        dist.barrier()
-      torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-      step(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for k in range(1, nst):
-      streams[k].wait_event(e0)
-    for i in range(args.steps):
-      step(i)
-    for k in range(1, nst):  # the timed region ends when every stream has finished its steps
-      done = torch.cuda.Event()
-      done.record(streams[k])
-      stream.wait_event(done)
-    e1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    launches_timed = launches_so_far() - launches0 if graphs is None else None
-
-    # per-kernel durations (cudaEvents between the launches, plain stream launches)
-    ws.profile(True)
-    prof_steps = min(args.steps, 200)
-    for i in range(prof_steps):
-      plans[i % ring][0].run()
-    kms, _ = ws.profile_read()
-    ws.profile(False)
-    kms = [x / prof_steps for x in kms]
-
-  t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  ms_total = float(t.item())
-  ms_step = ms_total / args.steps
+  mods = (guidance, synth, _lib, torch, dist)
+  m = gpu_measure(*mods, cfg, args, dev, local_rank, world, rank, args.steps, args.warmup, key64=args.key64, clocks=True)
+  ms_step = m['ms_step']
+  src_bytes, out_bytes = m['src_bytes'], m['out_bytes']
   panos_per_s = world * n * p / (ms_step * 1e-3)
   mpoints = world * n * s * p * h * w / (ms_step * 1e-3) / 1e6
 
   # e2e: host buffers, H2D + kernels + D2H inside the C-ABI call (se3ds_reproject_host)
-  e2e_out = {}
-  for _ in range(3):
-    guidance.reproject_host(host_inp['rgb'], host_inp['depth'], host_inp['src_pos'], host_inp['tgt_pos'],
-                            mask_frames=1, out=e2e_out, device=local_rank, workspace=ws)
-  if world > 1:
-    dist.barrier()
-  torch.cuda.synchronize()
-  t0 = time.perf_counter()
-  for _ in range(args.e2e_steps):
-    guidance.reproject_host(host_inp['rgb'], host_inp['depth'], host_inp['src_pos'], host_inp['tgt_pos'],
-                            mask_frames=1, out=e2e_out, device=local_rank, workspace=ws)
-  torch.cuda.synchronize()
-  e2e_ms = (time.perf_counter() - t0) / args.e2e_steps * 1e3
-  t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  e2e_ms = float(t.item())
-  h2d = sum(host_inp[k].numel() * host_inp[k].element_size() for k in host_inp)
-  d2h = sum(v.numel() * v.element_size() for v in e2e_out.values())
+  gen_n = min(n, 8)
+  inp = synth.make_inputs(gen_n, s, p, h, seed=1000 * rank + 99, dist=args.dist, sweep=cfg['sweep'])
+  if gen_n < n:
+    inp = {k: np.concatenate([v] * (n // gen_n), axis=0) for k, v in inp.items()}
+  host_inp = {k: torch.as_tensor(v).pin_memory() for k, v in inp.items()}
+  ews = _lib.Workspace(local_rank, 0, args.chunk_mb << 20)
+  e2e_ms, h2d, d2h, _ = e2e_measure(guidance, torch, dist, host_inp, args, local_rank, world, False, ews)
+  e2e_c_ms, h2d_c, d2h_c, _ = e2e_measure(guidance, torch, dist, host_inp, args, local_rank, world, True, ews)
+  ews.close()
+  ceiling = copy_ceiling(torch, dev, h2d, d2h)
+
+  extras = {}
+  if not args.no_extras:
+    # other configs / modes, short runs (sub-records; the headline stays the config above)
+    def sub(name, c, **kw):
+      r = gpu_measure(*mods, c, args, dev, local_rank, world, rank, kw.pop('steps'), 5, **kw)
+      sb, ob = alg_bytes(c)
+      hw = c['h'] * 2 * c['h']
+      return {'workload': workload_name(name, c, args.dist), 'ms_per_step': r['ms_step'], 'steps': kw.get('steps'),
+              'panos_per_s': world * c['n'] * c['p'] / (r['ms_step'] * 1e-3),
+              'mpoints_per_s': world * c['n'] * c['s'] * c['p'] * hw / (r['ms_step'] * 1e-3) / 1e6,
+              'roofline_step_frac': (sb + ob) / (r['ms_step'] * 1e-3) / 1e9 / measured_peak_gbs()[0],
+              'kernel_shares_ms': r['shares']}
+    if args.config == 'c2' and not args.key64:
+      extras['c2_key64'] = sub('c2', CONFIGS['c2'], steps=300, key64=True)
+      extras['c2_key64']['note'] = '64-bit packed depth|point-index z-buffer key (what return_winner uses)'
+      extras['c2_compact'] = sub('c2', CONFIGS['c2'], steps=300, compact=True)
+      extras['c2_compact']['note'] = 'SE3DS_FLAG_COMPACT_OUT: uint8 colours + float32 depth leave the resolve kernel (7 B instead of 20 B per pixel)'
+    if args.config == 'c2':
+      extras['c1'] = sub('c1', CONFIGS['c1'], steps=300)
+      extras['c3'] = sub('c3', CONFIGS['c3'], steps=30)
+      extras['c4'] = sub('c4', CONFIGS['c4'], steps=60)
+      c5 = dict(CONFIGS['c5'], n=4)
+      extras['c5_n4'] = sub('c5 (batch reduced from 64 to 4 per GPU)', c5, steps=6)
+    if world > 1:
+      extras['sharded_c4'] = sharded_record(args, world, rank, dev)
 
   if rank == 0:
     peak, peak_kind = measured_peak_gbs()
     names = ['splat_depth_kernel', 'splat_feat_kernel', 'resolve_kernel']
     kalg = [src_bytes, 0, out_bytes]
+    kms = m['shares'] if sum(m['shares']) > 0 else m['serial']
     dom = max(range(3), key=lambda i: kms[i])
     traffic = committed_traffic()
-    step_gbs = (src_bytes + out_bytes) / (sum(kms) * 1e-3) / 1e9
     line = {
         'metric': 'reprojected panoramas/s', 'value': panos_per_s, 'unit': 'panos/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(args.config, cfg, args.dist), 'per_gpu_batch': n,
-                   'cache': f'inputs+outputs rotate over a ring of {ring} sets ({ring * set_bytes >> 20} MiB > 2x L2)',
-                   'launch': 'cuda_graph_replay' if graphs is not None else 'stream launches (programmatic dependent launch)', 'parallelism': f'dp{world}',
-                   'chunk_mb': args.chunk_mb or 'default', 'streams': nst, 'lanes': args.lanes or 'default', 'inputs_ready_flag': True, 'pdl': not args.no_pdl, 'zbuffer_key': 'u64 depth|index' if args.key64 else 'u32 depth (no winner index requested)',
+                   'cache': f"inputs+outputs rotate over a ring of {m['ring']} sets ({m['ring'] * m['set_bytes'] >> 20} MiB > 2x L2)",
+                   'launch': 'cuda_graph_replay' if m['graph'] else 'stream launches (programmatic dependent launch)',
+                   'parallelism': f'dp{world}', 'chunk_mb': args.chunk_mb or 'default', 'lanes': args.lanes or 'default',
+                   'inputs_ready_flag': True, 'pdl': not args.no_pdl,
+                   'zbuffer_key': 'u64 depth|index' if args.key64 else 'u32 depth (no winner index requested)',
                    'projection': 'certified_fast+canonical_fallback' if args.proj_mode == 1 else 'canonical'},
         'mpoints_per_s': mpoints,
         'e2e': {'value': world * n * p / (e2e_ms * 1e-3), 'unit': 'panos/s', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms},
-        'gpu_launches': (launches_per_step * args.steps if launches_timed is None else launches_timed),
-        'clocks': clocks,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms,
+                'per_rank_gbs': {'h2d': h2d / (e2e_ms * 1e-3) / 1e9, 'd2h': d2h / (e2e_ms * 1e-3) / 1e9,
+                                 'note': 'bytes of the step / time of the step (uploads, kernels and downloads overlap)'},
+                'host_link_ceiling_gbs': ceiling,
+                'compact_out': {'value': world * n * p / (e2e_c_ms * 1e-3), 'unit': 'panos/s', 'ms_per_step': e2e_c_ms,
+                                'h2d_bytes_per_step': h2d_c, 'd2h_bytes_per_step': d2h_c,
+                                'note': 'opt-in SE3DS_FLAG_COMPACT_OUT: uint8 colours + float32 depth come back (mask = 0 < depth < 1); '
+                                        'se3ds_expand_guidance restores the float32 tensors bit for bit'}},
+        'gpu_launches': m['launches_per_step'] * args.steps,
+        'clocks': m['clocks'],
         'roofline': {'bound': 'hbm', 'kernel': names[dom], 'achieved': kalg[dom] / (kms[dom] * 1e-3) / 1e9, 'peak': peak,
                      'unit': 'GB/s', 'frac': kalg[dom] / (kms[dom] * 1e-3) / 1e9 / peak, 'peak_kind': peak_kind,
                      'traffic': (traffic or {}).get(names[dom]), 'ms': kms[dom],
-                     'note': ('splat_depth is bound by instruction issue (ncu: ~80% issue-active, DRAM ~12%); '
+                     'how': 'share of the pipelined step: last end-of-kernel %globaltimer stamp minus that of the kernel before it '
+                            '(se3ds_ws_profile mode 2); the shares add up to the step',
+                     'note': ('splat_depth is bound by instruction issue and latency, not by HBM (ncu: profiles/r02_*); '
                               'resolve is the HBM-bound kernel, see roofline_hbm_kernel') if dom == 0 else ''},
         'roofline_hbm_kernel': {'bound': 'hbm', 'kernel': names[2], 'achieved': kalg[2] / (kms[2] * 1e-3) / 1e9,
                                 'peak': peak, 'unit': 'GB/s', 'frac': kalg[2] / (kms[2] * 1e-3) / 1e9 / peak,
                                 'traffic': (traffic or {}).get(names[2]), 'ms': kms[2]},
-        'roofline_step': {'bound': 'hbm', 'achieved': step_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': step_gbs / peak,
-                          'alg_bytes': src_bytes + out_bytes, 'ms_kernels': sum(kms),
-                          'frac_of_timed_step': (src_bytes + out_bytes) / (ms_step * 1e-3) / 1e9 / peak},
-        'kernels': [{'name': names[i], 'ms': kms[i], 'alg_bytes': kalg[i]} for i in range(3)],
+        'roofline_step': {'bound': 'hbm', 'achieved': (src_bytes + out_bytes) / (ms_step * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                          'frac': (src_bytes + out_bytes) / (ms_step * 1e-3) / 1e9 / peak, 'alg_bytes': src_bytes + out_bytes},
+        'kernels': [{'name': names[i], 'ms': kms[i], 'ms_alone': m['serial'][i], 'alg_bytes': kalg[i]} for i in range(3)],
+        'extra': extras,
     }
     if world == 1 and not args.no_cpu_baseline:
       line['cpu_baseline'] = cpu_baseline_single(cfg, args.dist)
+      line['parity_vs_libm'] = parity_vs_libm(guidance, torch, inp, dev)
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.barrier()

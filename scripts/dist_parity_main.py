@@ -24,13 +24,14 @@ def main():
       ref = guidance.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], per_job_bin=(mode == 'job'),
                                return_winner=True)
       ref = {k: v.clone() for k, v in ref.items()}
-      got = parallel.reproject_sharded(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], bin_mode=mode,
-                                       return_winner=True)
-      for k in ('proj_image', 'proj_depth', 'proj_mask', 'winner'):
-        same = torch.equal(got[k], ref[k])
-        ok &= same
-        if not same:
-          print(f'rank {rank}: MISMATCH {k} n={n} s={s} p={p} mode={mode}', flush=True)
+      for wire, chunks in (('compact', 0), ('compact', 1), ('f32', 0)):   # pipelined compact gather, one piece, float32 wire
+        got = parallel.reproject_sharded(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], bin_mode=mode,
+                                         return_winner=True, wire=wire, chunks=chunks)
+        for k in ('proj_image', 'proj_depth', 'proj_mask', 'winner'):
+          same = torch.equal(got[k], ref[k])
+          ok &= same
+          if not same:
+            print(f'rank {rank}: MISMATCH {k} n={n} s={s} p={p} mode={mode} wire={wire} chunks={chunks}', flush=True)
   flag = torch.tensor([int(ok)], device='cuda')
   dist.all_reduce(flag, op=dist.ReduceOp.MIN)
   if rank == 0:

@@ -13,7 +13,7 @@ except Exception as e:
 PY
 }
 python -m pytest tests -m gpu -q 2>&1 | tail -${2:-6}
-python bench.py --steps 1000 --warmup 20 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${TAG}_room.json 2> gpurun_out/${TAG}_room.err; summ gpurun_out/${TAG}_room.json
-python bench.py --steps 1000 --warmup 20 --no-cpu-baseline --e2e-steps 1 --dist rand > gpurun_out/${TAG}_rand.json 2> gpurun_out/${TAG}_rand.err; summ gpurun_out/${TAG}_rand.json
-python bench.py --steps 500 --warmup 20 --no-cpu-baseline --e2e-steps 1 --key64 > gpurun_out/${TAG}_k64.json 2> gpurun_out/${TAG}_k64.err; summ gpurun_out/${TAG}_k64.json
-python bench.py --config c3 --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${TAG}_c3.json 2> gpurun_out/${TAG}_c3.err; summ gpurun_out/${TAG}_c3.json
+python bench.py --steps 1000 --warmup 20 --no-cpu-baseline --e2e-steps 1 --no-extras > gpurun_out/${TAG}_room.json 2> gpurun_out/${TAG}_room.err; summ gpurun_out/${TAG}_room.json
+python bench.py --steps 1000 --warmup 20 --no-cpu-baseline --e2e-steps 1 --no-extras --dist rand > gpurun_out/${TAG}_rand.json 2> gpurun_out/${TAG}_rand.err; summ gpurun_out/${TAG}_rand.json
+python bench.py --steps 500 --warmup 20 --no-cpu-baseline --e2e-steps 1 --no-extras --key64 > gpurun_out/${TAG}_k64.json 2> gpurun_out/${TAG}_k64.err; summ gpurun_out/${TAG}_k64.json
+python bench.py --config c3 --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 --no-extras > gpurun_out/${TAG}_c3.json 2> gpurun_out/${TAG}_c3.err; summ gpurun_out/${TAG}_c3.json

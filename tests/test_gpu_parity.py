@@ -812,3 +812,42 @@ def test_guidance_memory_pose_sweep_and_states(mods):
   c = mem3(poses[:2])
   for k in a:
     assert torch.equal(a[k], c[k]), k
+
+
+@pytest.mark.parametrize('n,s,p,h,chunk_mb,per_job', [(2, 1, 1, 64, 0, False), (3, 2, 2, 32, 1, False), (2, 1, 3, 37, 0, True)])
+def test_compact_output_expands_to_the_float32_contract(mods, n, s, p, h, chunk_mb, per_job):
+  """SE3DS_FLAG_COMPACT_OUT (uint8 colours + float32 depth, 7 B instead of 20 B per pixel) followed by
+  se3ds_expand_guidance is bit-identical to the float32 outputs: single chunk, several chunks with the
+  owner-pixel patch, per-job bins, the host entry point, and the export / apply bin protocol."""
+  g, lib = mods['g'], mods['lib']
+  inp = mods['synth'].make_inputs(n, s, p, h, seed=51 + h, dist='rand', sweep=p > 1)
+  t = _cuda(inp)
+  ws = lib.Workspace(0, 0, chunk_mb << 20) if chunk_mb else lib.Workspace(0)
+  kw = dict(mask_frames=1, per_job_bin=per_job, workspace=ws)
+  want = {k: v.clone() for k, v in g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], **kw).items()}
+  got = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], compact=True, **kw)
+  assert got['proj_rgb_u8'].dtype == torch.uint8 and 'proj_mask' not in got
+  got = g.expand_guidance({k: v.clone() for k, v in got.items()})
+  for k in ('proj_image', 'proj_depth', 'proj_mask'):
+    assert torch.equal(got[k], want[k]), k
+  # host entry point: compact tensors come back over PCIe
+  hout = g.reproject_host(inp['rgb'], inp['depth'], inp['src_pos'], inp['tgt_pos'], mask_frames=1, per_job_bin=per_job,
+                          compact=True, workspace=ws)
+  exp = g.expand_guidance({k: v.cuda() for k, v in hout.items()})
+  for k in ('proj_image', 'proj_depth', 'proj_mask'):
+    assert torch.equal(exp[k], want[k]), k
+  # a job map re-orders the jobs on the way
+  j = n * p
+  perm = torch.randperm(j)
+  shuffled = {'proj_rgb_u8': got['proj_rgb_u8'][perm].contiguous(), 'proj_depth': got['proj_depth'][perm].contiguous()}
+  back = g.expand_guidance(shuffled, job_map=perm.to(torch.int32))   # slot s holds job perm[s]
+  for k in ('proj_image', 'proj_depth', 'proj_mask'):
+    assert torch.equal(back[k], want[k]), k
+  if not per_job:  # export / apply bin with compact tensors
+    a = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, export_bin=True, compact=True, workspace=ws)
+    a = {k: v.clone() for k, v in a.items()}
+    g.apply_bin(a.pop('bin'), a)
+    a = g.expand_guidance(a)
+    for k in ('proj_image', 'proj_depth', 'proj_mask'):
+      assert torch.equal(a[k], want[k]), k
+  ws.close()

@@ -226,6 +226,27 @@ def sharded_record(args, world, rank, dev, steps=60, warmup=5):
       dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     rec[label] = {'ms_per_step': ms.item(), 'panos_per_s': n * p / (ms.item() * 1e-3),
                   'bytes_held_per_rank': sum(v.numel() * v.element_size() for v in out.values() if torch.is_tensor(v))}
+  # the prepared (serving) form: buffers, kernel calls and maps built once, run() repeated
+  for label, kw in (('prepared_gather_expand', dict(gather=True, expand=True)), ('prepared_gather_compact', dict(gather=True, expand=False)),
+                    ('prepared_local', dict(gather=False, expand=False))):
+    plan = parallel.ShardedReprojection(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, pieces=args.pieces, **kw)
+    for _ in range(warmup):
+      out = plan.run()
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      out = plan.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rec[label] = {'ms_per_step': ms.item(), 'panos_per_s': n * p / (ms.item() * 1e-3), 'pieces': plan.npieces,
+                  'bytes_held_per_rank': sum(v.numel() * v.element_size() for v in out.values() if torch.is_tensor(v))}
+    del plan
   return rec
 
 
@@ -400,6 +421,7 @@ def main():
   ap.add_argument('--lanes', type=int, default=0, help='concurrent chunk lanes of one call (0 = library default, 2)')
   ap.add_argument('--lane-chunks', type=int, default=0, help='minimum chunks per lane (0 = library default, 2)')
   ap.add_argument('--no-pdl', action='store_true', help='disable programmatic dependent launch')
+  ap.add_argument('--pieces', type=int, default=2, help='pieces of the pipelined gather in the sharded c4 sub-record')
   ap.add_argument('--proj-mode', type=int, default=1, help='0 canonical projection only, 1 certified fast path (default)')
   args = ap.parse_args()
   cfg = dict(CONFIGS[args.config])

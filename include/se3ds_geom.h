@@ -166,7 +166,9 @@ int se3ds_project_cloud(se3ds_ws* ws, const float* coords, const void* feats, in
  *   project_feats_to_equirectangular (pano_utils.py:117-161 + point_cloud_utils.py:90-183) ->
  *   guidance assembly (models.py:282-293; gan_manager.py:484-494)
  * without materialising the cloud.
- *   rgb (N,S,H,W,3) rgb_dtype (U8, or I32 with values in [-1,255]); depth (N,S,H,W) f32;
+ *   rgb (N,S,H,W,3) rgb_dtype (U8, or I32 with values in [-2048, 2048] -- the per-channel maxima are reduced in
+ *   float16, exact for those integers; the reference only produces [-1, 255]; the Python shim refuses anything
+ *   else); depth (N,S,H,W) f32;
  *   src_pos (N,S,3) f32; tgt_pos (N,P,3) f32 (device).  Jobs are (n,p) row-major, J = N*P.
  *   proj_image (J,H,W,3) f32 = clip(rgb/255,0,1); proj_depth (J,H,W,1) f32; proj_mask (J,H,W,1)
  *   f32 in {0,1}; winner_out (J,H,W) int32 or NULL: index s*H*W + r*W + c of the nearest valid

@@ -32,6 +32,19 @@ def main():
           ok &= same
           if not same:
             print(f'rank {rank}: MISMATCH {k} n={n} s={s} p={p} mode={mode} wire={wire} chunks={chunks}', flush=True)
+    if (n * p) % dist.get_world_size() == 0:   # the prepared (serving) form
+      for mode in ('call', 'job'):
+        ref = guidance.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], per_job_bin=(mode == 'job'))
+        ref = {k: v.clone() for k, v in ref.items()}
+        for pieces in (1, 2):
+          plan = parallel.ShardedReprojection(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], bin_mode=mode, pieces=pieces)
+          for _ in range(2):
+            got = plan.run()
+          for k in ('proj_image', 'proj_depth', 'proj_mask'):
+            same = torch.equal(got[k], ref[k])
+            ok &= same
+            if not same:
+              print(f'rank {rank}: MISMATCH prepared {k} n={n} s={s} p={p} mode={mode} pieces={pieces}', flush=True)
   flag = torch.tensor([int(ok)], device='cuda')
   dist.all_reduce(flag, op=dist.ReduceOp.MIN)
   if rank == 0:

@@ -52,6 +52,14 @@ def _prep(rgb, depth, src_pos, tgt_pos, to_device: bool):
       raise ValueError(f'rgb must be uint8 or int32 with values in [-1, 255], got {rgb.dtype}')
   n, s, h, w, _ = rgb.shape
   assert w == 2 * h, 'Expected equirectangular input images'
+  if rgb.dtype == torch.int32 and rgb.numel():
+    # The fused kernels reduce the colours in float16 (one 8-byte vector reduction per point), which holds the
+    # integers of [-2048, 2048] exactly -- every value the reference produces lies in [-1, 255].  Anything else
+    # would be rounded silently, so it is refused here (one reduction and a sync, int32 inputs only); arbitrary
+    # float / int features go through pano_utils.project_feats_to_equirectangular, which keeps float32.
+    lo, hi = torch.aminmax(rgb)
+    if int(lo) < -2048 or int(hi) > 2048:
+      raise ValueError(f'int32 rgb values must lie in [-2048, 2048] for the fused path, got [{int(lo)}, {int(hi)}]')
   depth = conv(depth, 'depth').to(torch.float32).reshape(n, s, h, w).contiguous()
   src_pos = conv(src_pos, 'src_pos').to(torch.float32).reshape(n, s, 3).contiguous()
   tgt_pos = conv(tgt_pos, 'tgt_pos').to(torch.float32)
@@ -146,22 +154,34 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
             unproject_void: int = constants.INVALID_RGB_VALUE, project_void: int = constants.INVALID_RGB_VALUE,
             filter_void: bool = False, per_job_bin: bool = False, return_winner: bool = False,
             workspace: Optional[_lib.Workspace] = None, key64: bool = False,
-            inputs_ready: bool = False, compact: bool = False) -> PreparedReprojection:
-  """Same arguments as `reproject`; allocates the outputs once and returns a PreparedReprojection.
-  inputs_ready=True promises that the input tensors are not written by whatever kernel runs right
-  before each `run()` on the stream (SE3DS_FLAG_INPUTS_READY)."""
+            inputs_ready: bool = False, compact: bool = False, out: Optional[Dict[str, torch.Tensor]] = None,
+            bin_out: Optional[torch.Tensor] = None) -> PreparedReprojection:
+  """Same arguments as `reproject`; allocates the outputs once (or takes the dense, contiguous tensors of `out`)
+  and returns a PreparedReprojection.  inputs_ready=True promises that the input tensors are not written by
+  whatever kernel runs right before each `run()` on the stream (SE3DS_FLAG_INPUTS_READY).  bin_out: a (5,)
+  float32 device tensor that receives the call's reject bin instead of its owner pixel (see `reproject`)."""
   rgb, depth, src_pos, tgt_pos = _prep(rgb, depth, src_pos, tgt_pos, True)
   n, s, h, w, _ = rgb.shape
   p = tgt_pos.shape[1]
   j = n * p
   dev = rgb.device
+  given = out or {}
+  def buf(name, shape, dtype=torch.float32):
+    t = given.get(name)
+    if t is not None:
+      if tuple(t.shape) != shape or t.dtype != dtype or t.device != dev or not t.is_contiguous():
+        raise ValueError(f'out[{name!r}] must be a contiguous {dtype} tensor of shape {shape} on {dev}')
+      return t
+    return torch.empty(shape, dtype=dtype, device=dev)
   if compact:
-    out = dict(proj_rgb_u8=torch.empty((j, h, w, 3), dtype=torch.uint8, device=dev), proj_depth=torch.empty((j, h, w, 1), device=dev))
+    out = dict(proj_rgb_u8=buf('proj_rgb_u8', (j, h, w, 3), torch.uint8), proj_depth=buf('proj_depth', (j, h, w, 1)))
   else:
-    out = dict(proj_image=torch.empty((j, h, w, 3), device=dev), proj_depth=torch.empty((j, h, w, 1), device=dev),
-               proj_mask=torch.empty((j, h, w, 1), device=dev))
+    out = dict(proj_image=buf('proj_image', (j, h, w, 3)), proj_depth=buf('proj_depth', (j, h, w, 1)),
+               proj_mask=buf('proj_mask', (j, h, w, 1)))
   if return_winner:
-    out['winner'] = torch.empty((j, h, w), dtype=torch.int32, device=dev)
+    out['winner'] = buf('winner', (j, h, w), torch.int32)
+  if bin_out is not None:
+    out['bin'] = bin_out
   flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
            (_lib.FLAG_KEY64 if key64 else 0) | (_lib.FLAG_INPUTS_READY if inputs_ready else 0) |
            (_lib.FLAG_COMPACT_OUT if compact else 0))
@@ -169,7 +189,7 @@ def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_S
   args = (ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
           n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),
           int(project_void), flags, _lib.ptr(out['proj_rgb_u8'] if compact else out['proj_image']), _lib.ptr(out['proj_depth']),
-          _lib.ptr(out.get('proj_mask')), _lib.ptr(out.get('winner')), None)
+          _lib.ptr(out.get('proj_mask')), _lib.ptr(out.get('winner')), _lib.ptr(bin_out))
   return PreparedReprojection((rgb, depth, src_pos, tgt_pos), out, args, ws)
 
 
@@ -189,11 +209,11 @@ def expand_guidance(out: Dict[str, torch.Tensor], job_map: Optional[torch.Tensor
   _lib.check(_lib.load().se3ds_expand_guidance(_lib.ptr(rgb8), _lib.ptr(depth), j, h * w, _lib.ptr(job_map), _lib.ptr(image),
                                                _lib.ptr(depth_out), _lib.ptr(mask), _lib.stream_handle(dev)))
   out['proj_image'], out['proj_mask'] = image, mask
-  if depth_out is not None:
+  if depth_out is not None:  # everything in the result is in job order: the compact colours are dropped, not re-ordered
     out['proj_depth'] = depth_out
+    out.pop('proj_rgb_u8')
     if 'winner' in out:
       out['winner'] = torch.empty_like(out['winner']).index_copy_(0, job_map.long(), out['winner'])
-    out['proj_rgb_u8'] = torch.empty_like(rgb8).index_copy_(0, job_map.long(), rgb8)
   return out
 
 

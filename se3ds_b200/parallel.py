@@ -223,3 +223,101 @@ def reproject_sharded(rgb, depth, src_pos, tgt_pos, *, group=None, bin_mode: str
     result = expand_fn(result) if job_map is None else expand_fn(result, job_map=job_map.to(dev))
   result['job_range'] = (lo, hi)
   return result
+
+
+class ShardedReprojection(object):
+  """`reproject_sharded` with everything that does not depend on the data done once (the serving form: the same
+  shapes call after call).  The gather buffers, the prepared kernel calls of every piece (one C-ABI call each), the
+  slot -> job map and the bin vector are built in __init__; `run()` is: per piece one prepared call and its in-place
+  all-gathers (async, they travel while the next piece renders), one 5-float all-reduce for the reject bin, the bin
+  patch and -- with expand=True -- one expand kernel that writes the float32 tensors in job order.
+
+  Restrictions of the prepared form: the job count divides by the world size, bin_mode 'call' or 'job', compact wire.
+  The tensors passed in are kept and read in place by every run()."""
+
+  def __init__(self, rgb, depth, src_pos, tgt_pos, *, group=None, bin_mode: str = 'call', pieces: int = 2,
+               gather: bool = True, expand: bool = True, depth_scale: float = constants.DEPTH_SCALE, mask_frames: int = 0,
+               **conv):
+    from . import guidance
+    self.g = guidance
+    self.group, self.bin_mode, self.gather, self.expand, self.depth_scale = group, bin_mode, gather, expand, depth_scale
+    self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+    self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rgb = torch.as_tensor(rgb)
+    if rgb.dim() == 4:
+      rgb = rgb[:, None]
+    n, s, h, w, _ = rgb.shape
+    tgt_pos = torch.as_tensor(tgt_pos).reshape(n, -1, 3)
+    p = tgt_pos.shape[1]
+    jobs = n * p
+    if bin_mode not in ('call', 'job') or jobs % self.world:
+      raise ValueError('the prepared form needs bin_mode call / job and a job count that divides by the world size')
+    depth = torch.as_tensor(depth).reshape(n, s, h, w)
+    src_pos = torch.as_tensor(src_pos).reshape(n, s, 3)
+    dev = rgb.device
+    world, rank = self.world, self.rank
+    multi = gather and world > 1
+    cap = jobs // world
+    lo = rank * cap
+    npieces = max(1, min(cap, pieces)) if multi else 1
+    while cap % npieces:
+      npieces -= 1
+    jpp = cap // npieces
+    slots = npieces * world * jpp if multi else cap
+    self.rgb8 = torch.empty((slots, h, w, 3), dtype=torch.uint8, device=dev)
+    self.depth = torch.empty((slots, h, w, 1), dtype=torch.float32, device=dev)
+    self.multi, self.npieces, self.world_jpp, self.jpp, self.jobs, self.lo, self.hi = multi, npieces, world * jpp, jpp, jobs, lo, lo + cap
+    self.calls = []   # (piece, PreparedReprojection, bin tensor or None)
+    for c in range(npieces):
+      a0 = lo + c * jpp
+      done = 0
+      for grp in _merge_whole_items(job_segments(a0, a0 + jpp, p), p):
+        n0, n1 = grp[0][0], grp[-1][0] + 1
+        p0, p1 = grp[0][1], grp[0][2]
+        cnt = (n1 - n0) * (p1 - p0)
+        s0 = ((c * world + rank) * jpp + done) if multi else c * jpp + done
+        out = {'proj_rgb_u8': self.rgb8[s0:s0 + cnt], 'proj_depth': self.depth[s0:s0 + cnt]}
+        binb = torch.zeros(5, device=dev) if bin_mode == 'call' else None
+        plan = guidance.prepare(rgb[n0:n1].contiguous(), depth[n0:n1].contiguous(), src_pos[n0:n1].contiguous(),
+                                tgt_pos[n0:n1, p0:p1].contiguous(), depth_scale=depth_scale, mask_frames=mask_frames,
+                                per_job_bin=(bin_mode == 'job'), compact=True, out=out, bin_out=binb, **conv)
+        self.calls.append((c, plan, binb))
+        done += cnt
+    self.job_map = None
+    if multi and npieces > 1:
+      cs, rs, js = torch.meshgrid(torch.arange(npieces), torch.arange(world), torch.arange(jpp), indexing='ij')
+      self.job_map = (rs * cap + cs * jpp + js).reshape(-1).to(device=dev, dtype=torch.int32)
+    self.red = torch.zeros(5, device=dev)
+    self.owns_job0 = lo == 0
+
+  def run(self) -> Dict[str, torch.Tensor]:
+    handles = []
+    piece = 0
+    for i, (c, plan, _) in enumerate(self.calls):
+      plan.run()
+      last_of_piece = i + 1 == len(self.calls) or self.calls[i + 1][0] != c
+      if self.multi and last_of_piece:
+        for b in (self.rgb8, self.depth):
+          blk = b[c * self.world_jpp:(c + 1) * self.world_jpp]
+          handles.append(dist.all_gather_into_tensor(blk, blk[self.rank * self.jpp:(self.rank + 1) * self.jpp],
+                                                     group=self.group, async_op=True))
+    if self.bin_mode == 'call':
+      bins = torch.stack([b for _, _, b in self.calls])
+      red = self.red
+      red[0] = (-bins[:, 0]).max()
+      red[1:4] = bins[:, 1:4].max(dim=0).values
+      red[4] = -bins[0, 4] if self.owns_job0 else -float('inf')
+      if self.world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX, group=self.group)
+    for hnd in handles:
+      hnd.wait()
+    out = {'proj_rgb_u8': self.rgb8, 'proj_depth': self.depth}
+    if self.bin_mode == 'call' and self.jobs > 0 and (self.multi or self.owns_job0):
+      vec = torch.cat([-self.red[:1], self.red[1:4], -self.red[4:5]])
+      self.g.apply_bin(vec, out, self.depth_scale)
+    if self.expand:
+      out = self.g.expand_guidance(dict(out), job_map=self.job_map)
+    elif self.job_map is not None:
+      out['job_map'] = self.job_map
+    out['job_range'] = (self.lo, self.hi) if not self.multi else (0, self.jobs)
+    return out

@@ -851,3 +851,21 @@ def test_compact_output_expands_to_the_float32_contract(mods, n, s, p, h, chunk_
     for k in ('proj_image', 'proj_depth', 'proj_mask'):
       assert torch.equal(a[k], want[k]), k
   ws.close()
+
+
+def test_int32_colour_range_is_guarded(mods):
+  """the fused path reduces colours in float16 (exact on [-2048, 2048]); values outside are
+  refused instead of being rounded silently; inside the range int32 inputs are exact."""
+  g = mods['g']
+  inp = mods['synth'].make_inputs(1, 1, 1, 16, seed=3, dist='rand')
+  rgb = inp['rgb'].astype(np.int32)
+  rgb[0, 0, 5, 7] = 4097
+  with pytest.raises(ValueError, match='2048'):
+    g.reproject(torch.as_tensor(rgb), torch.as_tensor(inp['depth']), torch.as_tensor(inp['src_pos']), torch.as_tensor(inp['tgt_pos']))
+  rgb[0, 0, 5, 7] = 2047
+  rgb[0, 0, 6, 7] = -2000
+  out = g.reproject(torch.as_tensor(rgb), torch.as_tensor(inp['depth']), torch.as_tensor(inp['src_pos']), torch.as_tensor(inp['tgt_pos']),
+                    raw_features=True, return_winner=True)
+  ref = X.reproject(rgb, inp['depth'], inp['src_pos'], inp['tgt_pos'], mask_first_frame=False)
+  np.testing.assert_array_equal(out['proj_image'].cpu().numpy(), ref['raw_rgb'])
+  np.testing.assert_array_equal(out['winner'].cpu().numpy(), ref['winner'])

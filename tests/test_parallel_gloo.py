@@ -73,7 +73,7 @@ def oracle_expand(out, job_map=None):
     inv = np.empty_like(job_map.numpy()); inv[job_map.numpy()] = np.arange(len(inv))
     image, mask, depth = image[inv], mask[inv], depth[inv]
     out['proj_depth'] = torch.as_tensor(depth)
-    out['proj_rgb_u8'] = torch.as_tensor(rgb8[inv])
+    out.pop('proj_rgb_u8')
     if 'winner' in out:
       out['winner'] = out['winner'][torch.as_tensor(inv)]
   out['proj_image'], out['proj_mask'] = torch.as_tensor(image), torch.as_tensor(mask)

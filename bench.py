@@ -250,6 +250,47 @@ def sharded_record(args, world, rank, dev, steps=60, warmup=5):
   return rec
 
 
+def compat_record(torch, args, dev, steps=100):
+  """The un-fused drop-in calls of the reference signatures on a c2-sized MATERIALISED cloud (what models/models.py:
+  211-226,276-281 executes without code changes): pano_utils.equirectangular_to_pointcloud, then
+  pano_utils.project_feats_to_equirectangular on (xyz1 + src) - tgt.  Each call is timed by itself with CUDA events;
+  the two translations in between are the caller's elementwise glue and are not timed."""
+  from se3ds_b200 import synth
+  from se3ds_b200.utils import pano_utils
+  cfg = CONFIGS['c2']
+  n, h = cfg['n'], cfg['h']
+  w, hw = 2 * h, 2 * h * h
+  peak = measured_peak_gbs()[0]
+  sets = []
+  for r in range(3):  # 3 x (16 + 28 + 16) B per point and pixel > 2x L2
+    inp = synth.make_inputs(n, 1, 1, h, seed=500 + r, dist=args.dist)
+    rgb = torch.as_tensor(inp['rgb'][:, 0].astype(np.int32)).to(dev)
+    depth = torch.as_tensor(inp['depth'][:, 0]).to(dev)
+    off = torch.as_tensor(np.concatenate([inp['src_pos'][:, 0] - inp['tgt_pos'][:, 0], np.zeros((n, 1), np.float32)], 1)).to(dev)
+    xyz1, feats = pano_utils.equirectangular_to_pointcloud(rgb, depth, -1, 20.0)
+    sets.append((rgb, depth, (xyz1 + off[:, :, None]).contiguous(), feats))
+  def timed(fn):
+    for i in range(6):
+      fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+      fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+  t_un = timed(lambda i: pano_utils.equirectangular_to_pointcloud(sets[i % 3][0], sets[i % 3][1], -1, 20.0))
+  t_pr = timed(lambda i: pano_utils.project_feats_to_equirectangular(sets[i % 3][3], sets[i % 3][2], h, w, -1, 20.0))
+  un_bytes = n * hw * (4 + 12 + 16 + 12)  # f32 depth + int32 colours in, xyz1 + int32 features out
+  pr_bytes = n * hw * (16 + 12) + n * hw * (4 + 12)  # xyz1 + int32 features in, f32 depth + f32 features out
+  return {'workload': 'c2-sized materialised cloud: N8 512x1024, int32 colours (void -1), reference signatures, device tensors',
+          'unproject': {'ms': t_un, 'alg_bytes': un_bytes, 'frac_of_hbm_peak': un_bytes / (t_un * 1e-3) / 1e9 / peak},
+          'project': {'ms': t_pr, 'alg_bytes': pr_bytes, 'frac_of_hbm_peak': pr_bytes / (t_pr * 1e-3) / 1e9 / peak,
+                      'panos_per_s': n / (t_pr * 1e-3)},
+          'note': 'what the reference callers get without code changes; the fused path above replaces both calls and the glue'}
+
+
 def gpu_measure(guidance, synth, lib, torch, dist, cfg, args, dev, local_rank, world, rank, steps, warmup,
                 key64=False, compact=False, clocks=False):
   """Device-resident throughput of one config: K timed steps of the fused path over a ring of input / output sets
@@ -494,6 +535,8 @@ def main():
       extras['c4'] = sub('c4', CONFIGS['c4'], steps=60)
       c5 = dict(CONFIGS['c5'], n=4)
       extras['c5_n4'] = sub('c5 (batch reduced from 64 to 4 per GPU)', c5, steps=6)
+    if args.config == 'c2' and world == 1:
+      extras['compat_c2'] = compat_record(torch, args, dev)
     if world > 1:
       extras['sharded_c4'] = sharded_record(args, world, rank, dev)
 

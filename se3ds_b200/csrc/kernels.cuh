@@ -927,16 +927,21 @@ __global__ void unproject_kernel(const TI* __restrict__ feats, const float* __re
 struct CloudParams {
   const float* coords;  // (N,4,M)
   const void* feats;    // (N,M,C)
-  unsigned long long* zbuf;
+  unsigned long long* zbuf;  // KEY64: depth bits << 32 | point index << 1
+  uint32_t* zbuf32;          // !KEY64: depth bits
+  uint2* fbuf;               // F16 mode: per-channel maxima of small integer features (float16 x 4, armed 0)
+  float* fbuf32;             // F16 mode: side accumulator (N*HW*3, armed void_out) for values float16 cannot hold
+  uint32_t* used32;          // F16 mode: != 0 once any point went to the side accumulator
   uint32_t* sc_flat;
   float* sc_rad;
   uint32_t* bin;  // [0] = ~ordered(min depth), [1+c] = ordered(max feature c); all-zero = armed
   float* depth_out;
-  float* feats_out;  // (N,H,W,C), pre-filled with output_void_class; accumulated in place
+  float* feats_out;  // (N,H,W,C); legacy mode: pre-filled with output_void_class and accumulated in place
   int* winner_out;
   long long M;
   int N, C, H, W, HW, mode;
   float void_in, void_out, depth_scale;
+  FastProj fast;
 };
 
 __device__ __forceinline__ float load_feat(const uint8_t* f, size_t i) { return (float)f[i]; }
@@ -949,83 +954,189 @@ __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
 }
 
-template <typename T>
+// The compat path (utils/pano_utils.py:117-161 / utils/point_cloud_utils.py:90-183 on a materialised cloud),
+// three kernels chained with programmatic dependent launch:
+//   cloud_depth : projection (mode 0: certified fast projection with the canonical one as the fallback of the
+//                 lanes it cannot certify; mode 1: the coordinates are already "transformed") + REDG.MIN of the
+//                 64-bit (depth | index) key when winner indices are wanted, of the 32-bit depth otherwise
+//   cloud_feat  : tolerance test + per-channel max.  F16 mode (3 channels of integer features, output void 0:
+//                 every RGB caller of the reference): one 8-byte float16x4 reduction per point, like the fused
+//                 path; a value float16 cannot hold exactly goes to a float32 side accumulator instead, and the
+//                 resolve merges the two (a maximum can be taken in pieces).  Otherwise: float32 atomics into
+//                 the pre-filled output.
+//   cloud_resolve: depth, features, winner; re-arms what was touched.
+template <typename T, bool KEY64>
 __global__ void __launch_bounds__(kThreads) cloud_depth_kernel(const CloudParams q) {
+  pdl_enter();
   const int b = blockIdx.y;
-  const long long m = blockIdx.x * (long long)kThreads + threadIdx.x;
-  const bool on = m < q.M;
-  float px = 0.f, py = 0.f, pz = 0.f;
-  bool fvalid = true;
-  if (on) {
-    const float* cb = q.coords + (size_t)b * 4 * q.M;
-    const float x = cb[m], y = cb[q.M + m], z = cb[2 * q.M + m];
-    if (q.mode == 0) pseudo_perspective(x, y, z, px, py, pz);
-    else { px = x; py = y; pz = z; }
-    const size_t f0 = ((size_t)b * q.M + m) * q.C;
-    for (int c = 0; c < q.C; ++c) fvalid &= load_feat(static_cast<const T*>(q.feats), f0 + c) != q.void_in;
-  }
-  const int tpix = on ? pixel_of(px, py, pz, q.H, q.W) : -1;
-  const bool valid = on && fvalid && tpix >= 0;
-  if (valid) {
-    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | ((uint32_t)m << 1);
-    atomicMin(q.zbuf + (size_t)b * q.HW + tpix, key);
-  }
-  // reject bin: min depth of every rejected point (utils/point_cloud_utils.py:150-159)
-  const bool rej = on && !valid;
-  if (__ballot_sync(0xffffffffu, rej)) {
-    const uint32_t v = __reduce_max_sync(0xffffffffu, rej ? ~f32_ordered(pz) : 0u);
-    if ((threadIdx.x & 31) == 0 && v > *reinterpret_cast<volatile uint32_t*>(q.bin)) atomicMax(q.bin, v);
-  }
-  if (on) {
-    q.sc_flat[(size_t)b * q.M + m] = valid ? (uint32_t)tpix : kScInvalid;
-    q.sc_rad[(size_t)b * q.M + m] = pz;
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kThreads) cloud_feat_kernel(const CloudParams q) {
-  const int b = blockIdx.y;
-  const long long m = blockIdx.x * (long long)kThreads + threadIdx.x;
-  if (m >= q.M) return;
-  const uint32_t fl = q.sc_flat[(size_t)b * q.M + m];
-  const float rad = q.sc_rad[(size_t)b * q.M + m];
-  bool keep = false;
-  if (!(fl & kScInvalid)) {
-    const unsigned long long key = q.zbuf[(size_t)b * q.HW + fl];
-    const float zmin = key == kZArmed ? q.depth_scale : fminf(__uint_as_float((uint32_t)(key >> 32)), q.depth_scale);
-    keep = rad < __fadd_rn(zmin, 0.1f);
-  }
-  const size_t f0 = ((size_t)b * q.M + m) * q.C;
-  if (keep) {
-    float* dst = q.feats_out + ((size_t)b * q.HW + fl) * q.C;
-    for (int c = 0; c < q.C; ++c) atomic_max_f32(dst + c, load_feat(static_cast<const T*>(q.feats), f0 + c));
-  } else {
-    for (int c = 0; c < q.C; ++c) {
-      const uint32_t v = f32_ordered(load_feat(static_cast<const T*>(q.feats), f0 + c));
-      if (v > *reinterpret_cast<volatile uint32_t*>(q.bin + 1 + c)) atomicMax(q.bin + 1 + c, v);
+  // Persistent grid-stride loop: the warp keeps the largest reject-bin value it has seen in a register and
+  // goes back to memory only when one of its points exceeds it (same-address loads from every warp of a
+  // one-point-per-thread grid serialise at one L2 slice: 70 % of the kernel's stalls, profiles/r02_*).
+  uint32_t bin_seen = 0u;
+  const long long span = (long long)gridDim.x * kThreads;
+  for (long long m0 = blockIdx.x * (long long)kThreads; m0 < q.M; m0 += span) {
+    const long long m = m0 + threadIdx.x;
+    const bool on = m < q.M;
+    float pz = 0.f;
+    int tpix = -1;
+    bool fvalid = true;
+    if (on) {
+      const float* cb = q.coords + (size_t)b * 4 * q.M;
+      const float x = __ldg(cb + m), y = __ldg(cb + q.M + m), z = __ldg(cb + 2 * q.M + m);
+      const size_t f0 = ((size_t)b * q.M + m) * q.C;
+      for (int c = 0; c < q.C; ++c) fvalid &= load_feat(static_cast<const T*>(q.feats), f0 + c) != q.void_in;
+      if (q.mode == 0) {
+        const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+        float rs, fx;
+        bool ok;
+        int frow;
+        pz = fast_rad(r2, rs, ok);
+        const bool certain = project_pixel_fast(x, y, z, rs, q.H, q.W, q.fast, tpix, fx, frow) && ok;
+        if (!certain) {  // a few lanes in a thousand: the canonical projection
+          pz = canon_rad(x, y, z);
+          tpix = project_pixel_rad(x, y, z, q.H, q.W, pz);
+        }
+      } else {
+        pz = z;
+        tpix = pixel_of(x, y, z, q.H, q.W);
+      }
+    }
+    const bool valid = on && fvalid && tpix >= 0;
+    if (valid) {
+      if constexpr (KEY64) atomicMin(q.zbuf + (size_t)b * q.HW + tpix, ((unsigned long long)__float_as_uint(pz) << 32) | ((uint32_t)m << 1));
+      else atomicMin(q.zbuf32 + (size_t)b * q.HW + tpix, __float_as_uint(pz));
+    }
+    // reject bin: min depth of every rejected point (utils/point_cloud_utils.py:150-159)
+    const bool rej = on && !valid;
+    if (__any_sync(0xffffffffu, rej)) {
+      const uint32_t v = __reduce_max_sync(0xffffffffu, rej ? ~f32_ordered(pz) : 0u);
+      if (v > bin_seen) {
+        if ((threadIdx.x & 31) == 0) {
+          bin_seen = __ldcg(q.bin);
+          if (v > bin_seen) { atomicMax(q.bin, v); bin_seen = v; }
+        }
+        bin_seen = __shfl_sync(0xffffffffu, bin_seen, 0);
+      }
+    }
+    if (on) {
+      q.sc_flat[(size_t)b * q.M + m] = valid ? (uint32_t)tpix : kScInvalid;
+      q.sc_rad[(size_t)b * q.M + m] = pz;
     }
   }
 }
 
+template <typename T, bool KEY64, bool F16>
+__global__ void __launch_bounds__(kThreads) cloud_feat_kernel(const CloudParams q) {
+  pdl_enter();
+  const int b = blockIdx.y;
+  const T* feats = static_cast<const T*>(q.feats);
+  uint32_t bin_seen[3] = {0u, 0u, 0u};  // register copy of the reject bin's first channels (see cloud_depth_kernel)
+  const long long span = (long long)gridDim.x * kThreads;
+  for (long long m0 = blockIdx.x * (long long)kThreads; m0 < q.M; m0 += span) {
+    const long long m = m0 + threadIdx.x;
+    const bool on = m < q.M;
+    bool keep = false;
+    uint32_t fl = kScInvalid;
+    if (on) {
+      fl = q.sc_flat[(size_t)b * q.M + m];
+      const float rad = q.sc_rad[(size_t)b * q.M + m];
+      if (!(fl & kScInvalid)) {
+        float zmin;
+        if constexpr (KEY64) zmin = __uint_as_float((uint32_t)(__ldcg(q.zbuf + (size_t)b * q.HW + fl) >> 32));
+        else zmin = __uint_as_float(__ldcg(q.zbuf32 + (size_t)b * q.HW + fl));
+        keep = rad < __fadd_rn(fminf(zmin, q.depth_scale), 0.1f);  // armed bits are a NaN: fminf -> depth_scale
+      }
+    }
+    const size_t f0 = ((size_t)b * q.M + (on ? m : 0)) * q.C;
+    if (keep) {
+      if constexpr (F16) {
+        const int3 f = make_int3((int)feats[f0], (int)feats[f0 + 1], (int)feats[f0 + 2]);
+        if (max(max(abs(f.x), abs(f.y)), abs(f.z)) <= 2048) {
+          if (f.x > 0 || f.y > 0 || f.z > 0) red_max_f16x4(q.fbuf + (size_t)b * q.HW + fl, pack_f16x4(f));  // <= 0 cannot raise a maximum over 0
+        } else {  // float16 would round it: the float32 side accumulator
+          float* dst = q.fbuf32 + ((size_t)b * q.HW + fl) * 3;
+          atomic_max_f32(dst, (float)f.x); atomic_max_f32(dst + 1, (float)f.y); atomic_max_f32(dst + 2, (float)f.z);
+          *q.used32 = 1u;
+        }
+      } else {
+        float* dst = q.feats_out + ((size_t)b * q.HW + fl) * q.C;
+        for (int c = 0; c < q.C; ++c) atomic_max_f32(dst + c, load_feat(feats, f0 + c));
+      }
+    }
+    // reject bin: per-channel maximum of every rejected point (flat index 0 of the reference), reduced per warp;
+    // memory is consulted only when a value exceeds what this warp has already seen there
+    const bool rej = on && !keep;
+    if (__any_sync(0xffffffffu, rej)) {
+      for (int c = 0; c < q.C; ++c) {
+        const uint32_t v = __reduce_max_sync(0xffffffffu, rej ? f32_ordered(load_feat(feats, f0 + c)) : 0u);
+        const uint32_t seen = c < 3 ? bin_seen[c] : 0u;
+        if (v > seen) {
+          uint32_t now = v;
+          if ((threadIdx.x & 31) == 0) {
+            now = __ldcg(q.bin + 1 + c);
+            if (v > now) { atomicMax(q.bin + 1 + c, v); now = v; }
+          }
+          now = __shfl_sync(0xffffffffu, now, 0);
+          if (c < 3) bin_seen[c] = now;
+        }
+      }
+    }
+  }
+}
+
+template <bool KEY64, bool F16>
 __global__ void __launch_bounds__(kThreads) cloud_resolve_kernel(const CloudParams q) {
+  pdl_enter();
   const long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
   const long long total = (long long)q.N * q.HW;
   if (i >= total) return;
-  const unsigned long long key = q.zbuf[i];
+  unsigned long long key;
+  if constexpr (KEY64) key = q.zbuf[i];
+  else key = ((unsigned long long)q.zbuf32[i] << 32) | 0xFFFFFFFFu;
   const bool has = key != kZArmed;
   const float radw = __uint_as_float((uint32_t)(key >> 32));
   float zmin = has ? fminf(radw, q.depth_scale) : q.depth_scale;
+  float f[3] = {0.f, 0.f, 0.f};
+  if constexpr (F16) {
+    const uint2 fv = q.fbuf[i];
+    const float3 u = unpack_f16x4(fv);
+    f[0] = u.x; f[1] = u.y; f[2] = u.z;
+    if (*q.used32) {  // some value of this call did not fit float16: merge (and re-arm) the side accumulator
+      for (int c = 0; c < 3; ++c) {
+        f[c] = fmaxf(f[c], q.fbuf32[i * 3 + c]);
+        q.fbuf32[i * 3 + c] = q.void_out;
+      }
+    }
+    if (fv.x | fv.y) q.fbuf[i] = make_uint2(0u, 0u);
+  }
   if (i == 0) {
     if (q.bin[0]) zmin = fminf(zmin, f32_unordered(~q.bin[0]));
     for (int c = 0; c < q.C; ++c) {
-      if (q.bin[1 + c]) q.feats_out[c] = fmaxf(q.feats_out[c], f32_unordered(q.bin[1 + c]));
+      if (q.bin[1 + c]) {
+        const float bf = f32_unordered(q.bin[1 + c]);
+        if constexpr (F16) f[c] = fmaxf(f[c], bf);
+        else q.feats_out[c] = fmaxf(q.feats_out[c], bf);
+      }
       q.bin[1 + c] = 0u;
     }
     q.bin[0] = 0u;
   }
+  if constexpr (F16) {
+    q.feats_out[i * 3] = f[0]; q.feats_out[i * 3 + 1] = f[1]; q.feats_out[i * 3 + 2] = f[2];
+  }
   q.depth_out[i] = __fdiv_rn(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale);
-  if (q.winner_out) q.winner_out[i] = (has && radw <= q.depth_scale) ? (int)((uint32_t)key >> 1) : -1;
-  q.zbuf[i] = kZArmed;
+  if constexpr (KEY64) {
+    if (q.winner_out) q.winner_out[i] = (has && radw <= q.depth_scale) ? (int)((uint32_t)key >> 1) : -1;
+    if (has) q.zbuf[i] = kZArmed;
+  } else {
+    if (has) q.zbuf32[i] = 0xFFFFFFFFu;
+  }
+}
+
+// re-arms the `used32` flag after the resolve (one thread; launched only in F16 mode)
+__global__ void cloud_clear_flag_kernel(uint32_t* flag) {
+  pdl_enter();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *flag = 0u;
 }
 
 // tensorflow_addons.image.interpolate_bilinear (called at utils/pano_utils.py:339,412,472):

@@ -92,7 +92,7 @@ constexpr size_t kDefaultChunkBytes = (size_t)112 << 20;
 struct se3ds_ws {
   int device = 0, sm_count = 148;
   size_t max_bytes = kDefaultMaxBytes, chunk_bytes = kDefaultChunkBytes;
-  DevBuf zbuf, zbuf32, fbuf, scf, scr, bins, cbin;
+  DevBuf zbuf, zbuf32, fbuf, scf, scr, bins, cbin, cf32, cflag;  // cf32 / cflag: float32 side accumulator of the compat path
   std::vector<TableEntry> tables;
   bool dirty = false;  // a pass was enqueued but its resolve (which re-arms) was not
   // staging of the host-buffer entry point
@@ -122,7 +122,7 @@ struct se3ds_ws {
 namespace {
 
 size_t ws_total(const se3ds_ws* ws) {
-  size_t t = ws->zbuf.cap + ws->zbuf32.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->bins.cap + ws->cbin.cap +
+  size_t t = ws->zbuf.cap + ws->zbuf32.cap + ws->fbuf.cap + ws->scf.cap + ws->scr.cap + ws->bins.cap + ws->cbin.cap + ws->cf32.cap + ws->cflag.cap +
              ws->s_rgb.cap + ws->s_depth.cap + ws->s_src.cap + ws->s_tgt.cap + ws->s_img.cap +
              ws->s_dep.cap + ws->s_msk.cap + ws->s_win.cap;
   for (const auto& e : ws->tables) t += (size_t)(4 * e.h + 2 * e.w) * sizeof(float);
@@ -190,6 +190,8 @@ int rearm(se3ds_ws* ws, cudaStream_t stream) {
   if (ws->fbuf.p) CU(cudaMemsetAsync(ws->fbuf.p, 0, ws->fbuf.cap, stream));
   if (ws->bins.p) CU(cudaMemsetAsync(ws->bins.p, 0, ws->bins.cap, stream));
   if (ws->cbin.p) CU(cudaMemsetAsync(ws->cbin.p, 0, ws->cbin.cap, stream));
+  if (ws->cf32.p) CU(cudaMemsetAsync(ws->cf32.p, 0, ws->cf32.cap, stream));
+  if (ws->cflag.p) CU(cudaMemsetAsync(ws->cflag.p, 0, ws->cflag.cap, stream));
   ws->dirty = false;
   return SE3DS_OK;
 }
@@ -244,6 +246,18 @@ int get_tables(se3ds_ws* ws, int h, int w, cudaStream_t stream, const float** ou
   ws->tables.push_back({h, w, ws->margin_scale, dev});
   *out = dev;
   return SE3DS_OK;
+}
+
+// constants of the certified fast projection: polynomials in pixel units (canon_math.cuh)
+void fill_fast_proj(FastProj& fp, const se3ds_ws* ws, int h, int w, const float* tab) {
+  const double kx = (double)w / (2.0 * 3.141592653589793), ky = (double)h / 3.141592653589793;
+  const double atan_c[9] = CANON_ATAN_COEFFS, acos_c[5] = FAST_ACOS_COEFFS;
+  for (int i = 0; i < 9; ++i) fp.ca[i] = (float)(kx * atan_c[i]);
+  for (int i = 0; i < 5; ++i) fp.ce[i] = (float)(ky * acos_c[i]);
+  fp.kx = (float)kx;
+  fp.w4 = (float)(0.25 * w); fp.w34 = (float)(0.75 * w); fp.hf = (float)h;
+  fp.dx = (float)w * ws->margin_scale;
+  fp.rowb = reinterpret_cast<const float2*>(tab + 2 * (size_t)h + 2 * (size_t)w);
 }
 
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
@@ -377,7 +391,7 @@ int se3ds_ws_destroy(se3ds_ws* ws) {
   if (!ws) return SE3DS_OK;
   DeviceGuard guard_(ws->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&ws->zbuf, &ws->zbuf32, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->dbg, &ws->stamps, &ws->s_rgb, &ws->s_depth,
+  for (DevBuf* b : {&ws->zbuf, &ws->zbuf32, &ws->fbuf, &ws->scf, &ws->scr, &ws->bins, &ws->cbin, &ws->cf32, &ws->cflag, &ws->dbg, &ws->stamps, &ws->s_rgb, &ws->s_depth,
                     &ws->s_src, &ws->s_tgt, &ws->s_img, &ws->s_dep, &ws->s_msk, &ws->s_win})
     if (b->p) cudaFree(b->p);
   for (auto& e : ws->tables) cudaFree(e.dev);
@@ -579,38 +593,77 @@ int se3ds_project_cloud(se3ds_ws* ws, const float* coords, const void* feats, in
   const long long npix = (long long)n * h * w;
   if (ws->dirty)
     if (int rc = rearm(ws, st)) return rc;
-  if (int rc = grow(ws->zbuf, (size_t)npix * 8, 0xFF, st)) return rc;
+  const bool key64 = winner_out != nullptr;
+  // F16 mode: three channels of integer features with output void class 0 (every RGB caller of the reference)
+  const bool f16 = c == 3 && feat_dtype != SE3DS_F32 && output_void_class == 0.0f;
+  if (key64) { if (int rc = grow(ws->zbuf, (size_t)npix * 8, 0xFF, st)) return rc; }
+  else { if (int rc = grow(ws->zbuf32, (size_t)npix * 4, 0xFF, st)) return rc; }
+  if (f16) {
+    if (int rc = grow(ws->fbuf, (size_t)npix * 8, 0, st)) return rc;
+    if (int rc = grow(ws->cf32, (size_t)npix * 12, 0, st)) return rc;
+    if (int rc = grow(ws->cflag, 256, 0, st)) return rc;
+  }
   if (int rc = grow(ws->scf, (size_t)std::max<long long>(n * m, 1) * 4, -1, st)) return rc;
   if (int rc = grow(ws->scr, (size_t)std::max<long long>(n * m, 1) * 4, -1, st)) return rc;
   if (int rc = grow(ws->cbin, (size_t)(1 + c) * 4, 0, st)) return rc;
   CloudParams q{};
   q.coords = coords; q.feats = feats;
-  q.zbuf = (unsigned long long*)ws->zbuf.p; q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p;
+  q.zbuf = (unsigned long long*)ws->zbuf.p; q.zbuf32 = (uint32_t*)ws->zbuf32.p;
+  q.fbuf = (uint2*)ws->fbuf.p; q.fbuf32 = (float*)ws->cf32.p; q.used32 = (uint32_t*)ws->cflag.p;
+  q.sc_flat = (uint32_t*)ws->scf.p; q.sc_rad = (float*)ws->scr.p;
   q.bin = (uint32_t*)ws->cbin.p;
   q.depth_out = depth_out; q.feats_out = feats_out; q.winner_out = winner_out;
   q.M = m; q.N = n; q.C = c; q.H = h; q.W = w; q.HW = h * w; q.mode = mode;
   q.void_in = input_void_class; q.void_out = output_void_class; q.depth_scale = depth_scale;
-  ws->dirty = true;
-  fill_f32_kernel<<<(int)std::min<long long>((npix * c + kThreads - 1) / kThreads, 148 * 16), kThreads, 0, st>>>(feats_out, npix * c, output_void_class);
-  if (m > 0) {
-    const dim3 grid((unsigned)((m + kThreads - 1) / kThreads), n);
-    switch (feat_dtype) {
-      case SE3DS_U8:
-        cloud_depth_kernel<uint8_t><<<grid, kThreads, 0, st>>>(q);
-        cloud_feat_kernel<uint8_t><<<grid, kThreads, 0, st>>>(q);
-        break;
-      case SE3DS_I32:
-        cloud_depth_kernel<int><<<grid, kThreads, 0, st>>>(q);
-        cloud_feat_kernel<int><<<grid, kThreads, 0, st>>>(q);
-        break;
-      default:
-        cloud_depth_kernel<float><<<grid, kThreads, 0, st>>>(q);
-        cloud_feat_kernel<float><<<grid, kThreads, 0, st>>>(q);
-        break;
-    }
+  if (mode == 0) {
+    const float* tab = nullptr;
+    if (int rc = get_tables(ws, h, w, st, &tab)) return rc;
+    fill_fast_proj(q.fast, ws, h, w, tab);
   }
-  cloud_resolve_kernel<<<(unsigned)((npix + kThreads - 1) / kThreads), kThreads, 0, st>>>(q);
-  ws->launches += m > 0 ? 4 : 2;
+  ws->dirty = true;
+  const bool pdl = ws->pdl;
+  const dim3 block(kThreads);
+  if (!f16) {  // the float32 atomics accumulate in the caller's tensor: it starts as the output void class
+    fill_f32_kernel<<<(int)std::min<long long>((npix * c + kThreads - 1) / kThreads, 148 * 16), kThreads, 0, st>>>(feats_out, npix * c, output_void_class);
+    ws->launches += 1;
+  }
+  if (m > 0) {
+    // persistent grid-stride kernels: about one resident wave in x, the batch in y
+    const long long want = (m + kThreads - 1) / kThreads, cap = std::max<long long>(1, (long long)ws->sm_count * 16 / std::max(n, 1));
+    const dim3 grid((unsigned)std::min(want, cap), n);
+#define CLOUD_SPLAT(T)                                                                                       \
+  do {                                                                                                      \
+    if (key64) {                                                                                            \
+      CU(launch_pdl(cloud_depth_kernel<T, true>, grid, block, st, pdl, q));                                 \
+      if (f16) CU(launch_pdl(cloud_feat_kernel<T, true, true>, grid, block, st, pdl, q));                   \
+      else CU(launch_pdl(cloud_feat_kernel<T, true, false>, grid, block, st, pdl, q));                      \
+    } else {                                                                                                \
+      CU(launch_pdl(cloud_depth_kernel<T, false>, grid, block, st, pdl, q));                                \
+      if (f16) CU(launch_pdl(cloud_feat_kernel<T, false, true>, grid, block, st, pdl, q));                  \
+      else CU(launch_pdl(cloud_feat_kernel<T, false, false>, grid, block, st, pdl, q));                     \
+    }                                                                                                       \
+  } while (0)
+    switch (feat_dtype) {
+      case SE3DS_U8: CLOUD_SPLAT(uint8_t); break;
+      case SE3DS_I32: CLOUD_SPLAT(int); break;
+      default: CLOUD_SPLAT(float); break;
+    }
+#undef CLOUD_SPLAT
+    ws->launches += 2;
+  }
+  const dim3 rgrid((unsigned)((npix + kThreads - 1) / kThreads));
+  if (key64) {
+    if (f16) CU(launch_pdl(cloud_resolve_kernel<true, true>, rgrid, block, st, pdl, q));
+    else CU(launch_pdl(cloud_resolve_kernel<true, false>, rgrid, block, st, pdl, q));
+  } else {
+    if (f16) CU(launch_pdl(cloud_resolve_kernel<false, true>, rgrid, block, st, pdl, q));
+    else CU(launch_pdl(cloud_resolve_kernel<false, false>, rgrid, block, st, pdl, q));
+  }
+  ws->launches += 1;
+  if (f16) {
+    CU(launch_pdl(cloud_clear_flag_kernel, dim3(1), dim3(32), st, pdl, q.used32));
+    ws->launches += 1;
+  }
   if (int rc = launch_check("cloud projection kernels")) return rc;
   ws->dirty = false;
   return SE3DS_OK;
@@ -695,16 +748,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   q.prefilter_f = (s > 1 && lanes * lane_px * 8 <= ((size_t)48 << 20)) ? 1 : 0;
   if (int rc = grow(ws->dbg, 4 * sizeof(unsigned long long), 0, st)) return rc;
   q.dbg = (unsigned long long*)ws->dbg.p;
-  {  // certified fast projection: polynomials in pixel units (canon_math.cuh)
-    const double kx = (double)w / (2.0 * 3.141592653589793), ky = (double)h / 3.141592653589793;
-    const double atan_c[9] = CANON_ATAN_COEFFS, acos_c[5] = FAST_ACOS_COEFFS;
-    for (int i = 0; i < 9; ++i) q.fast.ca[i] = (float)(kx * atan_c[i]);
-    for (int i = 0; i < 5; ++i) q.fast.ce[i] = (float)(ky * acos_c[i]);
-    q.fast.kx = (float)kx;
-    q.fast.w4 = (float)(0.25 * w); q.fast.w34 = (float)(0.75 * w); q.fast.hf = (float)h;
-    q.fast.dx = (float)w * ws->margin_scale;
-  }
-  q.fast.rowb = reinterpret_cast<const float2*>(tab + 2 * (size_t)h + 2 * (size_t)w);
+  fill_fast_proj(q.fast, ws, h, w, tab);
   {
     volatile float one = 1.0f, ds = depth_scale;
     q.inv_depth_scale = one / ds;  // IEEE single division on the host: RN(1 / depth_scale)

@@ -869,3 +869,32 @@ def test_int32_colour_range_is_guarded(mods):
   ref = X.reproject(rgb, inp['depth'], inp['src_pos'], inp['tgt_pos'], mask_first_frame=False)
   np.testing.assert_array_equal(out['proj_image'].cpu().numpy(), ref['raw_rgb'])
   np.testing.assert_array_equal(out['winner'].cpu().numpy(), ref['winner'])
+
+
+@pytest.mark.parametrize('dtype,with_winner', [(np.int32, True), (np.int32, False), (np.uint8, False)])
+def test_project_cloud_rgb_fast_accumulator(mods, dtype, with_winner):
+  """The drop-in call of models/models.py:276-281 (3-channel integer colours, void -1 in, 0 out) takes the tuned compat
+  kernels: float16x4 reduction, 32-bit key without winner indices, certified fast projection.  Bit-exact against the
+  oracle, including values float16 cannot hold (they go to the float32 side accumulator) and a second call on the
+  same workspace (everything re-armed)."""
+  rng = np.random.default_rng(12)
+  h, n = 48, 2
+  inp = mods['synth'].make_inputs(n, 1, 1, h, seed=77, dist='rand')
+  rgb = inp['rgb'][:, 0].astype(np.int32)
+  if dtype == np.int32:
+    rgb[:, ::5, ::7] = -1                      # void pixels
+    rgb[0, 3::9, 2::11, 1] = 70000             # float16 cannot hold these
+    rgb[1, 4::13, 1::5, 2] = -3000
+  xyz1, feats = X.equirectangular_to_pointcloud(rgb, inp['depth'][:, 0], -1 if dtype == np.int32 else 0, 20.0)
+  xyz1 = (xyz1 + np.concatenate([inp['src_pos'][:, 0] - inp['tgt_pos'][:, 0], np.zeros((n, 1), F32)], 1)[:, :, None]).astype(F32)
+  feats = feats.astype(dtype)
+  void_in = -1 if dtype == np.int32 else 0
+  o = X.splat(xyz1, feats.astype(F32), h, 2 * h, 20.0, float(void_in))
+  for _ in range(2):
+    res = mods['pano'].project_feats_to_equirectangular(torch.as_tensor(feats), torch.as_tensor(xyz1), h, 2 * h, void_in, 20.0,
+                                                        return_winner=with_winner)
+    np.testing.assert_array_equal(res[0].cpu().numpy(), o['depth'])
+    np.testing.assert_array_equal(res[1].cpu().numpy(), o['feat'])
+    if with_winner:
+      np.testing.assert_array_equal(res[2].cpu().numpy(), o['winner'])
+  assert (o['feat'] > 60000).any() or dtype == np.uint8

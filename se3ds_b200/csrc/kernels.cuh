@@ -76,7 +76,26 @@ struct Bin {
   uint32_t zneg;
   int f[3];
   uint32_t own1;  // depth bits + 1 of the owner pixel's own winner (0 = none), where the bin is applied later
+  uint32_t pad[27];  // one replica per 128-byte line
 };
+// A bin is kept in kBinReplicas copies, 128 bytes apart; a block updates copy blockIdx % kBinReplicas and the
+// consumer (the owner pixel's thread, the patch / export kernels) folds them.  Loads and atomics on ONE address
+// from every block of a kernel serialise at one L2 slice (measured on the compat path: 70 % of a kernel's
+// stalls); spread over 16 lines they do not.
+constexpr int kBinReplicas = 16;
+__device__ __forceinline__ Bin* bin_replica(Bin* bin) {
+  return bin + ((blockIdx.x + blockIdx.y * 7u + blockIdx.z * 3u) % kBinReplicas);
+}
+// folds the replicas into `out` (zneg: max, f: max, own1: replica 0 only) and re-arms them
+__device__ __forceinline__ Bin bin_fold_and_rearm(Bin* bin) {
+  Bin r{0u, {0, 0, 0}, bin->own1, {}};
+  for (int i = 0; i < kBinReplicas; ++i) {
+    r.zneg = max(r.zneg, bin[i].zneg);
+    r.f[0] = max(r.f[0], bin[i].f[0]); r.f[1] = max(r.f[1], bin[i].f[1]); r.f[2] = max(r.f[2], bin[i].f[2]);
+    bin[i].zneg = 0u; bin[i].f[0] = 0; bin[i].f[1] = 0; bin[i].f[2] = 0; bin[i].own1 = 0u;
+  }
+  return r;
+}
 
 struct FusedParams {
   const void* rgb;
@@ -90,7 +109,7 @@ struct FusedParams {
   uint2* fbuf;
   uint32_t* sc_flat;
   float* sc_rad;
-  Bin* bins;  // J bins (per call: only bins[0] is used)
+  Bin* bins;  // J bins of kBinReplicas copies each (per call: only the first bin is used)
   float* out_image;
   float* out_depth;
   float* out_mask;
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
 #pragma unroll
   for (int k = 0; k < 4; ++k) act[k] = col0 + (VEC ? 0 : k) < W;  // VEC: W % 4 == 0, the four points are active together
 
-  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? job : 0);
+  Bin* bin = bin_replica(q.bins + (size_t)((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? job : 0) * kBinReplicas);
   unsigned long long* zb = q.zbuf + (size_t)lj * q.HW;
   uint32_t* zb32 = q.zbuf32 + (size_t)lj * q.HW;
   const size_t sc_frame = ((size_t)lj * q.S + s) * q.HW;
@@ -566,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 16) splat_feat_kernel(const FusedPar
   // point whose channels are all <= 0 changes nothing.  A masked row holds only -1 / unproject_void
   // features: the whole block (= one row segment) has nothing to do.
   if (row_masked(q, ix.s, ix.row) && q.uv <= 0) return;
-  Bin* bin = q.bins + ((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0);
+  Bin* bin = bin_replica(q.bins + (size_t)((q.flags & SE3DS_FLAG_BIN_PER_JOB) ? ix.job : 0) * kBinReplicas);
   bool bin_has = false;
   int3 bin_f = make_int3(0, 0, 0);
   if (ix.col0 < q.W) {
@@ -699,18 +718,18 @@ __device__ __forceinline__ void resolve_pixel(const FusedParams& q, int job, int
   if ((pix == 0) && (per_job || job == 0)) {  // owner pixel of a reject bin
     // A rejected point that is nearer than every valid point of this pixel takes the pixel's depth
     // (scatter-min over all points, point_cloud_utils.py:157-159): then no valid point is the winner.
-    Bin* bin = q.bins + (per_job ? job : 0);
+    Bin* bin = q.bins + (size_t)(per_job ? job : 0) * kBinReplicas;
     const uint32_t own1 = (KEY64 && ow >= 0) ? (uint32_t)(key >> 32) + 1u : 0u;
     if (q.bin_out != nullptr) {
       bin->own1 = own1;  // export mode: the reduced bin is applied by se3ds_apply_bin
     } else if (q.finalize_bins) {
-      if (bin->zneg) {
-        const float bz = f32_unordered(~bin->zneg);
+      const Bin r = bin_fold_and_rearm(bin);
+      if (r.zneg) {
+        const float bz = f32_unordered(~r.zneg);
         zmin = fminf(zmin, bz);
         if (KEY64 && bz < radw) ow = -1;
       }
-      f.x = fmaxf(f.x, (float)bin->f[0]); f.y = fmaxf(f.y, (float)bin->f[1]); f.z = fmaxf(f.z, (float)bin->f[2]);
-      *bin = Bin{0u, {0, 0, 0}, 0u};  // re-arm
+      f.x = fmaxf(f.x, (float)r.f[0]); f.y = fmaxf(f.y, (float)r.f[1]); f.z = fmaxf(f.z, (float)r.f[2]);
     } else {
       // more chunks will still add to the global bin: park this pixel's own values in it,
       // patch_owner_kernel finishes the pixel after the last chunk.
@@ -836,11 +855,10 @@ __global__ void __launch_bounds__(kThreads, KEY64 ? 10 : 12) resolve_kernel(cons
 // After the last chunk of a multi-chunk call with the global bin: finish job 0's pixel (0,0).
 __global__ void patch_owner_kernel(const FusedParams q) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  Bin* bin = q.bins;
-  const float zmin = bin->zneg ? f32_unordered(~bin->zneg) : q.depth_scale;
-  const float3 f = make_float3((float)bin->f[0], (float)bin->f[1], (float)bin->f[2]);
-  if (q.out_winner && bin->own1 && zmin < __uint_as_float(bin->own1 - 1u)) q.out_winner[0] = -1;  // a rejected point is nearer
-  *bin = Bin{0u, {0, 0, 0}, 0u};
+  const Bin r = bin_fold_and_rearm(q.bins);
+  const float zmin = r.zneg ? f32_unordered(~r.zneg) : q.depth_scale;
+  const float3 f = make_float3((float)r.f[0], (float)r.f[1], (float)r.f[2]);
+  if (q.out_winner && r.own1 && zmin < __uint_as_float(r.own1 - 1u)) q.out_winner[0] = -1;  // a rejected point is nearer
   const float depth = div_rcp(fminf(fmaxf(zmin, 0.0f), q.depth_scale), q.depth_scale, q.inv_depth_scale);
   q.out_depth[0] = depth;
   if (q.flags & SE3DS_FLAG_COMPACT_OUT) {
@@ -858,11 +876,10 @@ __global__ void patch_owner_kernel(const FusedParams q) {
 // Export mode (multi-GPU): hand the call's bin to the caller as (min depth | +inf, max R, G, B).
 __global__ void export_bin_kernel(const FusedParams q) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  Bin* bin = q.bins;
-  q.bin_out[0] = bin->zneg ? f32_unordered(~bin->zneg) : __int_as_float(0x7f800000);
-  q.bin_out[1] = (float)bin->f[0]; q.bin_out[2] = (float)bin->f[1]; q.bin_out[3] = (float)bin->f[2];
-  q.bin_out[4] = bin->own1 ? __uint_as_float(bin->own1 - 1u) : __int_as_float(0x7f800000);  // depth of the owner pixel's own winner
-  *bin = Bin{0u, {0, 0, 0}, 0u};
+  const Bin r = bin_fold_and_rearm(q.bins);
+  q.bin_out[0] = r.zneg ? f32_unordered(~r.zneg) : __int_as_float(0x7f800000);
+  q.bin_out[1] = (float)r.f[0]; q.bin_out[2] = (float)r.f[1]; q.bin_out[3] = (float)r.f[2];
+  q.bin_out[4] = r.own1 ? __uint_as_float(r.own1 - 1u) : __int_as_float(0x7f800000);  // depth of the owner pixel's own winner
 }
 
 // Applies a (reduced) bin to pixel (0,0) of the first job of finished guidance tensors.

@@ -727,7 +727,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   if (int rc = grow(ws->fbuf, lanes * lane_px * 8, 0, st)) return rc;
   if (int rc = grow(ws->scf, lanes * lane_px * s * 4, -1, st)) return rc;
   if (int rc = grow(ws->scr, lanes * lane_px * s * 4, -1, st)) return rc;
-  if (int rc = grow(ws->bins, (size_t)(per_job ? J : 1) * sizeof(Bin), 0, st)) return rc;
+  if (int rc = grow(ws->bins, (size_t)(per_job ? J : 1) * kBinReplicas * sizeof(Bin), 0, st)) return rc;
   const float* tab = nullptr;
   if (int rc = get_tables(ws, h, w, st, &tab)) return rc;
 

@@ -455,7 +455,7 @@ def main():
                   'stream launches keep the programmatic dependent launch overlap)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-extras', action='store_true', help='skip the sub-records of the other configs / modes')
-  ap.add_argument('--e2e-steps', type=int, default=20)
+  ap.add_argument('--e2e-steps', type=int, default=20, help='0 skips the host-buffer leg (very large configs: it pins the whole input set)')
   ap.add_argument('--chunk-mb', type=int, default=0, help='workspace L2 chunk size (0 = library default)')
   ap.add_argument('--n-override', type=int, default=0, help='override the batch size of the config (memory-bounded runs)')
   ap.add_argument('--key64', action='store_true', help='force the 64-bit packed depth|index z-buffer key')
@@ -505,12 +505,17 @@ def main():
   inp = synth.make_inputs(gen_n, s, p, h, seed=1000 * rank + 99, dist=args.dist, sweep=cfg['sweep'])
   if gen_n < n:
     inp = {k: np.concatenate([v] * (n // gen_n), axis=0) for k, v in inp.items()}
-  host_inp = {k: torch.as_tensor(v).pin_memory() for k, v in inp.items()}
-  ews = _lib.Workspace(local_rank, 0, args.chunk_mb << 20)
-  e2e_ms, h2d, d2h, _ = e2e_measure(guidance, torch, dist, host_inp, args, local_rank, world, False, ews)
-  e2e_c_ms, h2d_c, d2h_c, _ = e2e_measure(guidance, torch, dist, host_inp, args, local_rank, world, True, ews)
-  ews.close()
-  ceiling = copy_ceiling(torch, dev, h2d, d2h)
+  if args.e2e_steps > 0:
+    host_inp = {k: torch.as_tensor(v).pin_memory() for k, v in inp.items()}
+    ews = _lib.Workspace(local_rank, 0, args.chunk_mb << 20)
+    e2e_ms, h2d, d2h, _ = e2e_measure(guidance, torch, dist, host_inp, args, local_rank, world, False, ews)
+    e2e_c_ms, h2d_c, d2h_c, _ = e2e_measure(guidance, torch, dist, host_inp, args, local_rank, world, True, ews)
+    ews.close()
+    ceiling = copy_ceiling(torch, dev, h2d, d2h)
+  else:
+    e2e_ms = e2e_c_ms = float('inf')
+    h2d = d2h = h2d_c = d2h_c = 0
+    ceiling = None
 
   extras = {}
   if not args.no_extras:

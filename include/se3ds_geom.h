@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SE3DS_GEOM_VERSION 100 /* major*100 + minor */
+#define SE3DS_GEOM_VERSION 200 /* major*100 + minor; 200: round-2 ABI (apply_bin flags, ring / compact / expand / quantize entry points) */
 
 typedef struct se3ds_ws se3ds_ws;
 

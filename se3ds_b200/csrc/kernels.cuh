@@ -384,7 +384,9 @@ __global__ void __launch_bounds__(kThreads, 8) splat_depth_kernel(const FusedPar
         }
       } else {  // rejected: only its depth feeds the reject bin (point_cloud_utils.py:146-159)
         word = kScInvalid | dflag;
-        const uint32_t zneg = ~f32_ordered(rad);
+        // a NaN depth never lowers a minimum (scatter-min ignores it); said explicitly -- the bit pattern of a NaN
+        // that the compiler re-materialises is not something to build an ordering on
+        const uint32_t zneg = (rad != rad) ? 0u : ~f32_ordered(rad);
         if (zneg) bin_update_z(bin, zneg);
       }
       __stcg(q.sc_flat + sc_frame + pix, word);
@@ -1026,7 +1028,7 @@ __global__ void __launch_bounds__(kThreads) cloud_depth_kernel(const CloudParams
     // reject bin: min depth of every rejected point (utils/point_cloud_utils.py:150-159)
     const bool rej = on && !valid;
     if (__any_sync(0xffffffffu, rej)) {
-      const uint32_t v = __reduce_max_sync(0xffffffffu, rej ? ~f32_ordered(pz) : 0u);
+      const uint32_t v = __reduce_max_sync(0xffffffffu, (rej && pz == pz) ? ~f32_ordered(pz) : 0u);  // a NaN depth never lowers the minimum
       if (v > bin_seen) {
         if ((threadIdx.x & 31) == 0) {
           bin_seen = __ldcg(q.bin);

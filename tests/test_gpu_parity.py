@@ -898,3 +898,17 @@ def test_project_cloud_rgb_fast_accumulator(mods, dtype, with_winner):
     if with_winner:
       np.testing.assert_array_equal(res[2].cpu().numpy(), o['winner'])
   assert (o['feat'] > 60000).any() or dtype == np.uint8
+
+
+@pytest.mark.parametrize('conv_name', ['EVAL_METRIC', 'GAN_MANAGER'])
+def test_nan_depth_never_enters_the_reject_bin(mods, conv_name):
+  """Regression (found by tests/tools/gpu_fuzz.py in round 2): a NaN depth makes a NaN radius; scatter-min ignores
+  it, so it must not lower the reject bin's minimum depth either.  Full bit parity with 20 % NaN depths, masked
+  and unmasked rows, both bin modes."""
+  inp = mods['synth'].make_inputs(1, 1, 2, 64, seed=13, dist='room', sweep=True)
+  rng = np.random.default_rng(4)
+  inp['depth'][rng.random(inp['depth'].shape) < 0.2] = np.nan
+  conv = getattr(mods['g'], conv_name)
+  for per_job in (True, False):
+    out, ref = _check_fused(mods, inp, conv=conv, mask_frames=1, per_job_bin=per_job)
+    assert 0 < ref['depth'][0, 0, 0, 0] < 1   # the owner pixel holds a real rejected depth, not 0 and not the fill

@@ -548,7 +548,9 @@ def main():
   if rank == 0:
     peak, peak_kind = measured_peak_gbs()
     names = ['splat_depth_kernel', 'splat_feat_kernel', 'resolve_kernel']
-    kalg = [src_bytes, 0, out_bytes]
+    # the algorithmic bytes of SURVEY 8(d), credited to the kernel that moves them: K2 reads the depth plane
+    # (4 B per source point), K3 the colours (3 B per source point), K4 writes the guidance (20 B per pixel)
+    kalg = [src_bytes * 4 // 7, src_bytes * 3 // 7, out_bytes]
     kms = m['shares'] if sum(m['shares']) > 0 else m['serial']
     dom = max(range(3), key=lambda i: kms[i])
     traffic = committed_traffic()
@@ -579,9 +581,10 @@ def main():
                      'unit': 'GB/s', 'frac': kalg[dom] / (kms[dom] * 1e-3) / 1e9 / peak, 'peak_kind': peak_kind,
                      'traffic': (traffic or {}).get(names[dom]), 'ms': kms[dom],
                      'how': 'share of the pipelined step: last end-of-kernel %globaltimer stamp minus that of the kernel before it '
-                            '(se3ds_ws_profile mode 2); the shares add up to the step',
-                     'note': ('splat_depth is bound by instruction issue and latency, not by HBM (ncu: profiles/r02_*); '
-                              'resolve is the HBM-bound kernel, see roofline_hbm_kernel') if dom == 0 else ''},
+                            '(se3ds_ws_profile mode 2); the shares add up to the step.  Algorithmic bytes per kernel: depth (4 B/pt) to '
+                            'splat_depth, colours (3 B/pt) to splat_feat, guidance (20 B/px) to resolve; roofline_step holds the whole pass',
+                     'note': ('splat_depth (instruction issue + latency) and splat_feat (latency of a dependent gather + reduction per point) '
+                              'are not HBM-bound (ncu: profiles/r02_*); resolve is the HBM-bound kernel, see roofline_hbm_kernel') if dom != 2 else ''},
         'roofline_hbm_kernel': {'bound': 'hbm', 'kernel': names[2], 'achieved': kalg[2] / (kms[2] * 1e-3) / 1e9,
                                 'peak': peak, 'unit': 'GB/s', 'frac': kalg[2] / (kms[2] * 1e-3) / 1e9 / peak,
                                 'traffic': (traffic or {}).get(names[2]), 'ms': kms[2]},

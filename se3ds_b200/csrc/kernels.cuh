@@ -176,12 +176,13 @@ __device__ __forceinline__ uint32_t ldg_u8_stream(const void* p, uint64_t pol) {
 // A pixel's raw colour held in registers: uint8 sources stay packed in one word until they are used.
 template <typename RGB_T> struct RawRGB;
 template <> struct RawRGB<uint8_t> {
-  uint32_t r = 0, g = 0, b = 0;  // kept apart: combining them right after the loads would wait for the loads
+  uint32_t v = 0;  // r | g << 8 | b << 16
   __device__ __forceinline__ void load(const uint8_t* rgb, size_t pix, uint64_t pol) {
     const uint8_t* p = rgb + pix * 3;
-    r = ldg_u8_stream(p, pol); g = ldg_u8_stream(p + 1, pol); b = ldg_u8_stream(p + 2, pol);
+    v = ldg_u8_stream(p, pol) | (ldg_u8_stream(p + 1, pol) << 8) | (ldg_u8_stream(p + 2, pol) << 16);
   }
-  __device__ __forceinline__ int3 get() const { return make_int3(r, g, b); }
+  __device__ __forceinline__ int3 get() const { return make_int3(v & 255u, (v >> 8) & 255u, v >> 16); }
+  __device__ __forceinline__ uint32_t packed() const { return v; }
 };
 template <> struct RawRGB<int> {
   int3 v = {0, 0, 0};
@@ -190,6 +191,7 @@ template <> struct RawRGB<int> {
     v = make_int3((int)ldg_u32_stream(p, pol), (int)ldg_u32_stream(p + 1, pol), (int)ldg_u32_stream(p + 2, pol));
   }
   __device__ __forceinline__ int3 get() const { return v; }
+  __device__ __forceinline__ uint32_t packed() const { return 0u; }  // (only uint8 colours have a packed form)
 };
 
 // Feature of a source pixel as the reference sees it after mask_pano + unprojection
@@ -205,6 +207,14 @@ __device__ __forceinline__ uint2 pack_f16x4(int3 f) {
   const uint32_t g = __half_as_ushort(__int2half_rn(f.y));
   const uint32_t b = __half_as_ushort(__int2half_rn(f.z));
   return make_uint2(r | (g << 16), b);
+}
+// the same for three bytes r | g << 8 | b << 16 without conversions: 0x6400 | x is 1024 + x in float16 (ulp 1), and
+// subtracting 1024 is exact -- two byte permutes and two packed subtractions instead of three I2F and two permutes
+__device__ __forceinline__ uint2 pack_f16x4_u8(uint32_t c) {
+  const __half2 k = __halves2half2(__ushort_as_half((unsigned short)0x6400), __ushort_as_half((unsigned short)0x6400));
+  const uint32_t rg = __byte_perm(c, 0x64u, 0x4140), b0 = __byte_perm(c, 0x64u, 0x4542);
+  const __half2 hrg = __hsub2(*reinterpret_cast<const __half2*>(&rg), k), hb0 = __hsub2(*reinterpret_cast<const __half2*>(&b0), k);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&hrg), *reinterpret_cast<const uint32_t*>(&hb0));
 }
 __device__ __forceinline__ float3 unpack_f16x4(uint2 v) {
   return make_float3(__half2float(__ushort_as_half((unsigned short)(v.x & 0xffff))),
@@ -623,28 +633,34 @@ __global__ void __launch_bounds__(kThreads, 16) splat_feat_kernel(const FusedPar
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       const bool live = !(scf[k] & kScDropped);
-      const bool haspix = live && !(scf[k] & kScInvalid);
-      const int3 f = point_feat(q, scf[k] & kScDepthInv, masked, raw[k].get());
-      bool rejected = live && !haspix;
-      if (haspix) {
-        // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
-        const float zmin = fminf(__uint_as_float(zbits[k]), q.depth_scale);  // armed bits are a NaN: fminf -> depth_scale
-        const bool keep = scr[k] < __fadd_rn(zmin, 0.1f);
-        if (keep) {
-          // With several source frames many points share a pixel and most of them cannot raise the
-          // maximum any more: a plain read (the buffer only grows, a stale value is a safe filter)
-          // saves the reduction.  With one frame, or a workspace that does not fit in L2, the read
-          // costs more than it saves (measured: c3 -25 %, c5 +19 % for K3), so the host decides.
-          bool need = true;
-          if (q.prefilter_f) {
-            const float3 cur = unpack_f16x4(__ldcg(fb + (scf[k] & kScPixMask)));
-            need = (float)f.x > cur.x || (float)f.y > cur.y || (float)f.z > cur.z;
-          }
-          if (need) red_max_f16x4(fb + (scf[k] & kScPixMask), pack_f16x4(f));
+      const bool haspix = !(scf[k] & (kScDropped | kScInvalid));
+      // point_cloud_utils.py:168-169: depth < min_depth + 0.1 (min_depth includes the init fill)
+      const float zmin = fminf(__uint_as_float(zbits[k]), q.depth_scale);  // armed bits are a NaN: fminf -> depth_scale
+      const bool keep = haspix && scr[k] < __fadd_rn(zmin, 0.1f);
+      // the feature is the raw colour unless the depth was invalid or the row is masked (pano_utils.py:225,262-265)
+      const bool plain = std::is_same<RGB_T, uint8_t>::value && !masked && !(scf[k] & kScDepthInv);
+      if (keep) {
+        uint2 packed;
+        int3 f = make_int3(0, 0, 0);
+        if (plain) {
+          packed = pack_f16x4_u8(raw[k].packed());
+        } else {
+          f = point_feat(q, scf[k] & kScDepthInv, masked, raw[k].get());
+          packed = pack_f16x4(f);
         }
-        rejected = !keep;
-      }
-      if (rejected) {
+        // With several source frames many points share a pixel and most of them cannot raise the
+        // maximum any more: a plain read (the buffer only grows, a stale value is a safe filter)
+        // saves the reduction.  With one frame, or a workspace that does not fit in L2, the read
+        // costs more than it saves (measured: c3 -25 %, c5 +19 % for K3), so the host decides.
+        bool need = true;
+        if (q.prefilter_f) {
+          if (plain) f = raw[k].get();
+          const float3 cur = unpack_f16x4(__ldcg(fb + (scf[k] & kScPixMask)));
+          need = (float)f.x > cur.x || (float)f.y > cur.y || (float)f.z > cur.z;
+        }
+        if (need) red_max_f16x4(fb + (scf[k] & kScPixMask), packed);
+      } else if (live) {  // rejected: its feature goes to the reject bin
+        const int3 f = point_feat(q, scf[k] & kScDepthInv, masked, raw[k].get());
         bin_has = true;
         bin_f.x = max(bin_f.x, f.x); bin_f.y = max(bin_f.y, f.y); bin_f.z = max(bin_f.z, f.z);
       }

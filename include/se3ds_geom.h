@@ -75,6 +75,12 @@ typedef enum { SE3DS_U8 = 0, SE3DS_I32 = 1, SE3DS_F32 = 2 } se3ds_dtype;
                                      is lost: clip(x / 255, 0, 1) is a function of that byte and
                                      mask = 0 < depth < 1; se3ds_expand_guidance restores the float32
                                      tensors bit for bit.  Not combinable with SE3DS_FLAG_RAW_FEATURES. */
+#define SE3DS_FLAG_HOST_ASYNC 64u /* se3ds_reproject_host only: return as soon as the copies and kernels are
+                                     enqueued on the workspace's own streams; se3ds_ws_host_wait completes the
+                                     call.  Two workspaces used in turn keep the host link busy in both
+                                     directions: batch i+1 travels to the device while batch i travels back.
+                                     The batch then moves in one DMA transfer per tensor (the blocking call
+                                     pipelines item by item inside the call instead). */
 
 int se3ds_version(void);
 const char* se3ds_status_string(int status);
@@ -237,13 +243,19 @@ int se3ds_apply_bin(const float* bin, float depth_scale, unsigned flags, float* 
 
 /* Same as se3ds_reproject with HOST buffers (pinned memory recommended): copies the inputs to the
  * device, runs the fused path and copies the guidance tensors back, pipelined over batch items on
- * the workspace's own streams.  Blocks until the outputs are complete. */
+ * the workspace's own streams.  Blocks until the outputs are complete, unless SE3DS_FLAG_HOST_ASYNC is
+ * given: the call then returns once everything is enqueued, the host buffers (inputs and outputs) belong
+ * to the library until se3ds_ws_host_wait(ws) returns, and a further host call on the same workspace
+ * waits for the pending one first. */
 int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, const float* depth_host,
                          const float* src_pos_host, const float* tgt_pos_host, int n, int s, int p,
                          int h, int w, float depth_scale, double mask_proportion, int mask_frames,
                          int unproject_void, int project_void, unsigned flags,
                          float* proj_image_host, float* proj_depth_host, float* proj_mask_host,
                          int32_t* winner_out_host);
+
+/* Completes a pending SE3DS_FLAG_HOST_ASYNC call of this workspace (no-op when nothing is pending). */
+int se3ds_ws_host_wait(se3ds_ws* ws);
 
 /* tf.image.resize with half-pixel centres, as utils/pano_utils.py:203-208 uses it when
  * size_mult != 1: in (N,H,W,C) of `dtype` -> out (N,out_h,out_w,C); bilinear == 0: 'nearest', the

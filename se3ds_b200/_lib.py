@@ -24,6 +24,7 @@ FLAG_KEY64 = 4
 FLAG_INPUTS_READY = 8
 FLAG_RAW_FEATURES = 16
 FLAG_COMPACT_OUT = 32
+FLAG_HOST_ASYNC = 64
 
 _DTYPES = {torch.uint8: U8, torch.int32: I32, torch.float32: F32}
 
@@ -63,6 +64,7 @@ SIGNATURES = {
     'se3ds_apply_bin': [_vp, _f, _u, _vp, _vp, _vp, _vp, _vp],
     'se3ds_reproject_host': [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, _i, _i, _i, _u, _vp, _vp,
                              _vp, _vp],
+    'se3ds_ws_host_wait': [_vp],
     'se3ds_resize': [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     'se3ds_interpolate_bilinear': [_vp, _vp, _i, _i, _i, _i, _ll, _i, _vp, _vp],
     'se3ds_filtered_coords_and_feats': [_vp, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp],
@@ -179,6 +181,10 @@ class Workspace:
     d = (ctypes.c_float * 2)()
     check(load().se3ds_ws_verify_read(self.handle, ctypes.byref(c), ctypes.byref(d)))
     return dict(points=c[0], certified=c[1], wrong=c[2], max_dev_x=d[0], max_dev_y=d[1])
+
+  def host_wait(self):
+    """Completes a pending asynchronous se3ds_reproject_host call of this workspace."""
+    check(load().se3ds_ws_host_wait(self.handle))
 
   def profile(self, mode):
     """0 / False off, 1 / True cudaEvents between the launches (no overlap), 2 end-of-kernel stamps."""

@@ -240,10 +240,13 @@ def reproject_host(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.
                    project_void: int = constants.INVALID_RGB_VALUE, filter_void: bool = False,
                    per_job_bin: bool = False, return_winner: bool = False,
                    out: Optional[Dict[str, torch.Tensor]] = None, device: int = 0,
-                   workspace: Optional[_lib.Workspace] = None, compact: bool = False) -> Dict[str, torch.Tensor]:
+                   workspace: Optional[_lib.Workspace] = None, compact: bool = False,
+                   wait: bool = True) -> Dict[str, torch.Tensor]:
   """`reproject` for HOST tensors (pinned memory recommended): host->device copies, the fused
   kernels and the device->host copies of the guidance tensors all happen inside the C ABI call
-  (se3ds_reproject_host), which returns when the host outputs are complete."""
+  (se3ds_reproject_host), which returns when the host outputs are complete.  wait=False
+  (SE3DS_FLAG_HOST_ASYNC) returns once the work is enqueued: inputs and outputs must be left alone until
+  `workspace.host_wait()`; see HostReprojector for the double-buffered loop built on it."""
   rgb, depth, src_pos, tgt_pos = _prep(rgb, depth, src_pos, tgt_pos, False)
   for t in (rgb, depth, src_pos, tgt_pos):
     if t.is_cuda:
@@ -266,13 +269,61 @@ def reproject_host(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.
   pdepth = buf('proj_depth', (j, h, w, 1))
   winner = buf('winner', (j, h, w), torch.int32) if return_winner else None
   flags = ((_lib.FLAG_FILTER_VOID if filter_void else 0) | (_lib.FLAG_BIN_PER_JOB if per_job_bin else 0) |
-           (_lib.FLAG_COMPACT_OUT if compact else 0))
+           (_lib.FLAG_COMPACT_OUT if compact else 0) | (0 if wait else _lib.FLAG_HOST_ASYNC))
+  if not wait and workspace is None:
+    raise ValueError('wait=False needs an explicit workspace (the one to call host_wait() on)')
   ws = workspace or _lib.default_workspace(torch.device('cuda', device), role='host')
   _lib.check(_lib.load().se3ds_reproject_host(
       ws.handle, _lib.ptr(rgb), _lib.dtype_code(rgb), _lib.ptr(depth), _lib.ptr(src_pos), _lib.ptr(tgt_pos),
       n, s, p, h, w, float(depth_scale), float(mask_proportion), int(mask_frames), int(unproject_void),
       int(project_void), flags, _lib.ptr(image), _lib.ptr(pdepth), _lib.ptr(mask), _lib.ptr(winner)))
   return out
+
+
+class HostReprojector(object):
+  """Double-buffered `reproject_host`: `depth` workspaces (each with its own streams and staging buffers)
+  are used in turn, so batch i+1 travels to the device while batch i is computed and travels back -- the
+  host link is busy in both directions.  The reference has no counterpart (its tensors live wherever
+  TensorFlow puts them); this is what a server that feeds host batches calls.
+
+    pipe = HostReprojector(device=0, depth=2, mask_frames=1, compact=True)
+    for batch in batches:
+      done = pipe.submit(*batch)      # None while the pipeline fills, else the oldest finished result
+      if done is not None: consume(done)
+    for done in pipe.flush(): consume(done)
+
+  The tensors handed to submit() must stay untouched until their result comes back.  A returned result
+  (pinned host tensors, see reproject_host) stays valid until the next submit(): there is one more set of
+  output buffers than workspaces."""
+
+  def __init__(self, device: int = 0, depth: int = 2, **kwargs):
+    if depth < 1:
+      raise ValueError('depth must be >= 1')
+    self._kw = dict(kwargs, device=device)
+    self._ws = [_lib.Workspace(device) for _ in range(depth)]
+    self._out = [dict() for _ in range(depth + 1)]
+    self._calls = 0
+    self._pending = []  # (workspace slot, output slot, inputs kept alive) in submission order
+
+  def submit(self, rgb, depth, src_pos, tgt_pos):
+    slot, oslot = self._calls % len(self._ws), self._calls % len(self._out)
+    done = self._finish() if len(self._pending) == len(self._ws) else None  # the oldest call owns this workspace
+    reproject_host(rgb, depth, src_pos, tgt_pos, out=self._out[oslot], workspace=self._ws[slot], wait=False, **self._kw)
+    self._pending.append((slot, oslot, (rgb, depth, src_pos, tgt_pos)))
+    self._calls += 1
+    return done
+
+  def _finish(self):
+    slot, oslot, _ = self._pending.pop(0)
+    self._ws[slot].host_wait()
+    return self._out[oslot]
+
+  def flush(self):
+    """Completes everything in flight; -> the results in submission order (all valid until the next submit())."""
+    res = []
+    while self._pending:
+      res.append(self._finish())
+    return res
 
 
 class FrameRing(object):

@@ -422,6 +422,41 @@ def test_reproject_host_equals_device(mods):
     assert torch.equal(host[k], dev[k].cpu()), k
 
 
+@pytest.mark.parametrize('compact,depth', [(False, 2), (True, 2), (True, 3), (False, 1)])
+def test_host_reprojector_pipeline_equals_blocking_calls(mods, compact, depth):
+  """SE3DS_FLAG_HOST_ASYNC + se3ds_ws_host_wait behind guidance.HostReprojector: batches of different shapes
+  and contents in flight on `depth` workspaces give, in submission order, exactly what the blocking call gives."""
+  g = mods['g']
+  shapes = [(2, 1, 1, 64), (3, 2, 2, 32), (1, 1, 3, 48), (2, 1, 1, 64), (4, 1, 1, 32), (2, 2, 1, 64), (1, 1, 1, 16)]
+  batches = [mods['synth'].make_inputs(*sh, seed=70 + i, dist='rand', sweep=sh[2] > 1) for i, sh in enumerate(shapes)]
+  host = [tuple(torch.as_tensor(b[k]).pin_memory() for k in ('rgb', 'depth', 'src_pos', 'tgt_pos')) for b in batches]
+  want = [{k: v.clone() for k, v in g.reproject_host(*h, mask_frames=1, compact=compact).items()} for h in host]
+  pipe = g.HostReprojector(device=0, depth=depth, mask_frames=1, compact=compact)
+  got = []
+  for h in host:
+    done = pipe.submit(*h)
+    if done is not None:
+      got.append({k: v.clone() for k, v in done.items()})
+  got += [{k: v.clone() for k, v in d.items()} for d in pipe.flush()]
+  assert len(got) == len(want)
+  for a, b in zip(got, want):
+    assert a.keys() == b.keys()
+    for k in b:
+      assert torch.equal(a[k], b[k]), k
+  # a blocking call on a workspace with a pending asynchronous call waits for it first
+  ws = mods['lib'].Workspace(0)
+  o1, o2 = {}, {}
+  g.reproject_host(*host[0], mask_frames=1, compact=compact, workspace=ws, out=o1, wait=False)
+  g.reproject_host(*host[1], mask_frames=1, compact=compact, workspace=ws, out=o2)
+  ws.host_wait()  # nothing pending any more: a no-op
+  for o, b in ((o1, want[0]), (o2, want[1])):
+    for k in b:
+      assert torch.equal(o[k], b[k]), k
+  with pytest.raises(ValueError):
+    g.reproject_host(*host[0], mask_frames=1, wait=False)
+  ws.close()
+
+
 def test_full_size_c2_against_oracle(mods):
   """BASELINE.json configs[1]: 512x1024, batch 8 -- full size, still bit-exact."""
   inp = mods['synth'].make_inputs(8, 1, 1, 512, seed=13, dist='room')

@@ -493,19 +493,22 @@ def main():
 
   import torch
   import torch.distributed as dist
-  from se3ds_b200 import _lib, guidance, synth
+  from se3ds_b200 import _lib, guidance, hostmem, synth
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
   torch.cuda.set_device(local_rank)
+  numa = hostmem.bind_to_gpu_numa_node(local_rank)  # pinned buffers are placed by first touch: allocate them next to the GPU
   dev = torch.device('cuda', local_rank)
-  try:  # run (and first-touch the pinned host buffers) on the CPUs next to this rank's GPU
-    import pynvml
-    pynvml.nvmlInit()
-    pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
-  except Exception:  # pylint: disable=broad-except
-    pass
+  if numa['cpus'] is None:  # sysfs did not say: let NVML pick the CPUs next to this rank's GPU
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+      numa['nvml_affinity'] = len(os.sched_getaffinity(0))
+    except Exception:  # pylint: disable=broad-except
+      pass
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 
@@ -593,7 +596,7 @@ def main():
                        'float32 guidance tensors back, all results complete before the clock stops',
                 'per_rank_gbs': {'h2d': h2d / (e2e_p_ms * 1e-3) / 1e9, 'd2h': d2h / (e2e_p_ms * 1e-3) / 1e9,
                                  'note': 'bytes of the step / time of the step (uploads, kernels and downloads overlap)'},
-                'host_link_ceiling_gbs': ceiling,
+                'host_link_ceiling_gbs': ceiling, 'numa': numa,
                 'blocking_call': {'value': world * n * p / (e2e_ms * 1e-3), 'unit': 'panos/s', 'ms_per_step': e2e_ms,
                                   'note': 'one se3ds_reproject_host call at a time (pipelined over the batch items inside the call only)'},
                 'compact_out': {'value': world * n * p / (e2e_pc_ms * 1e-3), 'unit': 'panos/s', 'ms_per_step': e2e_pc_ms,

@@ -78,3 +78,11 @@ def test_plan_argument_errors():
     _lib.plan_chunks(0, 1, 1, 16)
   with pytest.raises(ValueError):
     _lib.plan_chunks(1, 1, 1, 16, lanes=5)
+
+
+def test_numa_helper_parses_cpulists_and_degrades_gracefully():
+  """se3ds_b200.hostmem: sysfs cpulist syntax; without a CUDA device nothing is bound."""
+  from se3ds_b200 import hostmem
+  assert hostmem._parse_cpulist('0-3,8,10-11') == {0, 1, 2, 3, 8, 10, 11}
+  assert hostmem._parse_cpulist('') == set()
+  assert hostmem._read('/nonexistent/se3ds') is None

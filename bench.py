@@ -228,8 +228,16 @@ def sharded_record(args, world, rank, dev, steps=60, warmup=5):
                   'bytes_held_per_rank': sum(v.numel() * v.element_size() for v in out.values() if torch.is_tensor(v))}
   # the prepared (serving) form: buffers, kernel calls and maps built once, run() repeated
   for label, kw in (('prepared_gather_expand', dict(gather=True, expand=True)), ('prepared_gather_compact', dict(gather=True, expand=False)),
+                    ('prepared_multicast_expand', dict(gather=True, expand=True, wire='multicast')),
+                    ('prepared_multicast_compact', dict(gather=True, expand=False, wire='multicast')),
                     ('prepared_local', dict(gather=False, expand=False))):
-    plan = parallel.ShardedReprojection(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, pieces=args.pieces, **kw)
+    try:
+      plan = parallel.ShardedReprojection(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, pieces=args.pieces, **kw)
+    except Exception as e:  # pylint: disable=broad-except
+      if kw.get('wire') != 'multicast':
+        raise
+      rec[label] = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
+      continue
     for _ in range(warmup):
       out = plan.run()
     torch.cuda.synchronize()

@@ -17,7 +17,7 @@ try:
   j = json.loads(open('gpurun_out/${TAG}_scale_${g}.json').read().strip().splitlines()[-1])
   print('gpus ${g}: panos/s %.0f ms/step %.4f e2e %.0f compact e2e %.0f' % (j['value'], j['ms_per_step'], j['e2e']['value'], j['e2e']['compact_out']['value']))
   if 'sharded_c4' in j['extra']:
-    print('   sharded c4:', {k: round(v['ms_per_step'], 3) for k, v in j['extra']['sharded_c4'].items() if isinstance(v, dict)})
+    print('   sharded c4:', {k: (round(v['ms_per_step'], 3) if 'ms_per_step' in v else v) for k, v in j['extra']['sharded_c4'].items() if isinstance(v, dict)})
   print('   c4 one GPU ms', j['extra'].get('c4', {}).get('ms_per_step'))
 except Exception as e:
   print('failed', e, open('gpurun_out/${TAG}_scale_${g}.err').read()[-2500:])

@@ -787,13 +787,14 @@ __global__ void __launch_bounds__(kThreads, KEY64 ? 10 : 12) resolve_kernel(cons
   pdl_enter();
   constexpr bool STAGED = PPT == 4 && !COMPACT;  // RGB stores go through shared memory (below)
   __shared__ float4 stage[STAGED ? kThreads * 3 : 1];
+  __shared__ __align__(16) uint32_t stage8[(PPT == 4 && COMPACT) ? kThreads * 3 : 1];  // the same for the packed colours
   const int lj = blockIdx.z;
   int n, p;
   if (q.PC == 1) { n = q.n0 + lj; p = q.p0; } else { const int a = lj / q.PC; n = q.n0 + a; p = q.p0 + (lj - a * q.PC); }
   const int job = n * q.P + p;
   const int row = blockIdx.y;
   const int col0 = (blockIdx.x * kThreads + threadIdx.x) * PPT;
-  if constexpr (STAGED) {
+  if constexpr (PPT == 4) {
     if (((blockIdx.x * kThreads + (threadIdx.x & ~31)) + 32) * PPT > q.W) {  // ragged warp: plain path
       if (col0 >= q.W) return;
     }
@@ -815,9 +816,29 @@ __global__ void __launch_bounds__(kThreads, KEY64 ? 10 : 12) resolve_kernel(cons
     __stcs(reinterpret_cast<float4*>(q.out_depth + o), make_float4(od[0], od[1], od[2], od[3]));
     if constexpr (COMPACT) {  // 12 bytes of colour per thread, 384 contiguous bytes per warp
       uint32_t* im8 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(q.out_image) + o * 3);
-      __stcs(im8, pk[0] | (pk[1] << 24));
-      __stcs(im8 + 1, (pk[1] >> 8) | (pk[2] << 16));
-      __stcs(im8 + 2, (pk[2] >> 16) | (pk[3] << 8));
+      const uint32_t w0 = pk[0] | (pk[1] << 24), w1 = (pk[1] >> 8) | (pk[2] << 16), w2 = (pk[2] >> 16) | (pk[3] << 8);
+      if (((blockIdx.x * kThreads + (threadIdx.x & ~31)) + 32) * PPT <= q.W) {
+        // a full warp: through shared memory, so that each store instruction writes 128 contiguous bytes (whole
+        // sectors -- what a store that leaves the GPU through NVLink, e.g. to a multicast mapping, wants)
+        const unsigned lane = threadIdx.x & 31u;
+        uint32_t* wstage = stage8 + (threadIdx.x >> 5) * 96;
+        wstage[lane * 3 + 0] = w0;
+        wstage[lane * 3 + 1] = w1;
+        wstage[lane * 3 + 2] = w2;
+        __syncwarp();
+        uint32_t* im0 = im8 - lane * 3;
+        if ((reinterpret_cast<uintptr_t>(im0) & 15u) == 0) {  // 24 lanes x 16 bytes
+          if (lane < 24) __stcs(reinterpret_cast<uint4*>(im0) + lane, reinterpret_cast<const uint4*>(wstage)[lane]);
+        } else {
+          __stcs(im0 + lane, wstage[lane]);
+          __stcs(im0 + 32 + lane, wstage[32 + lane]);
+          __stcs(im0 + 64 + lane, wstage[64 + lane]);
+        }
+      } else {
+        __stcs(im8, w0);
+        __stcs(im8 + 1, w1);
+        __stcs(im8 + 2, w2);
+      }
     } else {
     __stcs(reinterpret_cast<float4*>(q.out_mask + o), make_float4(om[0], om[1], om[2], om[3]));
     float4* im = reinterpret_cast<float4*>(q.out_image + o * 3);

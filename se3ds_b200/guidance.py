@@ -148,6 +148,14 @@ class PreparedReprojection:
     _lib.check(self._fn(*self._args, st))
     return self.out
 
+  def redirect_outputs(self, image_ptr: int, depth_ptr: int):
+    """The resolve kernel stores the (compact) colour and depth planes at these device addresses instead of
+    `out`'s tensors -- e.g. the NVSwitch multicast mapping of a symmetric buffer (parallel.ShardedReprojection,
+    wire='multicast': one store reaches every rank).  The addresses are only ever written."""
+    a = list(self._args)
+    a[17], a[18] = ctypes.c_void_p(image_ptr), ctypes.c_void_p(depth_ptr)
+    self._args = tuple(a)
+
 
 def prepare(rgb, depth, src_pos, tgt_pos, depth_scale: float = constants.DEPTH_SCALE,
             mask_proportion: float = 0.125, mask_frames: int = 0,

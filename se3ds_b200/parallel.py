@@ -232,12 +232,20 @@ class ShardedReprojection(object):
   all-gathers (async, they travel while the next piece renders), one 5-float all-reduce for the reject bin, the bin
   patch and -- with expand=True -- one expand kernel that writes the float32 tensors in job order.
 
+  wire='multicast' (NVSwitch): the gather buffer is symmetric memory (torch.distributed._symmetric_memory) and the
+  resolve kernel of every rank stores its compact planes through the buffer's MULTICAST mapping -- one store
+  instruction lands in the same slot of every rank's buffer, the switch replicates it.  Compute and collective are
+  one kernel: there is no all-gather call, no pieces, and a rank's NVLink egress is its own 7 B per pixel instead of
+  (world - 1) x that.  Two symmetric-memory barriers per run() order the stores against the readers of the
+  previous and of this result.  Raises RuntimeError where the platform has no multicast (callers fall back to
+  wire='nccl').
+
   Restrictions of the prepared form: the job count divides by the world size, bin_mode 'call' or 'job', compact wire.
   The tensors passed in are kept and read in place by every run()."""
 
   def __init__(self, rgb, depth, src_pos, tgt_pos, *, group=None, bin_mode: str = 'call', pieces: int = 2,
                gather: bool = True, expand: bool = True, depth_scale: float = constants.DEPTH_SCALE, mask_frames: int = 0,
-               **conv):
+               wire: str = 'nccl', **conv):
     from . import guidance
     self.g = guidance
     self.group, self.bin_mode, self.gather, self.expand, self.depth_scale = group, bin_mode, gather, expand, depth_scale
@@ -256,16 +264,32 @@ class ShardedReprojection(object):
     src_pos = torch.as_tensor(src_pos).reshape(n, s, 3)
     dev = rgb.device
     world, rank = self.world, self.rank
+    if wire not in ('nccl', 'multicast'):
+      raise ValueError("wire must be 'nccl' or 'multicast'")
     multi = gather and world > 1
+    self.mcast = multi and wire == 'multicast'
     cap = jobs // world
     lo = rank * cap
-    npieces = max(1, min(cap, pieces)) if multi else 1
+    npieces = max(1, min(cap, pieces)) if multi and not self.mcast else 1  # multicast: the transfer is inside the kernel
     while cap % npieces:
       npieces -= 1
     jpp = cap // npieces
     slots = npieces * world * jpp if multi else cap
-    self.rgb8 = torch.empty((slots, h, w, 3), dtype=torch.uint8, device=dev)
-    self.depth = torch.empty((slots, h, w, 1), dtype=torch.float32, device=dev)
+    self.symm = None
+    if self.mcast:
+      import torch.distributed._symmetric_memory as symm_mem
+      px = h * w
+      depth_off = (slots * px * 3 + 255) // 256 * 256  # [uint8 colours | float32 depth] in one symmetric allocation
+      self._symm_buf = symm_mem.empty(depth_off + slots * px * 4, dtype=torch.uint8, device=dev)
+      self.symm = symm_mem.rendezvous(self._symm_buf, group if group is not None else dist.group.WORLD)
+      mc = int(self.symm.multicast_ptr)
+      if not mc:
+        raise RuntimeError('symmetric memory on this platform has no multicast mapping (NVSwitch multicast unavailable)')
+      self.rgb8 = self._symm_buf[:slots * px * 3].view(slots, h, w, 3)
+      self.depth = self._symm_buf[depth_off:depth_off + slots * px * 4].view(torch.float32).view(slots, h, w, 1)
+    else:
+      self.rgb8 = torch.empty((slots, h, w, 3), dtype=torch.uint8, device=dev)
+      self.depth = torch.empty((slots, h, w, 1), dtype=torch.float32, device=dev)
     self.multi, self.npieces, self.world_jpp, self.jpp, self.jobs, self.lo, self.hi = multi, npieces, world * jpp, jpp, jobs, lo, lo + cap
     self.calls = []   # (piece, PreparedReprojection, bin tensor or None)
     for c in range(npieces):
@@ -281,6 +305,8 @@ class ShardedReprojection(object):
         plan = guidance.prepare(rgb[n0:n1].contiguous(), depth[n0:n1].contiguous(), src_pos[n0:n1].contiguous(),
                                 tgt_pos[n0:n1, p0:p1].contiguous(), depth_scale=depth_scale, mask_frames=mask_frames,
                                 per_job_bin=(bin_mode == 'job'), compact=True, out=out, bin_out=binb, **conv)
+        if self.mcast:  # same slot, every rank's buffer
+          plan.redirect_outputs(mc + s0 * px * 3, mc + depth_off + s0 * px * 4)
         self.calls.append((c, plan, binb))
         done += cnt
     self.job_map = None
@@ -292,11 +318,12 @@ class ShardedReprojection(object):
 
   def run(self) -> Dict[str, torch.Tensor]:
     handles = []
-    piece = 0
+    if self.mcast:
+      self.symm.barrier(channel=0)  # every rank is done reading the previous result: its slots may be overwritten
     for i, (c, plan, _) in enumerate(self.calls):
       plan.run()
       last_of_piece = i + 1 == len(self.calls) or self.calls[i + 1][0] != c
-      if self.multi and last_of_piece:
+      if self.multi and last_of_piece and not self.mcast:
         for b in (self.rgb8, self.depth):
           blk = b[c * self.world_jpp:(c + 1) * self.world_jpp]
           handles.append(dist.all_gather_into_tensor(blk, blk[self.rank * self.jpp:(self.rank + 1) * self.jpp],
@@ -311,6 +338,8 @@ class ShardedReprojection(object):
         dist.all_reduce(red, op=dist.ReduceOp.MAX, group=self.group)
     for hnd in handles:
       hnd.wait()
+    if self.mcast:
+      self.symm.barrier(channel=1)  # every rank's resolve kernels have finished: all slots of this buffer are complete
     out = {'proj_rgb_u8': self.rgb8, 'proj_depth': self.depth}
     if self.bin_mode == 'call' and self.jobs > 0 and (self.multi or self.owns_job0):
       vec = torch.cat([-self.red[:1], self.red[1:4], -self.red[4:5]])

@@ -552,10 +552,13 @@ def main():
   if not args.no_extras:
     # other configs / modes, short runs (sub-records; the headline stays the config above)
     def sub(name, c, **kw):
-      r = gpu_measure(*mods, c, args, dev, local_rank, world, rank, kw.pop('steps'), 5, **kw)
+      nsteps = kw.pop('steps')
+      r = gpu_measure(*mods, c, args, dev, local_rank, world, rank, nsteps, 5, **kw)
       sb, ob = alg_bytes(c)
       hw = c['h'] * 2 * c['h']
-      return {'workload': workload_name(name, c, args.dist), 'ms_per_step': r['ms_step'], 'steps': kw.get('steps'),
+      if min(r['shares']) < 0:  # several chunks on two lanes: a chunk's first kernel ends before the other lane's last one
+        r['shares'] = None
+      return {'workload': workload_name(name, c, args.dist), 'ms_per_step': r['ms_step'], 'steps': nsteps,
               'panos_per_s': world * c['n'] * c['p'] / (r['ms_step'] * 1e-3),
               'mpoints_per_s': world * c['n'] * c['s'] * c['p'] * hw / (r['ms_step'] * 1e-3) / 1e6,
               'roofline_step_frac': (sb + ob) / (r['ms_step'] * 1e-3) / 1e9 / measured_peak_gbs()[0],
@@ -617,9 +620,13 @@ def main():
         'roofline': {'bound': 'hbm', 'kernel': names[dom], 'achieved': kalg[dom] / (kms[dom] * 1e-3) / 1e9, 'peak': peak,
                      'unit': 'GB/s', 'frac': kalg[dom] / (kms[dom] * 1e-3) / 1e9 / peak, 'peak_kind': peak_kind,
                      'traffic': (traffic or {}).get(names[dom]), 'ms': kms[dom],
+                     'step_frac': (src_bytes + out_bytes) / (ms_step * 1e-3) / 1e9 / peak,
+                     'frac_r1_accounting': ([src_bytes, 0, out_bytes][dom] / (kms[dom] * 1e-3) / 1e9 / peak),
                      'how': 'share of the pipelined step: last end-of-kernel %globaltimer stamp minus that of the kernel before it '
                             '(se3ds_ws_profile mode 2); the shares add up to the step.  Algorithmic bytes per kernel: depth (4 B/pt) to '
-                            'splat_depth, colours (3 B/pt) to splat_feat, guidance (20 B/px) to resolve; roofline_step holds the whole pass',
+                            'splat_depth, colours (3 B/pt) to splat_feat, guidance (20 B/px) to resolve; step_frac / roofline_step hold the whole pass '
+                            '(SURVEY 8d: 7 B per source point + 20 B per target pixel over the timed step); frac_r1_accounting credits all source '
+                            'bytes to splat_depth and none to splat_feat, as the round-1 line did',
                      'note': ('splat_depth (instruction issue + latency) and splat_feat (latency of a dependent gather + reduction per point) '
                               'are not HBM-bound (ncu: profiles/r02_*); resolve is the HBM-bound kernel, see roofline_hbm_kernel') if dom != 2 else ''},
         'roofline_hbm_kernel': {'bound': 'hbm', 'kernel': names[2], 'achieved': kalg[2] / (kms[2] * 1e-3) / 1e9,

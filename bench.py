@@ -231,13 +231,21 @@ def sharded_record(args, world, rank, dev, steps=60, warmup=5):
                     ('prepared_multicast_expand', dict(gather=True, expand=True, wire='multicast')),
                     ('prepared_multicast_compact', dict(gather=True, expand=False, wire='multicast')),
                     ('prepared_local', dict(gather=False, expand=False))):
+    plan, why = None, ''
     try:
       plan = parallel.ShardedReprojection(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, pieces=args.pieces, **kw)
     except Exception as e:  # pylint: disable=broad-except
       if kw.get('wire') != 'multicast':
         raise
-      rec[label] = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
-      continue
+      why = f'{type(e).__name__}: {e}'[:200]
+    if kw.get('wire') == 'multicast':  # all ranks take the multicast path or none does
+      okf = torch.tensor([0 if plan is None else 1], device=dev)
+      if world > 1:
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+      if okf.item() == 0:
+        rec[label] = {'unavailable': why or 'another rank could not set up the multicast mapping'}
+        del plan
+        continue
     for _ in range(warmup):
       out = plan.run()
     torch.cuda.synchronize()
@@ -430,6 +438,8 @@ def e2e_measure(guidance, torch, dist, host_inp, args, local_rank, world, compac
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   h2d = sum(host_inp[k].numel() * host_inp[k].element_size() for k in host_inp)
   d2h = sum(v.numel() * v.element_size() for v in out.values())
+  if pipe is not None:
+    pipe.close()
   return float(t.item()), h2d, d2h, out
 
 

@@ -333,6 +333,13 @@ class HostReprojector(object):
       res.append(self._finish())
     return res
 
+  def close(self):
+    """Completes what is in flight and releases the workspaces (device staging buffers, streams)."""
+    self.flush()
+    for ws in self._ws:
+      ws.close()
+    self._ws = []
+
 
 class FrameRing(object):
   """The memory of a trajectory as the frames that were observed: rgb (N,cap,H,W,3) uint8 / int32,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SE3DS_GEOM_VERSION 200 /* major*100 + minor; 200: round-2 ABI (apply_bin flags, ring / compact / expand / quantize entry points) */
+#define SE3DS_GEOM_VERSION 201 /* major*100 + minor; 200: round-2 ABI (apply_bin flags, ring / compact / expand / quantize entry points); 201: + SE3DS_FLAG_HOST_ASYNC, se3ds_ws_host_wait */
 
 typedef struct se3ds_ws se3ds_ws;
 

@@ -44,7 +44,7 @@ def test_header_is_plain_c():
 
 def test_version_and_status_strings():
   lib = _lib.load()
-  assert lib.se3ds_version() == 200
+  assert lib.se3ds_version() == 201
   assert lib.se3ds_status_string(0) == b'ok'
   assert b'shape' in lib.se3ds_status_string(_lib.ERR_BAD_SHAPE)
 

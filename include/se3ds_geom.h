@@ -242,8 +242,8 @@ int se3ds_apply_bin(const float* bin, float depth_scale, unsigned flags, float* 
                     float* proj_mask, int32_t* winner, void* stream);
 
 /* Same as se3ds_reproject with HOST buffers (pinned memory recommended): copies the inputs to the
- * device, runs the fused path and copies the guidance tensors back, pipelined over batch items on
- * the workspace's own streams.  Blocks until the outputs are complete, unless SE3DS_FLAG_HOST_ASYNC is
+ * device, runs the fused path and copies the guidance tensors back, pipelined over groups of batch items
+ * (four stages) on the workspace's own streams.  Blocks until the outputs are complete, unless SE3DS_FLAG_HOST_ASYNC is
  * given: the call then returns once everything is enqueued, the host buffers (inputs and outputs) belong
  * to the library until se3ds_ws_host_wait(ws) returns, and a further host call on the same workspace
  * waits for the pending one first. */

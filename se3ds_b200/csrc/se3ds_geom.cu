@@ -140,7 +140,7 @@ struct ChunkPlan {
   int lanes, items_per_chunk, poses_per_chunk;
   long long chunk_jobs, nchunks;
 };
-void plan_chunks(size_t budget_bytes, int lanes, long long min_lane_points, int min_lane_chunks, bool per_item, int n,
+void plan_chunks(size_t budget_bytes, int lanes, long long min_lane_points, int min_lane_chunks, int host_group, int n,
                  int s, int p, int h, int w, ChunkPlan* out) {
   const long long hw = (long long)h * w, J = (long long)n * p;
   const size_t job_bytes = (size_t)hw * (16 + 8 * (size_t)s);
@@ -151,7 +151,7 @@ void plan_chunks(size_t budget_bytes, int lanes, long long min_lane_points, int 
     long long jpc = std::max<long long>(1, (long long)(budget_bytes / lanes / job_bytes));
     jpc = std::min(jpc, (J + lanes - 1) / lanes);
     jpc = std::min<long long>(jpc, std::max(1, 65535 / s));
-    if (per_item) jpc = std::min<long long>(jpc, p);  // one batch item per chunk: finest copy/compute overlap
+    if (host_group) jpc = std::min<long long>(jpc, (long long)p * host_group);  // host call: a chunk is one pipeline stage of the copies
     if (jpc >= p) {
       const long long nchunks = (n + (jpc / p) - 1) / (jpc / p);
       items_per_chunk = (int)((n + nchunks - 1) / nchunks);
@@ -298,6 +298,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
 // K2 grid: a block walks several rows (kernels.cuh); rows_per_block is sized so that the grid is about
 // one resident wave of kK2BlocksPerSM blocks per SM, capped so that short panos still spread over the SMs.
 constexpr int kK2BlocksPerSM = 8;
+constexpr int kHostStages = 4;  // pipeline stages of a blocking se3ds_reproject_host call (measured, see reproject_host)
 int k2_row_groups(const se3ds_ws* ws, int gx, int h, int job_frames) {
   const long long row_blocks = (long long)gx * h * job_frames;
   const long long resident = (long long)ws->sm_count * kK2BlocksPerSM;
@@ -453,7 +454,7 @@ int se3ds_plan_chunks(size_t l2_chunk_bytes, int lanes, long long min_points_per
   if (lanes < 1 || lanes > se3ds_ws::kMaxLanes) return fail(SE3DS_ERR_BAD_ARG, "lanes must be in [1, %d]", se3ds_ws::kMaxLanes);
   ChunkPlan c;
   plan_chunks(l2_chunk_bytes ? l2_chunk_bytes : kDefaultChunkBytes, lanes, min_points_per_lane ? min_points_per_lane : (1ll << 20),
-              min_chunks_per_lane ? min_chunks_per_lane : 2, false, n, s, p, h, w, &c);
+              min_chunks_per_lane ? min_chunks_per_lane : 2, 0, n, s, p, h, w, &c);
   plan[0] = c.lanes; plan[1] = c.items_per_chunk; plan[2] = c.poses_per_chunk; plan[3] = c.chunk_jobs; plan[4] = c.nchunks;
   return SE3DS_OK;
 }
@@ -688,6 +689,7 @@ namespace {
 // Host pipeline of se3ds_reproject_host: chunk c (one batch item) waits for its inputs on the
 // compute stream and hands its outputs to the device->host stream as soon as its resolve is done.
 struct HostPipe {
+  int group;  // batch items per pipeline stage (upload -> kernels -> download)
   cudaStream_t d2h;
   cudaEvent_t* in_ready;   // [n]
   cudaEvent_t* out_ready;  // [n]
@@ -726,7 +728,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   const long long J = (long long)n * p;
   ChunkPlan plan;
   plan_chunks(std::min(ws->chunk_bytes, ws->max_bytes), (pipe || ws->profile == 1) ? 1 : ws->lanes, ws->min_lane_points,
-              ws->min_lane_chunks, pipe != nullptr, n, s, p, h, w, &plan);
+              ws->min_lane_chunks, pipe ? pipe->group : 0, n, s, p, h, w, &plan);
   const int lanes = plan.lanes, items_per_chunk = plan.items_per_chunk, PC = plan.poses_per_chunk;
   const long long chunk_jobs = plan.chunk_jobs, nchunks_total = plan.nchunks;
   const bool per_job = flags & SE3DS_FLAG_BIN_PER_JOB;
@@ -790,7 +792,7 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
   long long chunk_no = 0;
   for (int n0 = 0; n0 < n; n0 += items_per_chunk) {
     const int nitems = std::min(items_per_chunk, n - n0);
-    if (pipe) CU(cudaStreamWaitEvent(st, pipe->in_ready[n0], 0));
+    if (pipe) CU(cudaStreamWaitEvent(st, pipe->in_ready[n0], 0));  // recorded after the upload of items n0 .. n0 + nitems - 1
     for (int p0 = 0; p0 < p; p0 += PC, ++chunk_no) {
       const int lane = (int)(chunk_no % lanes);
       q.n0 = n0; q.p0 = p0; q.PC = std::min(PC, p - p0);
@@ -803,10 +805,10 @@ int reproject_core(se3ds_ws* ws, const void* rgb, int rgb_dtype, const float* de
                                            : run_chunk<int>(ws, q, nitems, vec, key64, lane_st[lane]);
       if (rc) { join(); return rc; }
     }
-    if (pipe) {  // items_per_chunk == 1 here: ship item n0's guidance tensors
+    if (pipe) {  // ship the guidance tensors of this stage's items
       CU(cudaEventRecord(pipe->out_ready[n0], st));
       CU(cudaStreamWaitEvent(pipe->d2h, pipe->out_ready[n0], 0));
-      const size_t o = (size_t)n0 * p * hw, cnt = (size_t)p * hw;
+      const size_t o = (size_t)n0 * p * hw, cnt = (size_t)nitems * p * hw;
       if (compact) {
         CU(cudaMemcpyAsync((uint8_t*)pipe->image_host + o * 3, (const uint8_t*)proj_image + o * 3, cnt * 3, cudaMemcpyDeviceToHost, pipe->d2h));
       } else {
@@ -939,17 +941,24 @@ int se3ds_reproject_host(se3ds_ws* ws, const void* rgb_host, int rgb_dtype, cons
     if (winner_out_host) CU(cudaMemcpyAsync(winner_out_host, ws->s_win.p, npix * 4, cudaMemcpyDeviceToHost, down));
     return SE3DS_OK;
   }
-  // Blocking call: item by item (an event per item lets item i compute while item i+1 is still on the wire
-  // and item i-1 is already travelling back)
+  // Blocking call: a pipeline over groups of batch items -- group g computes while group g+1 is still on the wire
+  // and group g-1 is already travelling back.  Few stages: every DMA transfer costs ~5 us while both directions
+  // of the link are busy, and the uploads of later groups share the link with the downloads of earlier ones.
+  // Measured (512x1024 panos, compact / float32 outputs, ms per call): batch 8: 1 stage 1.16 / 2.13, 2: 0.98 / 1.90,
+  // 4: 0.95 / 1.83, 8: 1.02 / 1.87; batch 16: 1: 1.84 / 3.70, 4: 1.70 / 3.47, 8: 1.74 / 3.43, 16: 2.03 / 3.61.
+  const int group = (n + kHostStages - 1) / kHostStages;
+  ChunkPlan hplan;  // the chunks reproject_core will form: one upload event per chunk of items
+  plan_chunks(std::min(ws->chunk_bytes, ws->max_bytes), 1, ws->min_lane_points, ws->min_lane_chunks, group, n, s, p, h, w, &hplan);
   const size_t item_pts = (size_t)s * hw;
-  for (int i = 0; i < n; ++i) {
-    CU(cudaMemcpyAsync((char*)ws->s_rgb.p + i * item_pts * px, (const char*)rgb_host + i * item_pts * px, item_pts * px,
+  for (int i = 0; i < n; i += hplan.items_per_chunk) {
+    const size_t cnt = (size_t)std::min(hplan.items_per_chunk, n - i) * item_pts;
+    CU(cudaMemcpyAsync((char*)ws->s_rgb.p + i * item_pts * px, (const char*)rgb_host + i * item_pts * px, cnt * px,
                        cudaMemcpyHostToDevice, up));
-    CU(cudaMemcpyAsync((float*)ws->s_depth.p + i * item_pts, depth_host + i * item_pts, item_pts * 4,
+    CU(cudaMemcpyAsync((float*)ws->s_depth.p + i * item_pts, depth_host + i * item_pts, cnt * 4,
                        cudaMemcpyHostToDevice, up));
     CU(cudaEventRecord(ws->pipe_ev[i], up));
   }
-  HostPipe pipe{ws->d2h_stream, ws->pipe_ev.data(), ws->pipe_ev.data() + n, proj_image_host, proj_depth_host,
+  HostPipe pipe{group, ws->d2h_stream, ws->pipe_ev.data(), ws->pipe_ev.data() + n, proj_image_host, proj_depth_host,
                 proj_mask_host, winner_out_host};
   const int rc = reproject_core(ws, ws->s_rgb.p, rgb_dtype, (const float*)ws->s_depth.p, (const float*)ws->s_src.p,
                                 (const float*)ws->s_tgt.p, nullptr, n, s, s, p, h, w, depth_scale, mask_proportion, mask_frames,

@@ -410,9 +410,12 @@ def test_prepared_plans_back_to_back(mods):
   ws.close()
 
 
-def test_reproject_host_equals_device(mods):
+@pytest.mark.parametrize('n,s,p,h', [(2, 2, 1, 64), (10, 1, 2, 32), (5, 2, 1, 16)])
+def test_reproject_host_equals_device(mods, n, s, p, h):
+  """The blocking host call pipelines groups of batch items (four stages): 2 items -> one per stage, 10 items ->
+  groups of 3, 3, 3, 1 with the owner pixel patched after the last group; same bits as the device call."""
   g = mods['g']
-  inp = mods['synth'].make_inputs(2, 2, 1, 64, seed=12)
+  inp = mods['synth'].make_inputs(n, s, p, h, seed=12 + n, dist='rand', sweep=p > 1)
   t = _cuda(inp)
   dev = g.reproject(t['rgb'], t['depth'], t['src_pos'], t['tgt_pos'], mask_frames=1, return_winner=True)
   host = g.reproject_host(*(torch.as_tensor(inp[k]) for k in ('rgb', 'depth', 'src_pos', 'tgt_pos')),
@@ -420,6 +423,10 @@ def test_reproject_host_equals_device(mods):
   for k in ('proj_image', 'proj_depth', 'proj_mask', 'winner'):
     assert not host[k].is_cuda
     assert torch.equal(host[k], dev[k].cpu()), k
+  small = g.reproject_host(*(torch.as_tensor(inp[k]) for k in ('rgb', 'depth', 'src_pos', 'tgt_pos')), mask_frames=1, compact=True)
+  back = g.expand_guidance({k: v.cuda() for k, v in small.items()})
+  for k in ('proj_image', 'proj_depth', 'proj_mask'):
+    assert torch.equal(back[k], dev[k]), k
 
 
 @pytest.mark.parametrize('compact,depth', [(False, 2), (True, 2), (True, 3), (False, 1)])

@@ -86,3 +86,58 @@ def test_numa_helper_parses_cpulists_and_degrades_gracefully():
   assert hostmem._parse_cpulist('0-3,8,10-11') == {0, 1, 2, 3, 8, 10, 11}
   assert hostmem._parse_cpulist('') == set()
   assert hostmem._read('/nonexistent/se3ds') is None
+
+
+def test_host_reprojector_rotates_workspaces_and_output_sets(monkeypatch):
+  """guidance.HostReprojector without a device: the call order, which workspace / output set each batch gets,
+  when the oldest call is waited for, and that a returned result is not the set the next submit writes."""
+  from se3ds_b200 import guidance, _lib
+  log = []
+
+  class FakeWs:
+    count = 0
+
+    def __init__(self, device=0):
+      FakeWs.count += 1
+      self.name = 'ws%d' % FakeWs.count
+      self.closed = False
+
+    def host_wait(self):
+      log.append(('wait', self.name))
+
+    def close(self):
+      self.closed = True
+
+  def fake_reproject_host(rgb, depth, src_pos, tgt_pos, out=None, workspace=None, wait=True, **kw):
+    assert wait is False and kw == {'device': 0, 'mask_frames': 1}
+    out['batch'] = rgb
+    log.append(('submit', workspace.name, id(out), rgb))
+    return out
+
+  monkeypatch.setattr(_lib, 'Workspace', FakeWs)
+  monkeypatch.setattr(guidance, 'reproject_host', fake_reproject_host)
+  pipe = guidance.HostReprojector(device=0, depth=2, mask_frames=1)
+  got = []
+  for b in range(5):
+    done = pipe.submit(b, None, None, None)
+    if b < 2:
+      assert done is None  # the pipeline fills
+    else:
+      assert done['batch'] == b - 2  # oldest first
+      newest = [e for e in log if e[0] == 'submit'][-1]
+      assert newest[2] != id(done)  # the result just returned is not the set being written now
+      got.append(done['batch'])
+  got += [d['batch'] for d in pipe.flush()]
+  assert got == [0, 1, 2, 3, 4]
+  submits = [e for e in log if e[0] == 'submit']
+  assert [e[1] for e in submits] == ['ws1', 'ws2', 'ws1', 'ws2', 'ws1']
+  assert len({e[2] for e in submits}) == 3  # depth + 1 output sets
+  # a workspace is waited for exactly before it is reused, and in submission order at the end
+  assert [e[1] for e in log if e[0] == 'wait'] == ['ws1', 'ws2', 'ws1', 'ws2', 'ws1']
+  assert log.index(('wait', 'ws1')) < log.index(submits[2])
+  workspaces = list(pipe._ws)
+  pipe.close()
+  assert all(w.closed for w in workspaces)
+  import pytest
+  with pytest.raises(ValueError):
+    guidance.HostReprojector(depth=0)

@@ -627,18 +627,25 @@ def main():
                                         'se3ds_expand_guidance restores the float32 tensors bit for bit'}},
         'gpu_launches': m['launches_per_step'] * args.steps,
         'clocks': m['clocks'],
-        'roofline': {'bound': 'hbm', 'kernel': names[dom], 'achieved': kalg[dom] / (kms[dom] * 1e-3) / 1e9, 'peak': peak,
-                     'unit': 'GB/s', 'frac': kalg[dom] / (kms[dom] * 1e-3) / 1e9 / peak, 'peak_kind': peak_kind,
-                     'traffic': (traffic or {}).get(names[dom]), 'ms': kms[dom],
-                     'step_frac': (src_bytes + out_bytes) / (ms_step * 1e-3) / 1e9 / peak,
-                     'frac_r1_accounting': ([src_bytes, 0, out_bytes][dom] / (kms[dom] * 1e-3) / 1e9 / peak),
-                     'how': 'share of the pipelined step: last end-of-kernel %globaltimer stamp minus that of the kernel before it '
-                            '(se3ds_ws_profile mode 2); the shares add up to the step.  Algorithmic bytes per kernel: depth (4 B/pt) to '
-                            'splat_depth, colours (3 B/pt) to splat_feat, guidance (20 B/px) to resolve; step_frac / roofline_step hold the whole pass '
-                            '(SURVEY 8d: 7 B per source point + 20 B per target pixel over the timed step); frac_r1_accounting credits all source '
-                            'bytes to splat_depth and none to splat_feat, as the round-1 line did',
-                     'note': ('splat_depth (instruction issue + latency) and splat_feat (latency of a dependent gather + reduction per point) '
-                              'are not HBM-bound (ncu: profiles/r02_*); resolve is the HBM-bound kernel, see roofline_hbm_kernel') if dom != 2 else ''},
+        # achieved = B_alg / t with B_alg = 7 B per source point + 20 B per target pixel of the pass and t the
+        # time of the pass.  The pass is three kernels of nearly equal length chained by programmatic dependent launch,
+        # so the object describes the pass; the kernel that takes the largest share is in dominant_kernel.
+        'roofline': {'bound': 'hbm', 'kernel': 'fused pass: splat_depth_kernel -> splat_feat_kernel -> resolve_kernel (programmatic dependent launch)',
+                     'achieved': (src_bytes + out_bytes) / (ms_step * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                     'frac': (src_bytes + out_bytes) / (ms_step * 1e-3) / 1e9 / peak, 'peak_kind': peak_kind,
+                     'traffic': (sum(traffic[k] for k in names) if traffic and all(k in traffic for k in names) else None),
+                     'ms': ms_step, 'alg_bytes': src_bytes + out_bytes,
+                     'dominant_kernel': {'name': names[dom], 'ms': kms[dom], 'alg_bytes': kalg[dom],
+                                         'achieved': kalg[dom] / (kms[dom] * 1e-3) / 1e9, 'frac': kalg[dom] / (kms[dom] * 1e-3) / 1e9 / peak,
+                                         'traffic': (traffic or {}).get(names[dom])},
+                     'per_kernel_frac': {names[i]: kalg[i] / (kms[i] * 1e-3) / 1e9 / peak for i in range(3)},
+                     'how': 'pass: algorithmic bytes of the step / CUDA-event time of the step (the timed region).  Kernels: share of the '
+                            'pipelined step = last end-of-kernel %globaltimer stamp minus that of the kernel before it (se3ds_ws_profile '
+                            'mode 2; the shares add up to the step), algorithmic bytes credited to the kernel that moves them: depth (4 B/pt) '
+                            'to splat_depth, colours (3 B/pt) to splat_feat, guidance (20 B/px) to resolve.  traffic: cold-cache ncu DRAM bytes '
+                            'of the three launches (profiles/traffic.json); warm: profiles/r02_ncu_warm_summary.txt',
+                     'note': 'splat_depth (instruction issue + latency) and splat_feat (latency of a dependent gather + reduction per point) '
+                             'are not HBM-bound (ncu: profiles/r02_*); resolve is the HBM-bound kernel, see roofline_hbm_kernel'},
         'roofline_hbm_kernel': {'bound': 'hbm', 'kernel': names[2], 'achieved': kalg[2] / (kms[2] * 1e-3) / 1e9,
                                 'peak': peak, 'unit': 'GB/s', 'frac': kalg[2] / (kms[2] * 1e-3) / 1e9 / peak,
                                 'traffic': (traffic or {}).get(names[2]), 'ms': kms[2]},

@@ -151,6 +151,7 @@ void plan_chunks(size_t budget_bytes, int lanes, long long min_lane_points, int 
     long long jpc = std::max<long long>(1, (long long)(budget_bytes / lanes / job_bytes));
     jpc = std::min(jpc, (J + lanes - 1) / lanes);
     jpc = std::min<long long>(jpc, std::max(1, 65535 / s));
+    jpc = std::min<long long>(jpc, std::max<long long>(1, ((1ll << 32) - 1) / ((long long)s * hw)));  // 32-bit element offsets in the kernels
     if (host_group) jpc = std::min<long long>(jpc, (long long)p * host_group);  // host call: a chunk is one pipeline stage of the copies
     if (jpc >= p) {
       const long long nchunks = (n + (jpc / p) - 1) / (jpc / p);
@@ -334,13 +335,19 @@ int run_chunk_t(se3ds_ws* ws, const FusedParams& q, int nitems, cudaStream_t st)
   const int proj = ws->proj_mode;
   const bool pdl = ws->pdl && ws->profile != 1;
   constexpr bool VEC = PPT == 4;
-#define LAUNCH_K2(F, P)                                                                                         \
-  do {                                                                                                         \
-    if (q.tgt_rot) CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, true>, grid2, block, st, pdl, qs)); \
-    else CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, false>, grid2, block, st, pdl, qs));          \
+  // PLAIN: see splat_depth_kernel (no compaction, unproject_void == -1, every thread of the grid inside its row)
+  const bool plain = fast && VEC && !(q.flags & SE3DS_FLAG_FILTER_VOID) && q.uv == -1 && q.W % (kThreads * 4) == 0;
+#define LAUNCH_K2(F, P, PL)                                                                                        \
+  do {                                                                                                            \
+    if (q.tgt_rot) CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, true, PL>, grid2, block, st, pdl, qs)); \
+    else CU(launch_pdl(splat_depth_kernel<RGB_T, VEC, F, P, KEY64, false, PL>, grid2, block, st, pdl, qs));          \
   } while (0)
-  if (fast) { if (proj == 0) LAUNCH_K2(true, 0); else if (proj == 1) LAUNCH_K2(true, 1); else LAUNCH_K2(true, 2); }
-  else { if (proj == 0) LAUNCH_K2(false, 0); else if (proj == 1) LAUNCH_K2(false, 1); else LAUNCH_K2(false, 2); }
+  if constexpr (VEC && std::is_same<RGB_T, uint8_t>::value) {
+    if (plain) { if (proj == 0) LAUNCH_K2(true, 0, true); else if (proj == 1) LAUNCH_K2(true, 1, true); else LAUNCH_K2(true, 2, true); }
+  }
+  if (plain) {}
+  else if (fast) { if (proj == 0) LAUNCH_K2(true, 0, false); else if (proj == 1) LAUNCH_K2(true, 1, false); else LAUNCH_K2(true, 2, false); }
+  else { if (proj == 0) LAUNCH_K2(false, 0, false); else if (proj == 1) LAUNCH_K2(false, 1, false); else LAUNCH_K2(false, 2, false); }
 #undef LAUNCH_K2
   if (ev) CU(cudaEventRecord(ev[1], st));
   CU(launch_pdl(splat_feat_kernel<RGB_T, PPT, KEY64>, grid, block, st, pdl, qs));

@@ -66,6 +66,7 @@ class ClockSampler(threading.Thread):
     super().__init__(daemon=True)
     self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
     self._stop_evt = threading.Event()
+    self._armed = threading.Event()  # set right before the timed region: the NVML set-up and the thread start happen earlier
     try:
       import pynvml
       pynvml.nvmlInit()
@@ -88,6 +89,9 @@ class ClockSampler(threading.Thread):
     }
     get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
     while not self._stop_evt.is_set():
+      if not self._armed.is_set():
+        time.sleep(0.0002)
+        continue
       try:
         self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
         r = get_reasons(self.h)
@@ -97,6 +101,9 @@ class ClockSampler(threading.Thread):
       except Exception:  # pylint: disable=broad-except
         pass
       time.sleep(0.001)
+
+  def arm(self):
+    self._armed.set()
 
   def stop(self):
     self._stop_evt.set()
@@ -360,13 +367,22 @@ def gpu_measure(guidance, synth, lib, torch, dist, cfg, args, dev, local_rank, w
     plans[0].run()
     stream.synchronize()
     launches_per_step = ws.profile_read()[1] - l0
-    for i in range(warmup):
-      step(i)
-    barrier()
-    sampler = ClockSampler(local_rank) if clocks else None
+    # the sampler's NVML set-up (milliseconds) and its thread start come BEFORE the warm-up, so that nothing but the
+    # contract's barrier + synchronize sits between the last warm-up step and the first timed one (a GPU left idle for
+    # milliseconds starts the timed burst from a lower power state: +5 % on a 20-step run)
+    late = bool(os.environ.get('SE3DS_BENCH_LATE_SAMPLER'))
+    sampler = ClockSampler(local_rank) if clocks and not late else None
     if sampler:
       sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(warmup):
+      step(i)
+    barrier()
+    if clocks and late:
+      sampler = ClockSampler(local_rank)
+      sampler.start()
+    if sampler:
+      sampler.arm()
     e0.record(stream)
     for i in range(steps):
       step(i)
